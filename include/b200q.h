@@ -1,0 +1,131 @@
+/*
+ * b200q.h -- C-ABI of the B200-native microscaled-FP4 hot path (libb200q.so).
+ *
+ * This is the drop-in boundary: plain pointers, sizes and a CUDA stream; no torch
+ * types.  Each entry point names the reference interface it replaces (paths are
+ * relative to the IST-DASLab/qutlass checkout).  The reference's own precedent for a
+ * raw C boundary is qutlass/csrc/include/backward_host.h:4-46 (device pointers, ints,
+ * cudaStream_t, int return).
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers unless the name ends in _host.
+ *   - Nothing here allocates or frees device memory and nothing synchronises the
+ *     host: every call only enqueues work on `stream` (CUDA-graph capturable).
+ *   - Return value: 0 on success, negative B200Q_E* on failure; b200q_last_error()
+ *     returns a thread-local human-readable message for the last failure.
+ *   - e2m1: two codes per byte, element 2i in the low nibble (tests/mxfp4_test.py:80).
+ *   - "blocked" scale layout = cuBLAS block-scaled layout, 128x4 tiles of 512 B,
+ *     K-blocks fastest (qutlass/utils.py:160-193).
+ */
+#ifndef B200Q_H_
+#define B200Q_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* opaque here so the header does not need cuda_runtime.h; it IS a cudaStream_t */
+typedef struct CUstream_st* b200q_stream_t;
+
+#define B200Q_OK 0
+#define B200Q_EINVAL (-1)   /* bad argument (shape / alignment / enum)        */
+#define B200Q_ECUDA (-2)    /* a CUDA runtime / driver call failed             */
+#define B200Q_EUNSUPPORTED (-3) /* device is not sm_100                        */
+
+#define B200Q_METHOD_QUEST 0   /* Quartet / "quest": std-based scale           */
+#define B200Q_METHOD_ABSMAX 1  /* abs-max scale                                */
+
+#define B200Q_KIND_MXF4 0      /* e2m1 x e2m1, ue8m0 scales, group 32          */
+#define B200Q_KIND_NVF4 1      /* e2m1 x e2m1, ue4m3 scales, group 16          */
+
+/* ABI version of this header (bumped on incompatible change). */
+int b200q_abi_version(void);
+
+/* Thread-local message for the most recent failure on this thread ("" if none). */
+const char* b200q_last_error(void);
+
+/*
+ * Fused rotate + MXFP4 quantise.
+ * Replaces: fusedQuantizeMx{Quest,AbsMax}[Had64|Had128]_host
+ *           (qutlass/csrc/include/fused_quantize_host.h:22-70, fused_quantize_mx.cu:107-207),
+ *           fusedQuantizeMxAbsMax_host_sm100 (fused_quantize_mx_sm100.cu:192-207),
+ *           fusedQuantizeMxQuestWithMask_host (fused_quantize_mx_mask.cu:107-121)
+ *           and the separate to_blocked launch (qutlass/utils.py:16-133).
+ *
+ *   x_bf16      [numel] bf16, contiguous; rotated in consecutive groups of `had`
+ *   rot_bf16    [had, had] bf16 row-major [k, n]; xh = x_group @ rot
+ *   q_e2m1      [numel/2] bytes out
+ *   sf_rowmajor ue8m0 bytes out; scale of 32-group g stored at byte g (flat, as the
+ *               reference kernels do -- row-major [rows, row_len/32] when row_len%128==0);
+ *               may be NULL if only the blocked layout is wanted
+ *   sf_blocked  NULL, or the [pad128(rows) * pad4(row_len/32)] blocked buffer; written
+ *               completely (pad rows/cols are zero-filled) so to_blocked is a no-op
+ *   clip_mask   NULL, or [numel/32] uint32 (bit i = |xh_i/s| < 6), quest only
+ *   numel       total elements; row_len = size of the last dim (numel % row_len == 0)
+ *   had         32, 64 or 128 (numel % had == 0);  method = B200Q_METHOD_*
+ */
+int b200q_quantize_mx(const void* x_bf16, const void* rot_bf16, void* q_e2m1,
+                      void* sf_rowmajor, void* sf_blocked, void* clip_mask,
+                      int64_t numel, int64_t row_len, int had, int method,
+                      b200q_stream_t stream);
+
+/*
+ * Fused rotate + NVFP4 quantise (group 16, e4m3 scales, fp32 global scale on device).
+ * Replaces: fusedQuantizeNv{Quest,AbsMax}[Had32|Had64|Had128]_host
+ *           (fused_quantize_host.h:72-116, fused_quantize_nv.cu:109-252) and
+ *           fusedQuantizeNvAbsMax_host_sm100 (fused_quantize_nv_sm100.cu:192-207).
+ *   had in {16, 32, 64, 128}; global_scale_dev points at ONE float on the device.
+ */
+int b200q_quantize_nv(const void* x_bf16, const void* rot_bf16, void* q_e2m1,
+                      void* sf_rowmajor, void* sf_blocked, const float* global_scale_dev,
+                      int64_t numel, int64_t row_len, int had, int method,
+                      b200q_stream_t stream);
+
+/*
+ * Row-major scales -> blocked layout (standalone; only needed for scales that did
+ * not come from b200q_quantize_*).  Replaces triton_scale_swizzle (qutlass/utils.py:16-133).
+ *   sf_rowmajor [rows, cols] bytes (row stride = cols); sf_blocked [pad128(rows)*pad4(cols)].
+ */
+int b200q_swizzle_sf(const void* sf_rowmajor, void* sf_blocked, int64_t rows, int64_t cols,
+                     b200q_stream_t stream);
+
+/*
+ * Block-scaled FP4 GEMM:  D[M,N] = bf16( alpha * (A .* SFA) @ (B .* SFB)^T ), fp32 accumulate.
+ * Replaces: matmul_host_mxf4_bf16_tn / matmul_host_nvf4_bf16_tn
+ *           (qutlass/csrc/include/gemm.h:21-35, gemm.cu:174-326).
+ *   A [M, K/2], B [N, K/2] packed e2m1 (K-major, "tn"); SFA/SFB blocked scale buffers
+ *   (ue8m0 group 32 for MXF4, ue4m3 group 16 for NVF4) of pad128(M|N) x pad4(K/group);
+ *   alpha_dev: one fp32 on the device; D [M, N] bf16 row-major.
+ *   K % 32 == 0 (MX) / K % 32 == 0 (NV, 16-byte TMA row pitch), all pointers 16-byte aligned.
+ */
+int b200q_gemm_fp4(const void* A, const void* B, const void* SFA, const void* SFB,
+                   const float* alpha_dev, void* D_bf16, int M, int N, int K, int kind,
+                   b200q_stream_t stream);
+
+/*
+ * Same, with an explicit kernel configuration (tuning / tests):
+ *   cta_group 1|2, block_n in {64,128,256} (0 = heuristic for both).
+ */
+int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA, const void* SFB,
+                       const float* alpha_dev, void* D_bf16, int M, int N, int K, int kind,
+                       int cta_group, int block_n, b200q_stream_t stream);
+
+/*
+ * Host-buffer convenience for the whole path (what bench.py's e2e leg times):
+ *   x_host [M,K] bf16 (pinned) -> H2D -> rotate+quantise (abs_max, MX or NV) ->
+ *   GEMM against pre-quantised weights (device) -> D2H into d_host [M,N] bf16.
+ * `ws` is a caller-owned device workspace of b200q_linear_workspace_bytes(M,N,K,kind) bytes.
+ * Enqueues on `stream`; the caller synchronises.
+ */
+int64_t b200q_linear_workspace_bytes(int M, int N, int K, int kind);
+int b200q_linear_fp4_host(const void* x_host, const void* rot_bf16, const void* Wq, const void* Wsf_blocked,
+                          const float* alpha_dev, const float* global_scale_dev,
+                          void* d_host, void* ws, int M, int N, int K, int had, int kind,
+                          b200q_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H_ */

@@ -1,0 +1,243 @@
+"""qutlass_b200 -- B200-native (sm_100a) microscaled-FP4 hot path behind the QuTLASS Python surface.
+
+Drop-in for the hot-path subset of the reference's ``qutlass`` package
+(/root/reference/qutlass/__init__.py:34-203):
+
+    fusedQuantizeMx, fusedQuantizeNv, matmul_mxf4_bf16_tn, matmul_nvf4_bf16_tn, utils.to_blocked
+
+and the same op names/schemas under ``torch.ops._qutlass_C`` (bindings.cpp:498-507).  Host side =
+this module (argument checks, output allocation, stream selection) calling hand-written sm_100a
+CUDA in ``lib/libb200q.so`` through the thin C-ABI of ``include/b200q.h``.  No CUTLASS, FlashInfer,
+Triton, multi-backend dispatch or CPU fallback: without the built library or without a CUDA
+device every compute entry point raises.
+"""
+from __future__ import annotations
+
+from typing import Literal
+
+import torch
+
+from . import _lib
+from .utils import (get_padded_shape_mx, get_padded_shape_nv, pad_to_block, to_blocked,  # noqa: F401
+                    _attach_blocked)
+
+__all__ = [
+    "matmul_mxf4_bf16_tn", "matmul_nvf4_bf16_tn", "fusedQuantizeMx", "fusedQuantizeNv",
+    "matmul_ada_mxf4_bf16_tn", "matmul_mxf8_bf16_tn", "matmul_mxf8_bf16_nn", "backward_t_bf16",
+    "backward_qt_bf16", "backward_bf16_square_double_mxfp8", "mxfp4_transpose_mxfp8",
+]
+
+METHOD_QUEST, METHOD_ABSMAX = 0, 1
+KIND_MXF4, KIND_NVF4 = 0, 1
+
+
+def _check(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _check_cuda_same(name: str, tensors) -> None:
+    dev = None
+    for label, t in tensors:
+        _check(t.is_cuda, f"{name}: expected all tensors to be on CUDA, but {label} is on {t.device}")
+        if dev is None:
+            dev = t.device
+        _check(t.device == dev, f"{name}: expected all tensors on the same GPU, but {label} is on {t.device} (vs {dev})")
+
+
+def _check_contig(name: str, tensors) -> None:
+    for label, t in tensors:
+        _check(t.is_contiguous(), f"{name}: expected {label} to be contiguous")
+
+
+# --------------------------------------------------------------------------------------- GEMM
+def _matmul_fp4(name: str, a, b, a_sf, b_sf, alpha, kind: int, sf_dtype, min_k_bytes: int, cfg=(0, 0)):
+    """reference checks: qutlass/csrc/bindings.cpp:32-102"""
+    _check_contig(name, [("A", a), ("B", b), ("A_sf", a_sf), ("B_sf", b_sf)])
+    _check_cuda_same(name, [("A", a), ("B", b), ("A_sf", a_sf), ("B_sf", b_sf), ("alpha", alpha)])
+    _check(a.dtype == torch.uint8, "A must be uint8")
+    _check(b.dtype == torch.uint8, "B must be uint8")
+    sf_name = "float8_e8m0fnu" if kind == KIND_MXF4 else "float8_e4m3fn"
+    _check(a_sf.dtype == sf_dtype, f"A_sf must be {sf_name}")
+    _check(b_sf.dtype == sf_dtype, f"B_sf must be {sf_name}")
+    _check(a.dim() == 2 and b.dim() == 2, "A and B must be 2D")
+    _check(a.size(1) == b.size(1), "Inner dimensions must match for A @ B.T")
+    _check(a.size(1) >= min_k_bytes, f"A K-dim must be >= {min_k_bytes}")
+    _check(b.size(1) >= min_k_bytes, f"B K-dim must be >= {min_k_bytes}")
+    _check(alpha.dtype == torch.float32 and alpha.numel() >= 1, "alpha must be a float32 tensor with one element")
+    m, n, k = a.size(0), b.size(0), a.size(1) * 2
+    group = 32 if kind == KIND_MXF4 else 16
+    need_a = ((m + 127) // 128) * 128 * (((k // group) + 3) // 4) * 4
+    need_b = ((n + 127) // 128) * 128 * (((k // group) + 3) // 4) * 4
+    _check(a_sf.numel() >= need_a, f"A_sf has {a_sf.numel()} scales, the blocked layout needs {need_a}")
+    _check(b_sf.numel() >= need_b, f"B_sf has {b_sf.numel()} scales, the blocked layout needs {need_b}")
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().b200q_gemm_fp4_cfg(
+            a.data_ptr(), b.data_ptr(), a_sf.data_ptr(), b_sf.data_ptr(), alpha.data_ptr(), out.data_ptr(),
+            m, n, k, kind, cfg[0], cfg[1], _stream(a)))
+    return out
+
+
+def _backend_gate(backend: str) -> None:
+    if backend == "cutlass":
+        return  # the name is kept for drop-in compatibility; the kernel underneath is our own tcgen05 GEMM
+    if backend == "flashinfer":
+        raise ImportError("flashinfer backend requested but qutlass_b200 ships a single sm_100a backend "
+                          "(no multi-backend dispatch)")
+    raise ValueError(f"invalid backend {backend!r}; use 'cutlass' or 'flashinfer'")
+
+
+def matmul_mxf4_bf16_tn(a: torch.Tensor, b: torch.Tensor, a_sf: torch.Tensor, b_sf: torch.Tensor,
+                        alpha: torch.Tensor, backend: Literal["cutlass", "flashinfer"] = "cutlass") -> torch.Tensor:
+    """D = bf16(alpha * dq(a) @ dq(b).T), MXFP4 (reference: qutlass/__init__.py:34-76)."""
+    _backend_gate(backend)
+    return _matmul_fp4("matmul_mxf4_bf16_tn", a, b, a_sf, b_sf, alpha, KIND_MXF4, torch.float8_e8m0fnu, 32)
+
+
+def matmul_nvf4_bf16_tn(a: torch.Tensor, b: torch.Tensor, a_sf: torch.Tensor, b_sf: torch.Tensor,
+                        alpha: torch.Tensor, backend: Literal["cutlass", "flashinfer"] = "cutlass") -> torch.Tensor:
+    """D = bf16(alpha * dq(a) @ dq(b).T), NVFP4 (reference: qutlass/__init__.py:89-131)."""
+    _backend_gate(backend)
+    return _matmul_fp4("matmul_nvf4_bf16_tn", a, b, a_sf, b_sf, alpha, KIND_NVF4, torch.float8_e4m3fn, 16)
+
+
+# --------------------------------------------------------------------------------------- quantise
+def _quant_checks(name: str, a, r, outs, extra=()):
+    """reference checks: qutlass/csrc/bindings.cpp:218-252,292-333,335-426"""
+    _check_contig(name, [("A", a), ("B", r)] + [(f"OUT{i}", o) for i, o in enumerate(outs)])
+    _check_cuda_same(name, [("A", a), ("B", r)] + [(f"OUT{i}", o) for i, o in enumerate(outs)] + list(extra))
+    _check(a.dtype == torch.bfloat16, "A must be bf16")
+    _check(r.dtype == torch.bfloat16, "B must be bf16")
+    _check(r.dim() == 2 and r.size(0) == r.size(1), "Rotation matrix must be square")
+    had = r.size(0)
+    _check(a.numel() % had == 0, f"A must be divisible by{had}")
+    return had
+
+
+def _quantize_mx_into(a, r, out, out_sf, out_sf_blocked, out_mask, method: int):
+    had = _quant_checks("fusedQuantizeMx", a, r, [out, out_sf])
+    _check(had in (32, 64, 128), f"Unsupported rotation size {had}; expected 32, 64, or 128.")
+    _check(a.size(-1) % 32 == 0, "last dimension of A must be a multiple of 32")
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().b200q_quantize_mx(
+            a.data_ptr(), r.data_ptr(), out.data_ptr(), out_sf.data_ptr() if out_sf is not None else None,
+            out_sf_blocked.data_ptr() if out_sf_blocked is not None else None,
+            out_mask.data_ptr() if out_mask is not None else None,
+            a.numel(), a.size(-1), had, method, _stream(a)))
+
+
+def _quantize_nv_into(a, r, out, out_sf, out_sf_blocked, global_scale, method: int):
+    had = _quant_checks("fusedQuantizeNv", a, r, [out, out_sf], extra=[("global_scale", global_scale)])
+    _check(global_scale.dtype == torch.float32, "global_scale must be float")
+    _check(global_scale.dim() == 1 and global_scale.size(0) == 1, "global_scale must be a scalar")
+    _check(had in (16, 32, 64, 128), f"Unsupported rotation size {had}; expected 16, 32, 64, or 128.")
+    _check(a.size(-1) % 32 == 0, "last dimension of A must be a multiple of 32")
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().b200q_quantize_nv(
+            a.data_ptr(), r.data_ptr(), out.data_ptr(), out_sf.data_ptr() if out_sf is not None else None,
+            out_sf_blocked.data_ptr() if out_sf_blocked is not None else None, global_scale.data_ptr(),
+            a.numel(), a.size(-1), had, method, _stream(a)))
+
+
+def fusedQuantizeMx(a: torch.Tensor, b: torch.Tensor, *, method: Literal["quest", "abs_max"] = "quest",
+                    return_mask: bool = False):
+    """Fused rotate (x_group @ b) + MXFP4 quantise (reference: qutlass/__init__.py:149-180).
+
+    Returns (e2m1 packed uint8 [..., K/2], e8m0 scales [pad128(rows), pad4(K/32)] row-major) exactly like
+    the reference (+ the packed clip mask with return_mask=True).  The scale tensor additionally carries
+    the block-scaled copy the kernel wrote in the same pass, so ``to_blocked(scales)`` is a no-op.
+    """
+    if method not in ("quest", "abs_max"):
+        raise ValueError(f"invalid method {method!r}, must be 'quest' or 'abs_max'")
+    if method == "abs_max" and return_mask:
+        raise ValueError("return_mask is only supported for method 'quest'")
+    padded_rows, padded_cols = get_padded_shape_mx(a)
+    xh_e2m1 = torch.empty(*a.shape[:-1], a.size(-1) // 2, dtype=torch.uint8, device=a.device)
+    xh_e8m0 = torch.empty(padded_rows, padded_cols, dtype=torch.float8_e8m0fnu, device=a.device)
+    blocked = torch.empty(padded_rows * padded_cols, dtype=torch.float8_e8m0fnu, device=a.device)
+    clip_mask = None
+    if return_mask:
+        clip_mask = torch.empty(*a.shape[:-1], a.size(-1) // 8, dtype=torch.uint8, device=a.device)
+    _quantize_mx_into(a, b, xh_e2m1, xh_e8m0, blocked, clip_mask,
+                      METHOD_QUEST if method == "quest" else METHOD_ABSMAX)
+    _attach_blocked(xh_e8m0, blocked)
+    if return_mask:
+        return xh_e2m1, xh_e8m0, clip_mask
+    return xh_e2m1, xh_e8m0
+
+
+def fusedQuantizeNv(a: torch.Tensor, b: torch.Tensor, global_scale: torch.Tensor, *,
+                    method: Literal["quest", "abs_max"] = "abs_max"):
+    """Fused rotate + NVFP4 quantise (reference: qutlass/__init__.py:183-203)."""
+    if method not in ("quest", "abs_max"):
+        raise ValueError(f"invalid method {method!r}, must be 'quest' or 'abs_max'")
+    padded_rows, padded_cols = get_padded_shape_nv(a)
+    xh_e2m1 = torch.empty(*a.shape[:-1], a.size(-1) // 2, dtype=torch.uint8, device=a.device)
+    xh_e4m3 = torch.empty(padded_rows, padded_cols, dtype=torch.float8_e4m3fn, device=a.device)
+    blocked = torch.empty(padded_rows * padded_cols, dtype=torch.float8_e4m3fn, device=a.device)
+    _quantize_nv_into(a, b, xh_e2m1, xh_e4m3, blocked, global_scale,
+                      METHOD_QUEST if method == "quest" else METHOD_ABSMAX)
+    _attach_blocked(xh_e4m3, blocked)
+    return xh_e2m1, xh_e4m3
+
+
+# --------------------------------------------------------------------------------------- out of scope
+def _out_of_scope(name: str):
+    def fn(*args, **kwargs):
+        raise NotImplementedError(
+            f"qutlass_b200.{name}: outside the microscaled-FP4 forward hot path this build covers "
+            "(SURVEY.md section 8 'out of scope' / 'next').")
+    fn.__name__ = name
+    return fn
+
+
+matmul_ada_mxf4_bf16_tn = _out_of_scope("matmul_ada_mxf4_bf16_tn")      # sm_120-only prototype (gemm_ada.cu)
+matmul_mxf8_bf16_tn = _out_of_scope("matmul_mxf8_bf16_tn")              # QAT backward GEMMs
+matmul_mxf8_bf16_nn = _out_of_scope("matmul_mxf8_bf16_nn")
+backward_t_bf16 = _out_of_scope("backward_t_bf16")
+backward_qt_bf16 = _out_of_scope("backward_qt_bf16")
+backward_bf16_square_double_mxfp8 = _out_of_scope("backward_bf16_square_double_mxfp8")
+mxfp4_transpose_mxfp8 = _out_of_scope("mxfp4_transpose_mxfp8")
+
+
+# --------------------------------------------------------------------------------------- torch.ops._qutlass_C
+def _register_ops() -> None:
+    """Same op names and schemas as the reference's STABLE_TORCH_LIBRARY_FRAGMENT(_qutlass_C)
+    (qutlass/csrc/bindings.cpp:498-507), CUDA dispatch key."""
+    try:
+        lib = torch.library.Library("_qutlass_C", "FRAGMENT")
+    except Exception:  # pragma: no cover
+        return
+    defs = {
+        "matmul_mxf4_bf16_tn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
+        "matmul_nvf4_bf16_tn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
+        "fusedQuantizeMxQuest": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf) -> (Tensor, Tensor)",
+        "fusedQuantizeMxAbsMax": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf) -> (Tensor, Tensor)",
+        "fusedQuantizeNvQuest": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf, Tensor global_scale) -> (Tensor, Tensor)",
+        "fusedQuantizeNvAbsMax": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf, Tensor global_scale) -> (Tensor, Tensor)",
+        "fusedQuantizeMxQuestWithMask": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf, Tensor OUT_mask) -> (Tensor, Tensor, Tensor)",
+    }
+    impls = {
+        "matmul_mxf4_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_mxf4_bf16_tn(A, B, A_sf, B_sf, alpha),
+        "matmul_nvf4_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_nvf4_bf16_tn(A, B, A_sf, B_sf, alpha),
+        "fusedQuantizeMxQuest": lambda A, R, OUT, OUT_sf: (_quantize_mx_into(A, R, OUT, OUT_sf, None, None, METHOD_QUEST), (OUT, OUT_sf))[1],
+        "fusedQuantizeMxAbsMax": lambda A, R, OUT, OUT_sf: (_quantize_mx_into(A, R, OUT, OUT_sf, None, None, METHOD_ABSMAX), (OUT, OUT_sf))[1],
+        "fusedQuantizeNvQuest": lambda A, R, OUT, OUT_sf, gs: (_quantize_nv_into(A, R, OUT, OUT_sf, None, gs, METHOD_QUEST), (OUT, OUT_sf))[1],
+        "fusedQuantizeNvAbsMax": lambda A, R, OUT, OUT_sf, gs: (_quantize_nv_into(A, R, OUT, OUT_sf, None, gs, METHOD_ABSMAX), (OUT, OUT_sf))[1],
+        "fusedQuantizeMxQuestWithMask": lambda A, R, OUT, OUT_sf, OUT_mask: (_quantize_mx_into(A, R, OUT, OUT_sf, None, OUT_mask, METHOD_QUEST), (OUT, OUT_sf, OUT_mask))[1],
+    }
+    for name, schema in defs.items():
+        try:
+            lib.define(name + schema)
+            lib.impl(name, impls[name], "CUDA")
+        except Exception:  # already defined by another copy of the library in this process
+            pass
+    globals()["_OPS_LIB"] = lib  # keep alive
+
+
+_register_ops()

@@ -1,0 +1,54 @@
+"""ctypes loader for libb200q.so -- the C-ABI declared in include/b200q.h.
+
+There is NO CPU fallback and no alternative backend: if the library is missing the import of any
+compute entry point fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200q.so")
+
+# name -> (restype, argtypes); must match include/b200q.h exactly (tests/test_cabi.py checks the header)
+_vp, _i64, _i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+SIGNATURES = {
+    "b200q_abi_version": (_i32, []),
+    "b200q_last_error": (ctypes.c_char_p, []),
+    "b200q_quantize_mx": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "b200q_quantize_nv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "b200q_swizzle_sf": (_i32, [_vp, _vp, _i64, _i64, _vp]),
+    "b200q_gemm_fp4": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "b200q_gemm_fp4_cfg": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200q_linear_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "b200q_linear_fp4_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+}
+
+_lib = None
+
+
+class B200QError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -m qutlass_b200.build` "
+                "(there is no CPU or library fallback for this path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().b200q_last_error().decode(errors="replace")
+        raise B200QError(msg or f"libb200q call failed with code {rc}")

@@ -1,0 +1,46 @@
+// Shared host/device helpers for libb200q (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "b200q.h"
+
+namespace b200q {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+int check_device_sm100();          // 0 or B200Q_EUNSUPPORTED (cached per device)
+int num_sms();                     // SM count of the current device (cached)
+
+#define B200Q_REQUIRE(cond, ...)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::b200q::set_error(__VA_ARGS__);           \
+      return B200Q_EINVAL;                       \
+    }                                            \
+  } while (0)
+
+#define B200Q_CUDA(expr)                                                          \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      ::b200q::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                         __FILE__, __LINE__);                                     \
+      return B200Q_ECUDA;                                                         \
+    }                                                                             \
+  } while (0)
+
+// ---------------------------------------------------------------- scale layout
+// Byte offset of scale (r, c) in the block-scaled layout: 128x4 tiles of 512 B,
+// K-blocks fastest (reference: qutlass/utils.py:178-193).
+__host__ __device__ __forceinline__ int64_t sf_blocked_offset(int64_t r, int64_t c, int64_t padded_cols) {
+  return ((r >> 7) * (padded_cols >> 2) + (c >> 2)) * 512 + (r & 31) * 16 + ((r & 127) >> 5) * 4 + (c & 3);
+}
+
+__host__ __device__ __forceinline__ int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+__host__ __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace b200q

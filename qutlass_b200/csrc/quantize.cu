@@ -1,0 +1,445 @@
+// Fused rotate + microscaled-FP4 quantise for sm_100a (HBM-bound streaming kernel).
+//
+// Replaces the reference's CUTLASS-2.x "GEMM with quantising epilogue" kernels
+// (qutlass/csrc/fused_quantize_{mx,nv,mx_mask}.cu + cutlass_extensions/epilogue/threadblock/
+// epilogue_quant.h) and the separate Triton scale swizzle (qutlass/utils.py:16-133).
+//
+// Data flow per warp-tile (32 chunks of 32 bf16 = 2 KB in, 512 B + scales out):
+//   4 fully coalesced 128-bit global loads per lane  ->  XOR-swizzled per-warp shared-memory
+//   staging (bank-conflict free both ways)  ->  each lane owns ONE contiguous 32-element chunk
+//   in registers  ->  rotation: if R == c * Sylvester-Hadamard (checked on the device by every
+//   CTA, so the launch stays CUDA-graph capturable) a 5-stage in-register butterfly + warp-shuffle
+//   butterflies for H = 64/128, scaled by c read from R (bf16-rounded magnitude);
+//   otherwise a generic x @ R (fp32 FMA from shared memory)  ->  per-group scale (abs-max or
+//   Quartet/"quest", sequential fp32 sums exactly in the reference's order)  ->  e8m0 / e4m3 scale,
+//   cvt.rn.satfinite.e2m1x2  ->  one 128-bit store of 32 packed e2m1 per lane, scale bytes written
+//   BOTH row-major (what the reference returns) and directly in the tensor-core block-scaled
+//   layout (so to_blocked is a no-op), optional clip mask.
+//
+// Algorithmic bytes / element: 2 (bf16 in) + 0.5 (e2m1) + 1/32 (+1/32 blocked)  [MX].
+#include "common.cuh"
+#include <cuda_fp8.h>
+
+namespace b200q {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+
+struct QuantParams {
+  const uint4* x;          // bf16 input viewed as 16-byte units (8 bf16)
+  const __nv_bfloat16* rot;
+  uint4* q;                // one uint4 (32 e2m1) per chunk
+  uint8_t* sf_rm;          // may be null
+  uint8_t* sf_blk;         // may be null
+  uint32_t* mask;          // may be null
+  const float* gs;         // NV only
+  int64_t n_chunks;        // numel / 32
+  int64_t n_tiles;         // ceil(n_chunks / 32)
+  int64_t cols;            // scales per row (row_len / group)
+  int64_t padded_cols;
+  int64_t rows;
+  int64_t padded_rows;
+};
+
+__device__ __forceinline__ float rcp_approx_ftz(float a) {
+  float b;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(a));
+  return b;
+}
+
+// 8 floats -> 8 e2m1 codes in one 32-bit word; element 2i in the low nibble of byte i.
+// (same instruction the reference uses: epilogue_quant.h:78-97)
+__device__ __forceinline__ uint32_t cvt8_e2m1(const float* a) {
+  uint32_t val;
+  asm volatile(
+      "{\n"
+      ".reg .b8 b0, b1, b2, b3;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b0, %2, %1;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b1, %4, %3;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b2, %6, %5;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b3, %8, %7;\n"
+      "mov.b32 %0, {b0, b1, b2, b3};\n"
+      "}"
+      : "=r"(val)
+      : "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]));
+  return val;
+}
+
+// In-register Walsh-Hadamard butterflies over index bits [0, log2(N)) of v[0..31].
+template <int N>
+__device__ __forceinline__ void fwht_inreg(float* v) {
+#pragma unroll
+  for (int s = 1; s < N; s <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if ((i & s) == 0) {
+        float a = v[i], b = v[i | s];
+        v[i] = a + b;
+        v[i | s] = a - b;
+      }
+    }
+  }
+}
+
+// Butterfly stage across lanes (index bit >= 5 lives in the lane id).
+__device__ __forceinline__ void fwht_lane_stage(float* v, int lane_bit) {
+  const bool upper = (threadIdx.x & lane_bit) != 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float o = __shfl_xor_sync(0xffffffffu, v[i], lane_bit);
+    v[i] = upper ? (o - v[i]) : (v[i] + o);
+  }
+}
+
+template <int HAD, bool NV, int METHOD, bool MASK>
+__global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p) {
+  // per-warp staging: 2 KB of bf16 (swizzled 16-B units) -- reused as fp32 scratch by the generic path
+  __shared__ __align__(16) uint4 s_stage[kWarpsPerCta][128];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- 1. rotation-structure check: R == c * (-1)^popcount(k & n) ?  (bitwise, bf16)
+  const unsigned short c_bits = reinterpret_cast<const unsigned short*>(p.rot)[0];
+  bool ok = true;
+  for (int idx = threadIdx.x; idx < HAD * HAD; idx += kThreads) {
+    const int k = idx / HAD, n = idx % HAD;
+    const unsigned short want = (__popc(k & n) & 1) ? (c_bits ^ 0x8000u) : c_bits;
+    ok = ok && (reinterpret_cast<const unsigned short*>(p.rot)[idx] == want);
+  }
+  const bool is_hadamard = __syncthreads_and(ok) != 0;
+  const float c_scale = __bfloat162float(p.rot[0]);
+
+  float gs = 1.f, gs_rcp = 1.f;
+  if constexpr (NV) {
+    gs = *p.gs;
+    gs_rcp = rcp_approx_ftz(gs);
+  }
+
+  // ---- 2. stream warp-tiles
+  uint4* stage = s_stage[warp];
+  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < p.n_tiles;
+       tile += (int64_t)gridDim.x * kWarpsPerCta) {
+    const int64_t unit0 = tile * 128;            // first 16-B unit of this tile
+    const int64_t n_units = p.n_chunks * 4;
+    // coalesced loads, swizzled staging
+    uint4 ld[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t u = unit0 + i * 32 + lane;
+      ld[i] = (u < n_units) ? __ldg(p.x + u) : make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = i * 8 + (lane >> 2), j = lane & 3;
+      stage[t * 4 + (j ^ ((t >> 1) & 3))] = ld[i];
+    }
+    __syncwarp();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 w = stage[lane * 4 + (j ^ ((lane >> 1) & 3))];
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[j * 8 + e * 2 + 0] = __uint_as_float(ww[e] << 16);
+        v[j * 8 + e * 2 + 1] = __uint_as_float(ww[e] & 0xffff0000u);
+      }
+    }
+
+    // ---- rotation
+    if (is_hadamard) {
+      fwht_inreg<(HAD < 32 ? HAD : 32)>(v);
+      if constexpr (HAD >= 64) fwht_lane_stage(v, 1);
+      if constexpr (HAD >= 128) fwht_lane_stage(v, 2);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= c_scale;
+    } else {
+      // generic x_group(1xH) @ R(HxH) for arbitrary runtime rotations (e.g. identity):
+      // stage the fp32 x of the whole warp-tile in shared memory, fp32 FMA on CUDA cores.
+      __shared__ float s_x[kWarpsPerCta][32 * 32];
+      float* sx = s_x[warp];
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sx[lane * 32 + i] = v[i];
+      __syncwarp();
+      constexpr int LPG = HAD >= 32 ? HAD / 32 : 1;          // lanes per rotation group
+      const int g_lane0 = lane & ~(LPG - 1);
+      const int sub = lane & (LPG - 1);
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      if constexpr (HAD >= 32) {
+        for (int k = 0; k < HAD; ++k) {
+          const float xk = sx[g_lane0 * 32 + k];
+          const __nv_bfloat16* rrow = p.rot + (int64_t)k * HAD + sub * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = fmaf(xk, __bfloat162float(rrow[i]), acc[i]);
+        }
+      } else {  // HAD == 16: two independent 16-groups in the lane's chunk
+        for (int k = 0; k < 16; ++k) {
+          const float x0 = sx[lane * 32 + k], x1 = sx[lane * 32 + 16 + k];
+          const __nv_bfloat16* rrow = p.rot + k * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float r = __bfloat162float(rrow[i]);
+            acc[i] = fmaf(x0, r, acc[i]);
+            acc[16 + i] = fmaf(x1, r, acc[16 + i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = acc[i];
+      __syncwarp();
+    }
+
+    // ---- quantise
+    const int64_t chunk = tile * 32 + lane;
+    uint32_t out[4];
+    uint32_t mask_word = 0;
+    uint32_t sf_bytes = 0;  // MX: 1 byte, NV: 2 bytes (little-endian)
+    if constexpr (!NV) {
+      float scale;
+      if constexpr (METHOD == B200Q_METHOD_QUEST) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s1 += v[i];
+          s2 = fmaf(v[i], v[i], s2);
+        }
+        const float mean = s1 / 32.f;
+        const float var = fmaf(-mean, mean, s2 / 32.f);
+        scale = 1.0f;
+        if (var >= 0.f) scale = (float)((double)sqrtf(var) * (2.92247856 / 6.) + 1e-8);
+      } else {
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
+        scale = amax + 1e-8f;
+      }
+      const uint32_t e = (__float_as_uint(scale) >> 23) & 0xffu;   // floor to 2^(e-127)
+      sf_bytes = e;
+      // exact 1 / 2^(e-127)
+      const float inv = (e >= 254u) ? __uint_as_float(0x00400000u >> (e - 254u)) : __uint_as_float((254u - e) << 23);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] *= inv;
+        if constexpr (METHOD == B200Q_METHOD_ABSMAX) v[i] *= 3.0f;
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float* vv = v + 16 * h;
+        float out_scale;
+        uint8_t sfb;
+        if constexpr (METHOD == B200Q_METHOD_QUEST) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            s1 += vv[i];
+            s2 = fmaf(vv[i], vv[i], s2);
+          }
+          const float r16 = 0.0625f;
+          const float mean = s1 * r16;
+          const float scale = (float)((double)sqrtf(fmaf(-mean, mean, s2 * r16)) * (2.92247856 / 6.) + 1e-8);
+          const __nv_fp8_e4m3 t(scale);
+          sfb = *reinterpret_cast<const uint8_t*>(&t);
+          const float sq = float(t);
+          out_scale = (sq > 0.f) ? rcp_approx_ftz(sq) : 0.f;
+        } else {
+          float amax = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(vv[i]));
+          float sfv = gs * (amax * rcp_approx_ftz(6.0f));
+          const __nv_fp8_e4m3 t(sfv);
+          sfb = *reinterpret_cast<const uint8_t*>(&t);
+          sfv = float(t);
+          out_scale = (sfv != 0.f) ? rcp_approx_ftz(sfv * gs_rcp) : 0.f;
+        }
+        sf_bytes |= (uint32_t)sfb << (8 * h);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) vv[i] *= out_scale;
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) out[w] = cvt8_e2m1(v + 8 * w);
+    if constexpr (MASK) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mask_word |= (fabsf(v[i]) < 6.f) ? (1u << i) : 0u;
+    }
+
+    // ---- stores
+    if (chunk < p.n_chunks) {
+      p.q[chunk] = make_uint4(out[0], out[1], out[2], out[3]);
+      if constexpr (MASK) {
+        if (p.mask) p.mask[chunk] = mask_word;
+      }
+      if constexpr (!NV) {
+        if (p.sf_rm) p.sf_rm[chunk] = (uint8_t)sf_bytes;
+        if (p.sf_blk) {
+          const int64_t r = chunk / p.cols, c = chunk % p.cols;
+          p.sf_blk[sf_blocked_offset(r, c, p.padded_cols)] = (uint8_t)sf_bytes;
+        }
+      } else {
+        if (p.sf_rm) reinterpret_cast<uint16_t*>(p.sf_rm)[chunk] = (uint16_t)sf_bytes;
+        if (p.sf_blk) {
+          const int64_t g = chunk * 2;
+          const int64_t r = g / p.cols, c = g % p.cols;   // c is even: both bytes share a 4-byte cell
+          *reinterpret_cast<uint16_t*>(p.sf_blk + sf_blocked_offset(r, c, p.padded_cols)) = (uint16_t)sf_bytes;
+        }
+      }
+    }
+  }
+
+  // ---- 3. zero-fill the padding of the blocked scale buffer (rows >= rows, cols >= cols)
+  if (p.sf_blk) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * kThreads;
+    const int64_t pad_rows = p.padded_rows - p.rows;
+    for (int64_t i = tid; i < pad_rows * p.padded_cols; i += nthr) {
+      const int64_t r = p.rows + i / p.padded_cols, c = i % p.padded_cols;
+      p.sf_blk[sf_blocked_offset(r, c, p.padded_cols)] = 0;
+    }
+    const int64_t pad_cols = p.padded_cols - p.cols;
+    for (int64_t i = tid; i < p.rows * pad_cols; i += nthr) {
+      const int64_t r = i / pad_cols, c = p.cols + i % pad_cols;
+      p.sf_blk[sf_blocked_offset(r, c, p.padded_cols)] = 0;
+    }
+  }
+}
+
+template <int HAD, bool NV, int METHOD, bool MASK>
+static int launch(const QuantParams& p, cudaStream_t stream) {
+  int64_t ctas = ceil_div(p.n_tiles, kWarpsPerCta);
+  const int64_t max_ctas = (int64_t)num_sms() * 6;
+  if (ctas > max_ctas) ctas = max_ctas;
+  if (ctas < 1) ctas = 1;
+  quantize_kernel<HAD, NV, METHOD, MASK><<<(unsigned)ctas, kThreads, 0, stream>>>(p);
+  B200Q_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <bool NV, int METHOD, bool MASK>
+static int dispatch_had(int had, const QuantParams& p, cudaStream_t stream) {
+  switch (had) {
+    case 16:
+      if constexpr (NV) return launch<16, NV, METHOD, MASK>(p, stream);
+      break;
+    case 32: return launch<32, NV, METHOD, MASK>(p, stream);
+    case 64: return launch<64, NV, METHOD, MASK>(p, stream);
+    case 128: return launch<128, NV, METHOD, MASK>(p, stream);
+  }
+  set_error(NV ? "Unsupported rotation size %d; expected 16, 32, 64, or 128."
+               : "Unsupported rotation size %d; expected 32, 64, or 128.", had);
+  return B200Q_EINVAL;
+}
+
+static int fill_params(QuantParams& p, const void* x, const void* rot, void* q, void* sf_rm, void* sf_blk,
+                       int64_t numel, int64_t row_len, int had, int group) {
+  B200Q_REQUIRE(x && rot && q, "null pointer argument");
+  B200Q_REQUIRE(numel > 0 && row_len > 0 && numel % row_len == 0, "numel (%lld) must be a positive multiple of row_len (%lld)",
+                (long long)numel, (long long)row_len);
+  B200Q_REQUIRE(numel % had == 0, "A must be divisible by %d", had);
+  B200Q_REQUIRE(row_len % 32 == 0, "last dimension (%lld) must be a multiple of 32", (long long)row_len);
+  B200Q_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)q & 15) == 0, "x and q must be 16-byte aligned");
+  p.x = (const uint4*)x;
+  p.rot = (const __nv_bfloat16*)rot;
+  p.q = (uint4*)q;
+  p.sf_rm = (uint8_t*)sf_rm;
+  p.sf_blk = (uint8_t*)sf_blk;
+  p.mask = nullptr;
+  p.gs = nullptr;
+  p.n_chunks = numel / 32;
+  p.n_tiles = ceil_div(p.n_chunks, 32);
+  p.rows = numel / row_len;
+  p.cols = row_len / group;
+  p.padded_rows = round_up(p.rows, 128);
+  p.padded_cols = round_up(p.cols, 4);
+  return 0;
+}
+
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" int b200q_quantize_mx(const void* x_bf16, const void* rot_bf16, void* q_e2m1, void* sf_rowmajor,
+                                 void* sf_blocked, void* clip_mask, int64_t numel, int64_t row_len, int had,
+                                 int method, b200q_stream_t stream) {
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  QuantParams p;
+  rc = fill_params(p, x_bf16, rot_bf16, q_e2m1, sf_rowmajor, sf_blocked, numel, row_len, had, 32);
+  if (rc) return rc;
+  B200Q_REQUIRE(sf_rowmajor || sf_blocked, "at least one scale output is required");
+  p.mask = (uint32_t*)clip_mask;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (method == B200Q_METHOD_QUEST) {
+    if (clip_mask) return dispatch_had<false, B200Q_METHOD_QUEST, true>(had, p, s);
+    return dispatch_had<false, B200Q_METHOD_QUEST, false>(had, p, s);
+  } else if (method == B200Q_METHOD_ABSMAX) {
+    B200Q_REQUIRE(!clip_mask, "return_mask is only supported for method 'quest'");
+    return dispatch_had<false, B200Q_METHOD_ABSMAX, false>(had, p, s);
+  }
+  set_error("invalid method %d, must be quest (0) or abs_max (1)", method);
+  return B200Q_EINVAL;
+}
+
+extern "C" int b200q_quantize_nv(const void* x_bf16, const void* rot_bf16, void* q_e2m1, void* sf_rowmajor,
+                                 void* sf_blocked, const float* global_scale_dev, int64_t numel, int64_t row_len,
+                                 int had, int method, b200q_stream_t stream) {
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  QuantParams p;
+  rc = fill_params(p, x_bf16, rot_bf16, q_e2m1, sf_rowmajor, sf_blocked, numel, row_len, had, 16);
+  if (rc) return rc;
+  B200Q_REQUIRE(sf_rowmajor || sf_blocked, "at least one scale output is required");
+  B200Q_REQUIRE(global_scale_dev, "global_scale must be a device pointer to one float");
+  p.gs = global_scale_dev;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (method == B200Q_METHOD_QUEST) return dispatch_had<true, B200Q_METHOD_QUEST, false>(had, p, s);
+  if (method == B200Q_METHOD_ABSMAX) return dispatch_had<true, B200Q_METHOD_ABSMAX, false>(had, p, s);
+  set_error("invalid method %d, must be quest (0) or abs_max (1)", method);
+  return B200Q_EINVAL;
+}
+
+// ------------------------------------------------------------------ standalone swizzle
+namespace b200q {
+__global__ void swizzle_sf_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int64_t rows,
+                                  int64_t cols, int64_t padded_rows, int64_t padded_cols) {
+  // one thread per 4-byte cell of the blocked layout (4 consecutive K-scales of one row)
+  const int64_t n_cells = padded_rows * (padded_cols >> 2);
+  for (int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cell < n_cells;
+       cell += (int64_t)gridDim.x * blockDim.x) {
+    // blocked order: [row_block][col_block][r%32][(r%128)/32] cells
+    const int64_t blk = cell >> 7, within = cell & 127;
+    const int64_t rb = blk / (padded_cols >> 2), cb = blk % (padded_cols >> 2);
+    const int64_t r = rb * 128 + (within & 3) * 32 + (within >> 2);
+    const int64_t c0 = cb * 4;
+    uint32_t word = 0;
+    if (r < rows) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (c0 + j < cols) word |= (uint32_t)in[r * cols + c0 + j] << (8 * j);
+      }
+    }
+    reinterpret_cast<uint32_t*>(out)[cell] = word;
+  }
+}
+}  // namespace b200q
+
+extern "C" int b200q_swizzle_sf(const void* sf_rowmajor, void* sf_blocked, int64_t rows, int64_t cols,
+                                b200q_stream_t stream) {
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  B200Q_REQUIRE(sf_rowmajor && sf_blocked, "null pointer argument");
+  B200Q_REQUIRE(rows > 0 && cols > 0, "rows and cols must be positive");
+  const int64_t pr = round_up(rows, 128), pc = round_up(cols, 4);
+  const int64_t n_cells = pr * (pc >> 2);
+  int64_t ctas = ceil_div(n_cells, 256);
+  if (ctas > (int64_t)num_sms() * 8) ctas = (int64_t)num_sms() * 8;
+  swizzle_sf_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)sf_rowmajor, (uint8_t*)sf_blocked,
+                                                                     rows, cols, pr, pc);
+  B200Q_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,67 @@
+"""Scale-layout helpers mirroring qutlass/utils.py of the reference (same names, same results),
+without Triton: the swizzle is either already done by the quantise kernel (no-op) or a small CUDA kernel.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_BLOCKED_ATTR = "_b200q_blocked"
+
+
+def ceil_div(a, b):
+    return (a + b - 1) // b
+
+
+def get_padded_shape_mx(a: torch.Tensor):
+    """reference: qutlass/utils.py:140-147"""
+    rows, cols = a.numel() // a.size(-1), a.size(-1) // 32
+    return ceil_div(rows, 128) * 128, ceil_div(cols, 4) * 4
+
+
+def get_padded_shape_nv(a: torch.Tensor):
+    """reference: qutlass/utils.py:150-157"""
+    rows, cols = a.numel() // a.size(-1), a.size(-1) // 16
+    return ceil_div(rows, 128) * 128, ceil_div(cols, 4) * 4
+
+
+def _attach_blocked(sf_rowmajor: torch.Tensor, blocked: torch.Tensor) -> None:
+    setattr(sf_rowmajor, _BLOCKED_ATTR, (blocked, sf_rowmajor._version))
+
+
+def to_blocked(input_matrix: torch.Tensor, use_triton_kernel: bool = False) -> torch.Tensor:
+    """Row-major scales (H, W) -> flattened block-scaled layout (reference: qutlass/utils.py:160-193).
+
+    If `input_matrix` came straight out of fusedQuantizeMx / fusedQuantizeNv the blocked copy was
+    already written by the quantise kernel and is returned as is (no launch).  Otherwise one CUDA
+    swizzle kernel runs.  `use_triton_kernel` is accepted for drop-in compatibility and ignored
+    (there is no Triton here); like the reference's Triton path, inputs need not be pre-padded.
+    """
+    cached = getattr(input_matrix, _BLOCKED_ATTR, None)
+    if cached is not None and cached[1] == input_matrix._version:
+        return cached[0]
+    assert input_matrix.dim() == 2, "to_blocked expects a 2-D scale matrix"
+    assert input_matrix.element_size() == 1, "Expected element size to be 1 byte (8 bits)"
+    if not input_matrix.is_cuda:
+        raise RuntimeError("to_blocked: input must be a CUDA tensor (no CPU path in qutlass_b200)")
+    x = input_matrix.contiguous()
+    rows, cols = x.shape
+    if not use_triton_kernel:
+        # the reference's torch path asserts the input is already padded (utils.py:187)
+        assert (rows, cols) == (ceil_div(rows, 128) * 128, ceil_div(cols, 4) * 4)
+    out = torch.empty(ceil_div(rows, 128) * 128 * ceil_div(cols, 4) * 4, dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200q_swizzle_sf(x.data_ptr(), out.data_ptr(), rows, cols,
+                                                torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def pad_to_block(tensor, dims, blocksize):
+    """reference: qutlass/utils.py:196-204"""
+    pad_dims = [0 for _ in range(2 * len(tensor.shape))]
+    for dim in dims:
+        size = tensor.shape[dim]
+        next_multiple_of_block = ((size - 1) // blocksize + 1) * blocksize
+        pad_dims[-2 * dim - 1] = next_multiple_of_block - size
+    return torch.nn.functional.pad(tensor, pad_dims, "constant", 0.0)
