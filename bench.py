@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the microscaled-FP4 hot path (driver contract).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--kind mx|nv] [--had H]
+
+Workload (BASELINE.json configs[1]): Llama-3-8B FFN, M=4096, N=14336, K=4096, MXFP4 W4A4 abs_max.
+One "step" is the reference's "actual" benchmark iteration (benchmarks/bench_mxfp4_sm100.py:93-106):
+    fusedQuantizeMx(a, H, "abs_max")  ->  to_blocked (a no-op here)  ->  matmul_mxf4_bf16_tn
+with the weights quantised once outside the loop.  metric = effective TFLOP/s = 2*M*N*K / t.
+
+N > 1 (torchrun): weak scaling -- every rank owns its own 4096 activation rows (global M = 4096*N),
+weights are quantised on rank 0 and broadcast ONCE over NCCL at setup; no collective in the timed loop.
+
+--impl reference: the reference's CPU-side oracle path (unpack e2m1 * scale -> fp32 torch.matmul -> bf16)
+timed on the host cores (oracle/cpu_baseline.py); rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M, N, K = 4096, 14336, 4096
+METRIC = "MXFP4 GEMM effective TFLOPS on Llama-3-8B FFN shapes; % of B200 FP4 peak"
+NOMINAL_FP4_TFLOPS = 9000.0
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), bf16=d.get("bf16_tflops", 1590.0),
+                    bf16_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+    return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one `nvidia-smi -lms 20` process)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = os.path.join(ROOT, "gpurun_out", f"bench_clocks_gpu{index}.csv") if os.path.isdir(
+            os.path.join(ROOT, "gpurun_out")) else f"/tmp/bench_clocks_gpu{index}.csv"
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.25)   # let the first samples land before the timed region starts
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = [[x.strip() for x in l.split(",")] for l in open(self.path) if l.strip()]
+        rows = [r for r in rows if len(r) >= 7]
+        if not rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        pw = [float(r[2]) for r in rows]
+        load = [r for r in rows if float(r[2]) >= 0.6 * max(pw)] or rows   # samples taken under load
+        sm = sorted(float(r[0]) for r in load)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in load)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(rows[0][1]), reasons=reasons, samples=len(load),
+                    power_w_max=max(pw))
+
+
+def run_reference(args):
+    """CPU arm: the reference's test-oracle path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import cpu_baseline as C
+    kind = args.kind
+    # bounded sample: the full config costs a few seconds per step on a many-core host; cap steps
+    steps = max(1, min(args.steps, 3))
+    warm = max(1, min(args.warmup, 1))
+    m_s = 64 if os.environ.get("B200Q_BENCH_TINY") else M   # tiny mode: contract self-test only
+    r = C.time_cpu_path(m_s, N, K, kind, steps=steps, warmup=warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["tflops"], "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp4 e2m1 x e2m1 -> fp32 accumulate -> bf16 (CPU: fp32 matmul of dequantised operands)",
+        "data": "synthetic",
+        "config": {"workload": f"Llama-3-8B FFN M={M} N={N} K={K} {'MXFP4' if kind == 'mx' else 'NVFP4'} W4A4, "
+                               "CPU dequantise(A,B)+torch.matmul fp32 -> bf16"},
+        "cpu_baseline": {"value": r["tflops"], "unit": "TFLOP/s", "cores": r["threads"], "kind": "port",
+                         "sample": f"{steps} step(s) of M={m_s} rows x full N,K (dequant LUT + fp32 matmul)"},
+        "e2e": {"value": r["tflops"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--kind", default="mx", choices=["mx", "nv"])
+    ap.add_argument("--had", type=int, default=128)
+    ap.add_argument("--cta-group", type=int, default=0)
+    ap.add_argument("--block-n", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import qutlass_b200 as Q
+    from qutlass_b200 import _lib
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: qutlass_b200 has no CPU path"}))
+        return 2
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    kind = args.kind
+    knd = Q.KIND_MXF4 if kind == "mx" else Q.KIND_NVF4
+    sf_dtype = torch.float8_e8m0fnu if kind == "mx" else torch.float8_e4m3fn
+    group = 32 if kind == "mx" else 16
+
+    # ---------------- setup (untimed): rotation, weights quantised once on rank 0, ONE broadcast
+    import oracle as O  # only for the Hadamard matrix helper
+    torch.manual_seed(1234 + rank)
+    H = torch.from_numpy(O.bf16_bits(O.hadamard_matrix(args.had)).astype(np.int16)).view(torch.bfloat16).to(dev)
+    gs = torch.tensor([1.0], dtype=torch.float32, device=dev)
+    alpha = torch.tensor([1.0], dtype=torch.float32, device=dev)
+    NSETS = 4  # rotate buffer sets so every timed iteration reads/writes data that is not L2 resident
+    wq = torch.empty(N, K // 2, dtype=torch.uint8, device=dev)
+    wsf = torch.empty(((N + 127) // 128) * 128 * (((K // group) + 3) // 4) * 4, dtype=sf_dtype, device=dev)
+    if rank == 0:
+        w = torch.randn(N, K, dtype=torch.bfloat16, device=dev)
+        if kind == "mx":
+            q_, s_ = Q.fusedQuantizeMx(w, H, method="abs_max")
+        else:
+            q_, s_ = Q.fusedQuantizeNv(w, H, gs, method="abs_max")
+        wq.copy_(q_)
+        wsf.copy_(Q.to_blocked(s_))
+        del w, q_, s_
+    if world > 1:
+        dist.broadcast(wq, 0)
+        wsf_u8 = wsf.view(torch.uint8)
+        dist.broadcast(wsf_u8, 0)
+    wqs = [wq] + [wq.clone() for _ in range(NSETS - 1)]
+    wsfs = [wsf] + [wsf.clone() for _ in range(NSETS - 1)]
+    acts = [torch.randn(M, K, dtype=torch.bfloat16, device=dev) for _ in range(NSETS)]
+    pr, pc = ((M + 127) // 128) * 128, (((K // group) + 3) // 4) * 4
+    aqs = [torch.empty(M, K // 2, dtype=torch.uint8, device=dev) for _ in range(NSETS)]
+    asfs = [torch.empty(pr * pc, dtype=sf_dtype, device=dev) for _ in range(NSETS)]
+    outs = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(NSETS)]
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    method = Q.METHOD_ABSMAX
+
+    def quant(i):
+        s = i % NSETS
+        if kind == "mx":
+            rc = lib.b200q_quantize_mx(acts[s].data_ptr(), H.data_ptr(), aqs[s].data_ptr(), None, asfs[s].data_ptr(), None,
+                                       M * K, K, args.had, method, stream)
+        else:
+            rc = lib.b200q_quantize_nv(acts[s].data_ptr(), H.data_ptr(), aqs[s].data_ptr(), None, asfs[s].data_ptr(),
+                                       gs.data_ptr(), M * K, K, args.had, method, stream)
+        _lib.check(rc)
+
+    def gemm(i):
+        s = i % NSETS
+        _lib.check(lib.b200q_gemm_fp4_cfg(aqs[s].data_ptr(), wqs[s].data_ptr(), asfs[s].data_ptr(), wsfs[s].data_ptr(),
+                                          alpha.data_ptr(), outs[s].data_ptr(), M, N, K, knd, args.cta_group,
+                                          args.block_n, stream))
+
+    def step(i):
+        quant(i)
+        gemm(i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    flops = 2.0 * M * N * K
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_step = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    # dominant kernel alone (CUDA events on the launching stream), and the quantise kernel alone
+    ms_gemm = timed(gemm, args.steps, 3)
+    ms_quant = timed(quant, args.steps, 3)
+
+    value = flops * world / (ms_step * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp4 (e2m1 x e2m1, block-scaled, fp32 accumulate, bf16 out)", "data": "synthetic",
+        "config": {
+            "workload": f"Llama-3-8B FFN M={M} (per GPU) N={N} K={K} {'MXFP4' if kind == 'mx' else 'NVFP4'} W4A4 abs_max, "
+                        f"step = fused Hadamard-{args.had} rotate+quantise of activations + block-scaled FP4 GEMM "
+                        "(weights pre-quantised)",
+            "global_batch_rows": M * world, "parallelism": f"dp{world} (M-sharded, weights broadcast once at setup)",
+            "l2_policy": f"rotating {NSETS} buffer sets (activations/outputs/weights), {NSETS * 190} MB footprint > 126 MB L2",
+        },
+        "gpu_launches": 2 * args.steps,
+        "gemm_only_tflops_per_gpu": flops / (ms_gemm * 1e-3) / 1e12,
+        "quantize_us": ms_quant * 1e3,
+    }
+    if rank == 0:
+        pk = _peaks()
+        fp4_peak = 4.0 * pk["bf16_sustained"]
+        ach = flops / (ms_gemm * 1e-3) / 1e12
+        line["roofline"] = {
+            "bound": "tensor", "achieved": ach, "peak": fp4_peak, "unit": "TFLOP/s", "frac": ach / fp4_peak,
+            "traffic": None,
+            "peak_basis": f"4 x {pk['source']} sustained cuBLAS bf16 ({pk['bf16_sustained']} TF/s): kind::mxf4 issues 4x the MACs "
+                          "per tcgen05.mma slot of kind::f16; no FP4 figure in MEASURED_PEAKS.json",
+            "frac_of_nominal_9PF": ach / NOMINAL_FP4_TFLOPS,
+            "frac_of_4x_burst_bf16": ach / (4.0 * pk["bf16"]),
+            "kernel": "gemm_fp4_kernel", "algorithmic_flops_per_launch": flops,
+            "quantize_hbm": {
+                "bound": "hbm", "achieved": (M * K * (2 + 0.5 + 1.0 / group)) / (ms_quant * 1e-3) / 1e9,
+                "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": (M * K * (2 + 0.5 + 1.0 / group)) / (ms_quant * 1e-3) / 1e9 / pk["hbm_gbs"],
+            },
+        }
+        line["clocks"] = clocks
+
+    # ---------------- e2e: host buffers through the C-ABI (H2D + quantise + GEMM + D2H inside the timed region)
+    if not args.no_e2e:
+        ws_bytes = lib.b200q_linear_workspace_bytes(M, N, K, knd)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        x_host = torch.randn(M, K, dtype=torch.bfloat16).pin_memory()
+        d_host = torch.empty(M, N, dtype=torch.bfloat16).pin_memory()
+
+        def e2e_step(i):
+            _lib.check(lib.b200q_linear_fp4_host(x_host.data_ptr(), H.data_ptr(), wqs[i % NSETS].data_ptr(),
+                                                 wsfs[i % NSETS].data_ptr(), alpha.data_ptr(), gs.data_ptr(),
+                                                 d_host.data_ptr(), ws.data_ptr(), M, N, K, args.had, knd, stream))
+
+        e2e_steps = max(3, min(args.steps, 20))
+        ms_e2e = timed(e2e_step, e2e_steps, 3)
+        line["e2e"] = {"value": flops * world / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s",
+                       "h2d_bytes_per_step": M * K * 2, "d2h_bytes_per_step": M * N * 2, "ms_per_step": ms_e2e,
+                       "api": "b200q_linear_fp4_host (C-ABI, pinned host buffers)"}
+
+    # ---------------- cpu_baseline (rank 0, N=1 only): bounded sample on the host cores
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import cpu_baseline as C
+        r = C.time_cpu_path(M, N, K, kind, steps=1, warmup=1)
+        line["cpu_baseline"] = {"value": r["tflops"], "unit": "TFLOP/s", "cores": r["threads"], "kind": "port",
+                                "sample": f"1 step of the full config (M={M}): LUT dequantise A,B + fp32 torch.matmul + bf16"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

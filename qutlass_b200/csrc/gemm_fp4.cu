@@ -7,18 +7,21 @@
 //   A [M,K/2], B [N,K/2] packed e2m1 (K-major); SFA/SFB in the cuBLAS block-scaled layout
 //   (512-B blocks = 128 rows x 4 scales, K-blocks fastest), g = 32 (ue8m0) or 16 (ue4m3).
 //
-// Kernel shape (persistent, warp-specialised, 192 threads, 1 CTA / SM):
-//   warp 0     TMA producer: per k-tile (256 K-elements = one 128-byte swizzle row) loads the A tile
-//              (128 rows), this CTA's part of the B tile, and the SFA / SFB blocks into a shared-memory
-//              stage; completion via mbarrier complete_tx.
-//   warp 1     MMA issuer (one elected lane): copies the stage's scale blocks smem -> TMEM with
-//              tcgen05.cp (32x128b.warpx4), then 4 x tcgen05.mma.kind::mxf4[nvf4].block_scale (K = 64 each);
-//              tcgen05.commit releases the stage and, after the last k-tile, publishes the accumulator.
-//              With kCtaGroup == 2 the CTA pair computes a 256 x BN tile (cta_group::2), each CTA holding
-//              128 rows of A and half of the B rows; the peer CTA's warp 1 relays "my stage landed" to the
-//              leader's barrier.
-//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns, alpha (device scalar) in fp32, RNE to bf16,
-//              vectorised 16-byte global stores; double-buffered accumulators overlap it with the next tile.
+// Kernel shape (persistent, warp-specialised, 320 threads, 1 CTA / SM):
+//   warp 0     TMA producer (one lane): per k-tile (256 K-elements = one 128-byte swizzle row) FOUR tensor-map
+//              loads -- A tile (128 rows), this CTA's share of the B tile, SFA blocks, SFB blocks -- into a
+//              shared-memory stage; completion by mbarrier complete_tx.  With kCtaGroup == 2 both CTAs of the
+//              pair signal the LEADER's barrier (cp.async.bulk.tensor ... .cta_group::2).
+//   warp 1     MMA issuer (one lane, leader CTA only): scale blocks smem -> TMEM with tcgen05.cp
+//              (32x128b.warpx4), then 4 x tcgen05.mma.kind::mxf4[nvf4].block_scale (K = 64 each);
+//              tcgen05.commit frees the stage (multicast to both CTAs) and, after the last k-tile, publishes
+//              the accumulator.  With kCtaGroup == 2 the pair computes a 256 x BN tile, each CTA holding 128
+//              rows of A, BN/2 rows of B and its 128 x BN fp32 accumulator.
+//   warps 2-9  epilogue (8 warps = 4 TMEM lane quarters x 2 column halves): drain the WHOLE accumulator half
+//              into registers with back-to-back tcgen05.ld (<= 128 registers / thread) and immediately release
+//              TMEM -- so even the single-buffered 256-column accumulator only stalls the tensor pipe for the
+//              drain, not for the stores -- then alpha (device scalar, fp32), RNE to bf16, 128B-swizzled
+//              shared-memory staging and TMA tensor stores (full 128-byte lines; clips the M/N tails).
 //
 // Bit-exactness (reference tests demand out == bf16(fp64 matmul)): a single fp32 accumulation chain
 // per output over all of K (no split-K), alpha applied once in fp32, one RNE to bf16.
@@ -27,6 +30,7 @@
 
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace b200q {
 using namespace ptx;
@@ -34,16 +38,16 @@ using namespace ptx;
 constexpr int BM = 128;          // rows of A per CTA
 constexpr int BK_BYTES = 128;    // one k-tile = 256 e2m1 = 128 bytes per row (one 128B-swizzle row)
 constexpr int BK = 256;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 320
 constexpr int kSmemBudget = 227 * 1024;
-
-__host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
 
 template <int kCtaGroup, int BN, bool kNV>
 struct GemmCfg {
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 64 in [64, 256]");
   static constexpr int SFKB = kNV ? 4 : 2;                       // 512-B scale blocks per 128 rows per k-tile
-  static constexpr int G = cgcd(BN, 128);
-  static constexpr int NB = (128 - G + BN + 127) / 128;          // SFB row-blocks a tile can touch
+  // a BN-wide tile starts at a multiple of 64 rows of B: its scales begin 0 or 2 TMEM columns into a block
+  static constexpr int NB = (BN % 128 == 0) ? BN / 128 : (BN + 64 + 127) / 128;   // SFB row-blocks a tile can touch
   static constexpr int B_ROWS = BN / kCtaGroup;                  // B rows this CTA stages
   static constexpr int A_BYTES = BM * BK_BYTES;
   static constexpr int B_BYTES = B_ROWS * BK_BYTES;
@@ -52,37 +56,43 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + SFA_BYTES + SFB_BYTES;
   static constexpr int SFA_COLS = SFKB * 4;
   static constexpr int SFB_COLS = SFKB * 4 * NB;
-  static constexpr int ACC_STAGES = (2 * BN + SFA_COLS + SFB_COLS <= 512) ? 2 : 1;
-  static constexpr int TMEM_USED = ACC_STAGES * BN + SFA_COLS + SFB_COLS;
+  static constexpr int SF_COLS = SFA_COLS + SFB_COLS;
+  static constexpr int ACC_STAGES = (2 * BN + SF_COLS <= 512) ? 2 : 1;
+  static constexpr int TMEM_USED = ACC_STAGES * BN + SF_COLS;
   static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
+  // epilogue: each of the 8 warps owns 32 rows x EPI_COLS columns, stored in chunks of EPI_CHUNK columns
+  static constexpr int EPI_COLS = BN / 2;
+  static constexpr int EPI_CHUNK = (EPI_COLS % 64 == 0) ? 64 : 32;
+  static constexpr int EPI_NCHUNK = EPI_COLS / EPI_CHUNK;
+  static constexpr int STG_BYTES = 32 * EPI_CHUNK * 2;           // one staging buffer per epilogue warp
+  static constexpr int STG_TOTAL = kEpiWarps * STG_BYTES;
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int STAGES_RAW = (kSmemBudget - BAR_BYTES - 1024) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (kSmemBudget - BAR_BYTES - 1024 - STG_TOTAL) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_TOTAL + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr uint32_t TX_BYTES = (uint32_t)STAGE_BYTES * kCtaGroup;   // what the (leader's) full barrier expects
   static_assert(TMEM_USED <= 512, "TMEM overflow");
   static_assert(STAGES >= 2, "not enough shared memory for 2 stages");
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32, 256]");
   static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-byte alignment for the 128B swizzle");
+  static_assert(EPI_COLS % 32 == 0 && EPI_COLS <= 128, "epilogue register budget");
 };
 
 struct GemmParams {
-  const uint8_t* sfa;
-  const uint8_t* sfb;
   const float* alpha;
   __nv_bfloat16* d;
   int M, N, K;
   int tiles_m;        // ceil(M / (BM * cta_group))   (cluster tiles along M)
   int tiles_n;        // ceil(N / BN)
   int k_tiles;        // ceil(K / 256)
-  int sf_col_blocks;  // ceil(K / group / 4): 512-B blocks per row-block in SFA / SFB
-  int sfa_row_blocks; // ceil(M / 128)
-  int sfb_row_blocks; // ceil(N / 128)
+  int tma_store;      // 1: TMA-store epilogue (needs N % 8 == 0); 0: direct global stores
+  int flags;          // profiling: bit0 skip stores, bit1 skip TMEM loads
 };
 
 template <int kCtaGroup, int BN, bool kNV>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb,
+                const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
   using Cfg = GemmCfg<kCtaGroup, BN, kNV>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ACC = Cfg::ACC_STAGES;
@@ -93,16 +103,15 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   // 1024-byte alignment (128B swizzle atoms); identical offset in both CTAs of a pair
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  // barrier map (8 bytes each)
+  const uint32_t stg_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = stg_base + Cfg::STG_TOTAL;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto peer_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };          // leader only: peer CTA's stage landed
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + ACC + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 2 * ACC);
-  volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 2 * ACC));
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STG_TOTAL + 8 * (2 * STAGES + 2 * ACC));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -116,14 +125,16 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_a);
     prefetch_tensormap(&tmap_b);
+    prefetch_tensormap(&tmap_sfa);
+    prefetch_tensormap(&tmap_sfb);
+    prefetch_tensormap(&tmap_d);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-      mbar_init(peer_bar(s), 1);
+      mbar_init(full_bar(s), 1);     // one arrive.expect_tx by the leader's producer; bytes from both CTAs
+      mbar_init(empty_bar(s), 1);    // one tcgen05.commit (multicast to both CTAs)
     }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4 * kCtaGroup);   // 4 epilogue warps per CTA arrive on the leader's barrier
+      mbar_init(tempty_bar(a), kEpiWarps * kCtaGroup);   // every epilogue warp of the pair arrives on the leader's
     }
     fence_mbar_init();
   }
@@ -134,50 +145,42 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   tc_fence_before();
   if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
+  // shfl from lane 0: lets the compiler treat the TMEM base as warp-uniform (uniform-datapath operands)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_gen, 0);
   const uint32_t tmem_sfa = tmem_base + ACC * BN;
   const uint32_t tmem_sfb = tmem_sfa + Cfg::SFA_COLS;
 
   // ------------------------------------------------------------------ roles
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop with warp-uniform values; one elected lane issues.  (Issuing from a
+    // divergent `lane == 0` branch makes the compiler wrap every TMA / tcgen05 op in an R2UR waterfall loop.)
+    {
+      const bool elected = elect_one();
       int stage = 0;
       uint32_t phase = 0;
+      // completion goes to the leader's barrier (own barrier when kCtaGroup == 1)
+      const uint32_t full0 = (kCtaGroup == 2) ? mapa(bar_base, 0) : bar_base;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
         const int m0 = (tm * kCtaGroup + (int)cta_rank) * BM;            // this CTA's A rows
         const int n0 = tn * BN;
         const int nb0 = n0 + (int)cta_rank * Cfg::B_ROWS;                // this CTA's B rows
-        const int sfa_rb = m0 / 128;
-        const int sfb_rb0 = n0 / 128;
         for (int kt = 0; kt < p.k_tiles; ++kt) {
-          mbar_wait(empty_bar(stage), phase ^ 1, 1);
+          mbar_wait(bar_base + 8u * (STAGES + stage), phase ^ 1, 1);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           const uint32_t ssfa = sb + Cfg::B_BYTES;
           const uint32_t ssfb = ssfa + Cfg::SFA_BYTES;
-          // scale blocks available for this k-tile (K tail: fewer than SFKB)
-          int kb_avail = p.sf_col_blocks - kt * SFKB;
-          if (kb_avail > SFKB) kb_avail = SFKB;
-          uint32_t tx = Cfg::A_BYTES + Cfg::B_BYTES;
-          const bool sfa_ok = sfa_rb < p.sfa_row_blocks;
-          if (sfa_ok) tx += kb_avail * 512;
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb)
-            if (sfb_rb0 + nb < p.sfb_row_blocks) tx += kb_avail * 512;
-          mbar_arrive_expect_tx(full_bar(stage), tx);
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kt * BK_BYTES, m0);
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kt * BK_BYTES, nb0);
-          if (sfa_ok)
-            bulk_load_1d(ssfa, p.sfa + ((int64_t)sfa_rb * p.sf_col_blocks + (int64_t)kt * SFKB) * 512, kb_avail * 512,
-                         full_bar(stage));
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb)
-            if (sfb_rb0 + nb < p.sfb_row_blocks)
-              bulk_load_1d(ssfb + nb * SFKB * 512,
-                           p.sfb + ((int64_t)(sfb_rb0 + nb) * p.sf_col_blocks + (int64_t)kt * SFKB) * 512,
-                           kb_avail * 512, full_bar(stage));
+          const uint32_t fb = full0 + 8u * stage;
+          if (elected) {
+            if (is_leader) mbar_arrive_expect_tx(bar_base + 8u * stage, Cfg::TX_BYTES);
+            tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, kt * BK_BYTES, m0);
+            tma_load_2d<kCtaGroup>(sb, &tmap_b, fb, kt * BK_BYTES, nb0);
+            tma_load_3d<kCtaGroup>(ssfa, &tmap_sfa, fb, 0, kt * SFKB, m0 / 128);
+            tma_load_3d<kCtaGroup>(ssfb, &tmap_sfb, fb, 0, kt * SFKB, n0 / 128);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -185,79 +188,82 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (warp == 1) {
     if (is_leader) {
       // ===================== MMA issuer =====================
-      if (lane == 0) {
-        constexpr uint32_t idesc_base = make_idesc_fp4(BM * kCtaGroup, BN, !kNV);
-        int stage = 0;
-        uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-          const int tn = tile / p.tiles_m;
-          const int n0 = tn * BN;
-          const uint32_t sfb_shift = (uint32_t)((n0 % 128) / 32);     // column shift inside the first SFB block
-          mbar_wait<kCtaGroup == 2>(tempty_bar(acc), acc_phase ^ 1, 2);
+      const bool elected = elect_one();   // whole warp runs the (uniform) loop; one lane issues
+      // One thread issues every tcgen05 op, so its own dependent-ALU chain is on the critical path: all
+      // descriptors are pre-split into a constant high word and a low word that is one add away per op.
+      // (Measured: issuing the scale copies of k-tile g+1 ahead of the MMAs of k-tile g is SLOWER -- the
+      // tensor pipe runs cp/mma in order -- so the order is cp(g), mma(g).)
+      constexpr uint32_t idesc_base = make_idesc_fp4(BM * kCtaGroup, BN, !kNV);
+      constexpr uint32_t kDescHiAB = (1024u >> 4) | (1u << 14) | (kLayoutSw128 << 29);   // SBO 1024 B, version 1, 128B swizzle
+      constexpr uint32_t kDescHiSF = (128u >> 4) | (1u << 14);                            // SBO 128 B, version 1, no swizzle
+      constexpr uint32_t kStage16 = Cfg::STAGE_BYTES >> 4;
+      const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);                  // LBO = 16 B
+      const uint32_t sfa_lo0 = ((smem_base & 0x3FFFFu) >> 4) + ((Cfg::A_BYTES + Cfg::B_BYTES) >> 4);
+      auto mk = [](uint32_t lo, uint32_t hi) {
+        uint64_t d;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+        return d;
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int tn = tile / p.tiles_m;
+        const int n0 = tn * BN;
+        const uint32_t sfb_shift = (uint32_t)((n0 % 128) / 32);     // 0 or 2 columns into the first SFB block
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc * BN;
+        const uint32_t tsfb = tmem_sfb + sfb_shift;
+        int k_left = p.K;
+        for (int kt = 0; kt < p.k_tiles; ++kt, k_left -= BK) {
+          mbar_wait(bar_base + 8u * stage, phase, 3);
           tc_fence_after();
-          const uint32_t tmem_acc = tmem_base + acc * BN;
-          for (int kt = 0; kt < p.k_tiles; ++kt) {
-            mbar_wait(full_bar(stage), phase, 3);
-            if constexpr (kCtaGroup == 2) mbar_wait<true>(peer_bar(stage), phase, 4);
-            tc_fence_after();
-            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-            const uint32_t sb = sa + Cfg::A_BYTES;
-            const uint32_t ssfa = sb + Cfg::B_BYTES;
-            const uint32_t ssfb = ssfa + Cfg::SFA_BYTES;
-            // scales: smem -> TMEM (each 512-B block -> 4 columns, replicated over the 4 lane quarters)
+          const uint32_t a_lo = a_lo0 + stage * kStage16;
+          const uint32_t b_lo = a_lo + (Cfg::A_BYTES >> 4);
+          const uint32_t sfa_lo = sfa_lo0 + stage * kStage16;
+          const uint32_t sfb_lo = sfa_lo + (Cfg::SFA_BYTES >> 4);
+          if (elected) {
+          // scales: smem -> TMEM (each 512-B block -> 4 columns, replicated over the 4 lane quarters)
+#pragma unroll
+          for (int b = 0; b < SFKB; ++b)
+            tmem_cp_32x128b_warpx4<kCtaGroup>(tmem_sfa + b * 4, mk(sfa_lo + b * 32, kDescHiSF));
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
             for (int b = 0; b < SFKB; ++b)
-              tmem_cp_32x128b_warpx4<kCtaGroup>(tmem_sfa + b * 4, make_smem_desc(ssfa + b * 512, 0, 128, kLayoutNone));
+              tmem_cp_32x128b_warpx4<kCtaGroup>(tmem_sfb + b * (4 * NB) + nb * 4,
+                                                mk(sfb_lo + (nb * SFKB + b) * 32, kDescHiSF));
+          // 4 MMAs of K = 64 (32 bytes = 2 x 16 B along the swizzled row each); K tail issues fewer
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-              for (int b = 0; b < SFKB; ++b)
-                tmem_cp_32x128b_warpx4<kCtaGroup>(tmem_sfb + b * (4 * NB) + nb * 4,
-                                                  make_smem_desc(ssfb + (nb * SFKB + b) * 512, 0, 128, kLayoutNone));
-            // 4 MMAs of K = 64 (32 bytes along the swizzled row each)
-            int kblocks = (p.K - kt * BK + 63) / 64;
-            if (kblocks > 4) kblocks = 4;
-            const uint64_t adesc = make_smem_desc(sa, 16, 1024, kLayoutSw128);
-            const uint64_t bdesc = make_smem_desc(sb, 16, 1024, kLayoutSw128);
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb) {
-              if (kb < kblocks) {
-                const uint32_t chunk = kNV ? kb : (kb >> 1);
-                const uint32_t sf_id = kNV ? 0u : (uint32_t)((kb & 1) * 2);
-                mma_fp4_block_scaled<kCtaGroup, kNV>(tmem_acc, adesc + (uint64_t)(kb * 2), bdesc + (uint64_t)(kb * 2),
-                                                     idesc_with_sf_id(idesc_base, sf_id, sf_id), tmem_sfa + chunk * 4,
-                                                     tmem_sfb + chunk * (4 * NB) + sfb_shift,
-                                                     (kt > 0 || kb > 0) ? 1u : 0u);
-              }
+          for (int kb = 0; kb < 4; ++kb) {
+            if (k_left > kb * 64) {
+              constexpr uint32_t dummy = 0; (void)dummy;
+              const uint32_t chunk = kNV ? kb : (kb >> 1);
+              const uint32_t sf_id = kNV ? 0u : (uint32_t)((kb & 1) * 2);
+              mma_fp4_block_scaled<kCtaGroup, kNV>(tmem_acc, mk(a_lo + kb * 2, kDescHiAB), mk(b_lo + kb * 2, kDescHiAB),
+                                                   idesc_base | (sf_id << 4) | (sf_id << 29), tmem_sfa + chunk * 4,
+                                                   tsfb + chunk * (4 * NB), (kt > 0 || kb > 0) ? 1u : 0u);
             }
-            tc_commit<kCtaGroup>(empty_bar(stage));              // stage free once these MMAs have read it
-            if (kt == p.k_tiles - 1) tc_commit<kCtaGroup>(tfull_bar(acc));   // accumulator complete
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
-        }
-      }
-    } else {
-      // ===================== peer relay (2-CTA only) =====================
-      if (lane == 0) {
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-          for (int kt = 0; kt < p.k_tiles; ++kt) {
-            mbar_wait(full_bar(stage), phase, 5);
-            mbar_arrive_cluster(mapa(peer_bar(stage), 0));
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          tc_commit<kCtaGroup>(bar_base + 8u * (STAGES + stage));              // stage free once these MMAs have read it
+          if (kt == p.k_tiles - 1) tc_commit<kCtaGroup>(tfull_bar(acc));   // accumulator complete
           }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                        // which column half of the tile
+    const int col0 = half * Cfg::EPI_COLS;
     const float alpha = __ldg(p.alpha);
-    const bool vec_ok = (p.N % 8) == 0;
+    const uint32_t stg = stg_base + ew * Cfg::STG_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty_leader = (kCtaGroup == 2) ? mapa(tempty_bar(0), 0) : tempty_bar(0);
@@ -265,47 +271,66 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
       const int m0 = (tm * kCtaGroup + (int)cta_rank) * BM;
       const int n0 = tn * BN;
-      const int row = m0 + q * 32 + lane;
       mbar_wait(tfull_bar(acc), acc_phase, 6);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      __nv_bfloat16* drow = p.d + (int64_t)row * p.N + n0;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c, r);
+      const uint32_t taddr = tmem_base + acc * BN + col0 + ((uint32_t)(q * 32) << 16);
+      // drain this warp's 32 x EPI_COLS slice of the accumulator into registers, then release TMEM at once
+      uint32_t r[Cfg::EPI_COLS];
+      if (!(p.flags & 2)) {
+#pragma unroll
+        for (int j = 0; j < Cfg::EPI_COLS / 32; ++j) tmem_ld_32x32b_x32(taddr + j * 32, r + j * 32);
         tmem_ld_wait();
-        if (c + 32 >= BN) {
-          // all of this warp's TMEM reads for the tile are done -> release the accumulator
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (kCtaGroup == 2) mbar_arrive_cluster(tempty_leader + 8u * acc);
-            else mbar_arrive(tempty_bar(acc));
-          }
-        }
-        if (row < p.M) {
-          uint32_t packed[16];
+      } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float lo = __uint_as_float(r[2 * i]) * alpha;
-            const float hi = __uint_as_float(r[2 * i + 1]) * alpha;
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-            packed[i] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          if (vec_ok) {
+        for (int i = 0; i < Cfg::EPI_COLS; ++i) r[i] = 0;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCtaGroup == 2) mbar_arrive_cluster(tempty_leader + 8u * acc);
+        else mbar_arrive(tempty_bar(acc));
+      }
+      if (!(p.flags & 1)) {
+        if (p.tma_store) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              if (n0 + c + v * 8 < p.N)
-                *reinterpret_cast<uint4*>(drow + c + v * 8) =
-                    make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+          for (int ch = 0; ch < Cfg::EPI_NCHUNK; ++ch) {
+            // staging buffer must have been read by the previous TMA store
+            if (lane == 0) bulk_wait_group_read<0>();
+            __syncwarp();
+            constexpr int PIECES = Cfg::EPI_CHUNK / 8;   // 16-byte pieces per staged row (8 or 4)
+#pragma unroll
+            for (int jj = 0; jj < PIECES; ++jj) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float lo = __uint_as_float(r[ch * Cfg::EPI_CHUNK + jj * 8 + 2 * e]) * alpha;
+                const float hi = __uint_as_float(r[ch * Cfg::EPI_CHUNK + jj * 8 + 2 * e + 1]) * alpha;
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                w[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              // hardware swizzle of the store tensor map: 128B rows -> chunk ^= row % 8; 64B rows -> chunk ^= (row / 2) % 4
+              const int phys = (Cfg::EPI_CHUNK == 64) ? (jj ^ (lane & 7)) : (jj ^ ((lane >> 1) & 3));
+              const uint32_t addr = stg + lane * (Cfg::EPI_CHUNK * 2) + phys * 16;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                           : "memory");
             }
-          } else {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_d, stg, n0 + col0 + ch * Cfg::EPI_CHUNK, m0 + q * 32);
+              bulk_commit_group();
+            }
+          }
+        } else {
+          // direct stores (row pitch not a multiple of 16 bytes, i.e. N % 8 != 0): thread = row
+          const int row = m0 + q * 32 + lane;
+          if (row < p.M) {
+            uint16_t* drow = reinterpret_cast<uint16_t*>(p.d) + (int64_t)row * p.N + n0 + col0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (n0 + c + i < p.N) {
-                const uint32_t w = packed[i >> 1];
-                reinterpret_cast<uint16_t*>(drow)[c + i] = (uint16_t)((i & 1) ? (w >> 16) : (w & 0xffffu));
+            for (int i = 0; i < Cfg::EPI_COLS; ++i) {
+              if (n0 + col0 + i < p.N) {
+                __nv_bfloat16 h = __float2bfloat16_rn(__uint_as_float(r[i]) * alpha);
+                drow[i] = *reinterpret_cast<uint16_t*>(&h);
               }
             }
           }
@@ -313,6 +338,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait_group<0>();   // all TMA stores of this warp have completed
   }
 
   // ------------------------------------------------------------------ teardown
@@ -342,26 +368,50 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// [rows, row_bytes] uint8 tensor, box = [box_rows, 128 bytes], 128B swizzle, zero fill out of bounds
-static int make_operand_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t row_bytes, int box_rows) {
+static int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* ptr, const cuuint64_t* dims,
+                  const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapSwizzle sw, const char* what) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
     return B200Q_ECUDA;
   }
-  cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)BK_BYTES, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld row_bytes=%lld box_rows=%d)", (int)r,
-              (long long)rows, (long long)row_bytes, box_rows);
+    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
     return B200Q_ECUDA;
   }
   return 0;
+}
+
+// [rows, row_bytes] uint8 operand, box = [box_rows, 128 bytes], 128B swizzle, zero fill out of bounds
+static int make_operand_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t row_bytes, int box_rows,
+                             const char* what) {
+  cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)BK_BYTES, (cuuint32_t)box_rows};
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, what);
+}
+
+// blocked scale buffer as a 3-D tensor {128 x u32 (one 512-B block), col_blocks, row_blocks};
+// box = {128, kblocks, rblocks}; out-of-range blocks read as zero (scale 2^-127 / 0.0: never NaN)
+static int make_sf_tmap(CUtensorMap* tm, const void* ptr, int64_t row_blocks, int64_t col_blocks, int box_kb,
+                        int box_rb, const char* what) {
+  cuuint64_t dims[3] = {128, (cuuint64_t)col_blocks, (cuuint64_t)row_blocks};
+  cuuint64_t strides[2] = {512, (cuuint64_t)col_blocks * 512};
+  cuuint32_t box[3] = {128, (cuuint32_t)box_kb, (cuuint32_t)box_rb};
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, what);
+}
+
+// D [M, N] bf16 row-major, box = [32 rows, chunk cols], swizzle matching the staging layout
+static int make_d_tmap(CUtensorMap* tm, const void* ptr, int64_t M, int64_t N, int chunk) {
+  cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)N * 2};
+  cuuint32_t box[2] = {(cuuint32_t)chunk, 32};
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box,
+                chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "D");
 }
 
 template <int kCtaGroup, int BN, bool kNV>
@@ -374,24 +424,32 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
     B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  CUtensorMap ta, tb;
-  int rc = make_operand_tmap(&ta, A, M, K / 2, BM);
-  if (rc) return rc;
-  rc = make_operand_tmap(&tb, B, N, K / 2, Cfg::B_ROWS);
-  if (rc) return rc;
-  GemmParams p;
   const int group = kNV ? 16 : 32;
-  p.sfa = (const uint8_t*)SFA;
-  p.sfb = (const uint8_t*)SFB;
+  const int64_t sf_col_blocks = ceil_div(ceil_div(K, group), 4);
+  CUtensorMap ta, tb, tsa, tsb, td;
+  int rc;
+  if ((rc = make_operand_tmap(&ta, A, M, K / 2, BM, "A"))) return rc;
+  if ((rc = make_operand_tmap(&tb, B, N, K / 2, Cfg::B_ROWS, "B"))) return rc;
+  if ((rc = make_sf_tmap(&tsa, SFA, ceil_div(M, 128), sf_col_blocks, Cfg::SFKB, 1, "SFA"))) return rc;
+  if ((rc = make_sf_tmap(&tsb, SFB, ceil_div(N, 128), sf_col_blocks, Cfg::SFKB, Cfg::NB, "SFB"))) return rc;
+  GemmParams p;
   p.alpha = alpha;
   p.d = (__nv_bfloat16*)D;
   p.M = M; p.N = N; p.K = K;
   p.tiles_m = (int)ceil_div(M, BM * kCtaGroup);
   p.tiles_n = (int)ceil_div(N, BN);
   p.k_tiles = (int)ceil_div(K, BK);
-  p.sf_col_blocks = (int)ceil_div(ceil_div(K, group), 4);
-  p.sfa_row_blocks = (int)ceil_div(M, 128);
-  p.sfb_row_blocks = (int)ceil_div(N, 128);
+  p.tma_store = (N % 8 == 0) ? 1 : 0;
+  {
+    const char* f = getenv("B200Q_GEMM_DEBUG_FLAGS");
+    p.flags = f ? atoi(f) : 0;
+    if (p.flags & 4) p.tma_store = 0;
+  }
+  if (p.tma_store) {
+    if ((rc = make_d_tmap(&td, D, M, N, Cfg::EPI_CHUNK))) return rc;
+  } else {
+    td = ta;  // unused
+  }
   const int total = p.tiles_m * p.tiles_n;
   int clusters = num_sms() / kCtaGroup;
   if (clusters > total) clusters = total;
@@ -407,7 +465,7 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tsa, tsb, td, p));
   return 0;
 }
 
@@ -418,8 +476,10 @@ static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B
   if (cta_group == CG && block_n == BNV) return launch_gemm<CG, BNV, kNV>(A, B, SFA, SFB, alpha, D, M, N, K, s);
   B200Q_CASE(1, 64)
   B200Q_CASE(1, 128)
+  B200Q_CASE(1, 192)
   B200Q_CASE(1, 256)
   B200Q_CASE(2, 128)
+  B200Q_CASE(2, 192)
   B200Q_CASE(2, 256)
 #undef B200Q_CASE
   set_error("unsupported GEMM configuration cta_group=%d block_n=%d", cta_group, block_n);
@@ -443,9 +503,23 @@ extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA,
                 "A, B, SFA, SFB must be 16-byte aligned");
   B200Q_REQUIRE(((uintptr_t)D_bf16 & 15) == 0 || (N % 8) != 0, "D must be 16-byte aligned");
   if (cta_group == 0 || block_n == 0) {
-    // heuristic: small M streams weights with many narrow tiles; large M uses the widest tile
-    if (M <= 128) { cta_group = 1; block_n = 64; }
-    else { cta_group = 1; block_n = 128; }
+    // heuristic (measured on B200, profiles/): small M streams weights with single-CTA tiles; otherwise CTA pairs
+    // (256-row tiles halve the B traffic per flop) with the tile width that minimises rounds x width.
+    if (M <= 128) { cta_group = 1; block_n = 128; }
+    else if (M <= 256 && N <= 4096) { cta_group = 1; block_n = 128; }
+    else {
+      cta_group = 2;
+      const int64_t clusters = num_sms() / 2;
+      const int64_t tm = ceil_div(M, 256);
+      int64_t best = -1;
+      const int cands[3] = {256, 192, 128};
+      for (int i = 0; i < 3; ++i) {
+        const int bn = cands[i];
+        const int64_t rounds = ceil_div(tm * ceil_div(N, bn), clusters);
+        const int64_t cost = rounds * (bn + 16);     // +16: fixed per-tile cost (accumulator hand-off)
+        if (best < 0 || cost < best) { best = cost; block_n = bn; }
+      }
+    }
   }
   cudaStream_t s = (cudaStream_t)stream;
   if (kind == B200Q_KIND_NVF4) return dispatch_cfg<true>(cta_group, block_n, A, B, SFA, SFB, alpha_dev, D_bf16, M, N, K, s);

@@ -112,12 +112,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
-// 2-D tiled load global -> this CTA's shared memory, completing on this CTA's mbarrier
+// 2-D / 3-D tiled loads global -> this CTA's shared memory.  kCtaGroup == 2: the completion may be signalled on
+// the mbarrier of EITHER CTA of the pair (bar is then a shared::cluster address, e.g. mapa(bar, 0) = the leader's).
+template <int kCtaGroup = 1>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
+  if constexpr (kCtaGroup == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+template <int kCtaGroup = 1>
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1,
+                                            int32_t c2) {
+  if constexpr (kCtaGroup == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
 }
 // 1-D bulk copy global -> shared (size multiple of 16, both 16-byte aligned)
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

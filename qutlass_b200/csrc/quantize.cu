@@ -99,13 +99,32 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- 1. rotation-structure check: R == c * (-1)^popcount(k & n) ?  (bitwise, bf16)
+  // first tile's loads go out before anything else (they overlap the rotation check)
+  uint4* stage = s_stage[warp];
+  const int64_t n_units = p.n_chunks * 4;
+  uint4 nxt[4];
+  {
+    const int64_t tile0 = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t u = tile0 * 128 + i * 32 + lane;
+      nxt[i] = (tile0 < p.n_tiles && u < n_units) ? __ldg(p.x + u) : make_uint4(0, 0, 0, 0);
+    }
+  }
+
+  // ---- 1. rotation-structure check: R == c * (-1)^popcount(k & n) ?  (bitwise, bf16; 16-byte loads)
   const unsigned short c_bits = reinterpret_cast<const unsigned short*>(p.rot)[0];
   bool ok = true;
-  for (int idx = threadIdx.x; idx < HAD * HAD; idx += kThreads) {
-    const int k = idx / HAD, n = idx % HAD;
-    const unsigned short want = (__popc(k & n) & 1) ? (c_bits ^ 0x8000u) : c_bits;
-    ok = ok && (reinterpret_cast<const unsigned short*>(p.rot)[idx] == want);
+  for (int u = threadIdx.x; u < HAD * HAD / 8; u += kThreads) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(p.rot) + u);
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    const int k = (u * 8) / HAD, n0 = (u * 8) % HAD;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned short got = (unsigned short)(ww[j >> 1] >> ((j & 1) * 16));
+      const unsigned short want = (__popc(k & (n0 + j)) & 1) ? (unsigned short)(c_bits ^ 0x8000u) : c_bits;
+      ok = ok && (got == want);
+    }
   }
   const bool is_hadamard = __syncthreads_and(ok) != 0;
   const float c_scale = __bfloat162float(p.rot[0]);
@@ -117,17 +136,20 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
   }
 
   // ---- 2. stream warp-tiles
-  uint4* stage = s_stage[warp];
   for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < p.n_tiles;
        tile += (int64_t)gridDim.x * kWarpsPerCta) {
-    const int64_t unit0 = tile * 128;            // first 16-B unit of this tile
-    const int64_t n_units = p.n_chunks * 4;
-    // coalesced loads, swizzled staging
+    // software prefetch: the next tile's 4 coalesced 16-byte loads are issued before this tile is processed
     uint4 ld[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t u = unit0 + i * 32 + lane;
-      ld[i] = (u < n_units) ? __ldg(p.x + u) : make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < 4; ++i) ld[i] = nxt[i];
+    {
+      const int64_t ntile = tile + (int64_t)gridDim.x * kWarpsPerCta;
+      const int64_t unit0 = ntile * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t u = unit0 + i * 32 + lane;
+        nxt[i] = (ntile < p.n_tiles && u < n_units) ? __ldg(p.x + u) : make_uint4(0, 0, 0, 0);
+      }
     }
     __syncwarp();
 #pragma unroll
@@ -312,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
 template <int HAD, bool NV, int METHOD, bool MASK>
 static int launch(const QuantParams& p, cudaStream_t stream) {
   int64_t ctas = ceil_div(p.n_tiles, kWarpsPerCta);
-  const int64_t max_ctas = (int64_t)num_sms() * 6;
+  const int64_t max_ctas = (int64_t)num_sms() * 4;   // 48 KB static smem -> 4 resident CTAs / SM: one persistent wave
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
   quantize_kernel<HAD, NV, METHOD, MASK><<<(unsigned)ctas, kThreads, 0, stream>>>(p);

@@ -1,0 +1,66 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads without a GPU and exports
+every symbol include/b200q.h declares, with the argument counts the Python binding assumes."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from qutlass_b200 import build
+    return build.build()
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "b200q.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"\b(int|int64_t|const char\*)\s+(b200q_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(3).strip()
+        n = 0 if args in ("void", "") else len([a for a in args.split(",") if a.strip()])
+        decls[m.group(2)] = n
+    return decls
+
+
+def test_header_declares_the_hot_path_entry_points():
+    d = _declared()
+    for name in ("b200q_quantize_mx", "b200q_quantize_nv", "b200q_swizzle_sf", "b200q_gemm_fp4",
+                 "b200q_gemm_fp4_cfg", "b200q_last_error", "b200q_abi_version", "b200q_linear_fp4_host",
+                 "b200q_linear_workspace_bytes"):
+        assert name in d, name
+
+
+def test_library_loads_and_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    for name in _declared():
+        assert hasattr(lib, name), f"{name} declared in include/b200q.h but not exported"
+
+
+def test_python_binding_signatures_match_header(lib_path):
+    from qutlass_b200 import _lib
+    d = _declared()
+    assert set(_lib.SIGNATURES) == set(d)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        assert len(args) == d[name], name
+    assert _lib.load().b200q_abi_version() == 1
+
+
+def test_no_libcuda_or_torch_link_dependency(lib_path):
+    """plain C-ABI: no torch types, and loadable on a box without the driver (cudart is static)."""
+    import subprocess
+    out = subprocess.run(["ldd", lib_path], capture_output=True, text=True).stdout
+    assert "libtorch" not in out and "libcuda.so" not in out and "libc10" not in out
+
+
+def test_product_never_imports_the_oracle():
+    """the oracle is test infrastructure: nothing under qutlass_b200/ (or the qutlass alias) may use it."""
+    for pkg in ("qutlass_b200", "qutlass"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dirpath, f)

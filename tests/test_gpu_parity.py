@@ -1,0 +1,388 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI
+(libb200q.so via qutlass_b200), against the CPU oracle on identical seeded inputs, against the
+committed golden fixtures generated from the reference's own test helpers, and -- at BASELINE.json's
+full sizes -- through size-independent properties.
+
+Tolerances (written here, from north_star and the reference's own tests):
+  * GEMM: bit-exact vs bf16(fp64 matmul of the dequantised operands) wherever fp32 accumulation is exact
+    (tests/mxfp4_test.py:237 `out.equal(...)`); otherwise |err| <= 2**-7 relative (north_star).
+  * quantise (floating point, rounding-boundary sensitive): mismatch fraction of dequantised values
+    <= 1e-4 for MX (tests/mxfp4_test.py:221) and <= 1e-2 for NV (reference bar is 1e-1, nvfp4_test.py:205).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("CUDA required", allow_module_level=True)
+
+import qutlass_b200 as Q  # noqa: E402
+from qutlass_b200 import _lib  # noqa: E402
+
+REL_TOL = 2.0 ** -7
+
+
+def _flat_sf(sf_t, rows, cols):
+    return H.u8_of(sf_t).reshape(-1)[: rows * cols].reshape(rows, cols)
+
+
+# ----------------------------------------------------------------------------- quantise
+@pytest.mark.parametrize("had", [32, 64, 128])
+@pytest.mark.parametrize("method", ["abs_max", "quest"])
+def test_quantize_mx_vs_oracle(had, method):
+    rows, k = 384, 2048
+    x = H.random_bf16((rows, k), seed=had)
+    R = O.hadamard_matrix(had)
+    ref = O.quantize_mx(x, R, method)
+    out = Q.fusedQuantizeMx(H.bf16_tensor_from_f32(x), H.bf16_tensor_from_f32(R), method=method,
+                            return_mask=(method == "quest"))
+    torch.cuda.synchronize()
+    cols = k // 32
+    assert out[1].shape == (384, 64) and out[1].dtype == torch.float8_e8m0fnu
+    assert out[0].shape == (rows, k // 2) and out[0].dtype == torch.uint8
+    sf = _flat_sf(out[1], rows, cols)
+    assert (sf != ref["sf"].reshape(rows, cols)).mean() <= 1e-4
+    dq = O.dequant_mx(H.u8_of(out[0]), sf)
+    dq_ref = O.dequant_mx(ref["q"].reshape(rows, -1), ref["sf"].reshape(rows, cols))
+    assert (dq != dq_ref).mean() <= 1e-4
+    if method == "quest":
+        mask = H.u8_of(out[2]).reshape(-1).view(np.uint32)
+        assert (mask != ref["mask"]).mean() <= 1e-4
+    # the blocked copy written by the same kernel == to_blocked(row-major) (no-op path) == CUDA swizzle kernel
+    blk_noop = H.u8_of(Q.to_blocked(out[1]))
+    np.testing.assert_array_equal(blk_noop, H.blocked_sf(sf))
+    fresh = out[1].clone()          # loses the attached buffer -> runs the swizzle kernel
+    np.testing.assert_array_equal(H.u8_of(Q.to_blocked(fresh, use_triton_kernel=True)), blk_noop)
+
+
+@pytest.mark.parametrize("had", [16, 32, 64, 128])
+@pytest.mark.parametrize("method", ["abs_max", "quest"])
+@pytest.mark.parametrize("gs", [1.0, 6.0])
+def test_quantize_nv_vs_oracle(had, method, gs):
+    rows, k = 256, 1024
+    x = H.random_bf16((rows, k), seed=100 + had)
+    R = O.hadamard_matrix(had)
+    ref = O.quantize_nv(x, R, gs, method)
+    gst = torch.tensor([gs], dtype=torch.float32, device="cuda")
+    q, sf_t = Q.fusedQuantizeNv(H.bf16_tensor_from_f32(x), H.bf16_tensor_from_f32(R), gst, method=method)
+    torch.cuda.synchronize()
+    cols = k // 16
+    assert sf_t.dtype == torch.float8_e4m3fn and sf_t.shape == (256, 64)
+    sf = _flat_sf(sf_t, rows, cols)
+    assert (sf != ref["sf"].reshape(rows, cols)).mean() <= 1e-3
+    dq = O.dequant_nv(H.u8_of(q), sf)
+    dq_ref = O.dequant_nv(ref["q"].reshape(rows, -1), ref["sf"].reshape(rows, cols))
+    assert (dq != dq_ref).mean() <= 1e-2
+    np.testing.assert_array_equal(H.u8_of(Q.to_blocked(sf_t)), H.blocked_sf(sf))
+
+
+@pytest.mark.parametrize("had", [32, 64, 128])
+@pytest.mark.parametrize("method", ["quest", "abs_max"])
+def test_quantize_mx_golden_reference_vectors(golden, had, method):
+    """GPU kernel vs the reference's fp64 test oracle output (golden), reference's own bar."""
+    x = O.bf16_from_bits(golden["mx_x_bits"])
+    R = O.bf16_from_bits(golden[f"had{had}_bits"])
+    tag = f"mx_h{had}_{'quest' if method == 'quest' else 'absmax'}"
+    q, sf_t = Q.fusedQuantizeMx(H.bf16_tensor_from_f32(x), H.bf16_tensor_from_f32(R), method=method)
+    torch.cuda.synchronize()
+    rows, k = x.shape
+    dq = O.dequant_mx(H.u8_of(q), _flat_sf(sf_t, rows, k // 32), alpha=1.0 if method == "quest" else 3.0)
+    assert (dq != golden[tag + "_dq"]).mean() <= 1e-4
+
+
+@pytest.mark.parametrize("had", [16, 32, 64, 128])
+def test_quantize_nv_golden_reference_vectors(golden, had):
+    x = O.bf16_from_bits(golden["mx_x_bits"])
+    R = O.bf16_from_bits(golden[f"had{had}_bits"])
+    gst = torch.tensor([6.0], dtype=torch.float32, device="cuda")
+    q, sf_t = Q.fusedQuantizeNv(H.bf16_tensor_from_f32(x), H.bf16_tensor_from_f32(R), gst)
+    torch.cuda.synchronize()
+    rows, k = x.shape
+    dq = O.dequant_nv(H.u8_of(q), _flat_sf(sf_t, rows, k // 16), alpha=6.0)
+    assert (dq != golden[f"nv_h{had}_dq"]).mean() <= 1e-2
+
+
+def test_quantize_edge_cases():
+    R32 = O.hadamard_matrix(32)
+    Rt = H.bf16_tensor_from_f32(R32)
+    # all-zero input: scale floor(1e-8) and all-zero codes; single row (M=1); leading batch dims; ragged K=96
+    z = torch.zeros(1, 4096, dtype=torch.bfloat16, device="cuda")
+    q, sf = Q.fusedQuantizeMx(z, Rt, method="abs_max")
+    torch.cuda.synchronize()
+    assert sf.shape == (128, 128)
+    ref = O.quantize_mx(np.zeros((1, 4096), np.float32), R32, "abs_max")
+    np.testing.assert_array_equal(_flat_sf(sf, 1, 128), ref["sf"].reshape(1, 128))
+    assert (O.e2m1_decode(O.unpack_e2m1(H.u8_of(q))) == 0).all()
+    # padding of the blocked buffer is zero-filled (pad rows never produce NaN scales)
+    blk = H.u8_of(Q.to_blocked(sf))
+    want = H.blocked_sf(ref["sf"].reshape(1, 128))
+    np.testing.assert_array_equal(blk, want)
+    # batch dims flattened like the reference (utils.py:141)
+    x = H.random_bf16((2, 5, 96), seed=5)
+    q, sf = Q.fusedQuantizeMx(H.bf16_tensor_from_f32(x), Rt, method="quest")
+    torch.cuda.synchronize()
+    assert q.shape == (2, 5, 48) and sf.shape == (128, 4)
+    ref = O.quantize_mx(x, R32, "quest")
+    dq = O.dequant_mx(H.u8_of(q).reshape(10, 48), _flat_sf(sf, 10, 3))
+    assert (dq != O.dequant_mx(ref["q"].reshape(10, 48), ref["sf"].reshape(10, 3))).mean() <= 1e-4
+    # arbitrary (non-Hadamard) runtime rotation: identity, as quartet_test.py:380 passes
+    eye = torch.eye(32, dtype=torch.bfloat16, device="cuda")
+    x = H.random_bf16((64, 256), seed=6)
+    q, sf = Q.fusedQuantizeMx(H.bf16_tensor_from_f32(x), eye, method="abs_max")
+    torch.cuda.synchronize()
+    ref = O.quantize_mx(x, np.eye(32, dtype=np.float32), "abs_max")
+    dq = O.dequant_mx(H.u8_of(q), _flat_sf(sf, 64, 8))
+    np.testing.assert_array_equal(dq, O.dequant_mx(ref["q"].reshape(64, 128), ref["sf"].reshape(64, 8)))
+
+
+def test_error_behaviour():
+    R = torch.eye(32, dtype=torch.bfloat16, device="cuda")
+    x = torch.zeros(4, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(ValueError):
+        Q.fusedQuantizeMx(x, R, method="nope")
+    with pytest.raises(ValueError):
+        Q.fusedQuantizeMx(x, R, method="abs_max", return_mask=True)
+    with pytest.raises(RuntimeError, match="A must be bf16"):
+        Q.fusedQuantizeMx(x.float(), R)
+    with pytest.raises(RuntimeError, match="Unsupported rotation size"):
+        Q.fusedQuantizeMx(x, torch.eye(8, dtype=torch.bfloat16, device="cuda"))
+    with pytest.raises(RuntimeError, match="square"):
+        Q.fusedQuantizeMx(x, torch.zeros(32, 16, dtype=torch.bfloat16, device="cuda"))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Q.fusedQuantizeMx(x.cpu(), R)
+    a = torch.zeros(4, 32, dtype=torch.uint8, device="cuda")
+    sf = torch.zeros(512, dtype=torch.float8_e8m0fnu, device="cuda")
+    al = torch.ones(1, device="cuda")
+    with pytest.raises(RuntimeError, match="A_sf must be float8_e8m0fnu"):
+        Q.matmul_mxf4_bf16_tn(a, a, sf.view(torch.float8_e4m3fn), sf, al)
+    with pytest.raises(RuntimeError, match="Inner dimensions"):
+        Q.matmul_mxf4_bf16_tn(a, torch.zeros(4, 64, dtype=torch.uint8, device="cuda"), sf, sf, al)
+    with pytest.raises(ValueError):
+        Q.matmul_mxf4_bf16_tn(a, a, sf, sf, al, backend="bogus")
+    with pytest.raises(ImportError):
+        Q.matmul_mxf4_bf16_tn(a, a, sf, sf, al, backend="flashinfer")
+    with pytest.raises(NotImplementedError):
+        Q.matmul_mxf8_bf16_tn(a, a, sf, sf, al)
+    # C-ABI error convention: negative code + message
+    lib = _lib.load()
+    assert lib.b200q_gemm_fp4(None, None, None, None, None, None, 1, 1, 32, 0, None) < 0
+    assert b"null" in lib.b200q_last_error()
+
+
+# ----------------------------------------------------------------------------- GEMM
+CFGS = [(0, 0), (1, 64), (1, 128), (1, 192), (1, 256), (2, 128), (2, 192), (2, 256)]
+
+
+@pytest.mark.parametrize("kind", ["mx", "nv"])
+@pytest.mark.parametrize("cfg", CFGS)
+@pytest.mark.parametrize("shape", [(128, 128, 256), (256, 512, 1024), (504, 504, 2048), (1, 504, 4096),
+                                   (16, 1000, 2176), (130, 72, 96), (5, 100, 64)])
+def test_gemm_bit_exact_vs_oracle(kind, cfg, shape):
+    m, n, k = shape
+    aq, asf = H.random_fp4_operand(m, k, kind, seed=m + 1, sf_mode="narrow")
+    bq, bsf = H.random_fp4_operand(n, k, kind, seed=n + 2, sf_mode="narrow")
+    want = H.gemm_oracle_bits(aq, asf, bq, bsf, kind, 1.0)
+    got = H.run_gemm(aq, asf, bq, bsf, kind, 1.0, cfg=cfg)
+    mism, rel = H.compare_bits(got, want)
+    if kind == "mx":
+        assert mism == 0.0, (mism, rel)       # pow2 scales within +-1: fp32 accumulation is exact
+    else:
+        assert rel <= REL_TOL and mism <= 1e-3, (mism, rel)
+
+
+@pytest.mark.parametrize("kind", ["mx", "nv"])
+def test_gemm_wide_dynamic_range_within_tolerance(kind):
+    m, n, k = 300, 1000, 2176
+    aq, asf = H.random_fp4_operand(m, k, kind, seed=7, sf_mode="wide")
+    bq, bsf = H.random_fp4_operand(n, k, kind, seed=8, sf_mode="wide")
+    dq = O.dequant_mx if kind == "mx" else O.dequant_nv
+    a_dq, b_dq = dq(aq, asf), dq(bq, bsf)
+    want = a_dq @ b_dq.T
+    got = O.bf16_from_bits(H.run_gemm(aq, asf, bq, bsf, kind, 1.0)).astype(np.float64)
+    # fp32 accumulation: error bounded relative to the magnitude of the terms, not of a cancelling sum
+    scale = np.abs(a_dq) @ np.abs(b_dq).T
+    assert (np.abs(got - want) <= REL_TOL * np.abs(want) + 2.0 ** -20 * scale).all()
+
+
+def test_gemm_config0_golden(golden):
+    """BASELINE.json configs[0] (M=N=K=256 MXFP4 abs_max) -- the reference-generated golden output."""
+    got = H.run_gemm(golden["c0_a_q"], golden["c0_a_s"], golden["c0_b_q"], golden["c0_b_s"], "mx", 1.0)
+    np.testing.assert_array_equal(got, golden["c0_out_bits"])
+
+
+def test_gemm_nv_golden(golden):
+    got = H.run_gemm(golden["nvg_a_q"], golden["nvg_a_s"], golden["nvg_b_q"], golden["nvg_b_s"], "nv", 1.0)
+    np.testing.assert_array_equal(got, golden["nvg_out_bits"])
+
+
+@pytest.mark.parametrize("had,method,shape", [(32, "abs_max", (1, 504, 4096)), (64, "abs_max", (1, 504, 4096)),
+                                              (128, "abs_max", (1, 504, 4096)), (32, "quest", (504, 504, 2048)),
+                                              (128, "quest", (504, 504, 2048))])
+def test_reference_style_quantize_then_gemm_mx(had, method, shape):
+    """mirrors tests/mxfp4_test.py:208-269: randn*25 -> fusedQuantizeMx -> to_blocked -> matmul, bit-exact
+    against the fp64 matmul of the dequantised operands."""
+    m, n, k = shape
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(had))
+    a = H.bf16_tensor_from_f32(H.random_bf16((m, k), seed=21))
+    b = H.bf16_tensor_from_f32(H.random_bf16((n, k), seed=22))
+    a_q, a_sf = Q.fusedQuantizeMx(a, R, method=method)
+    b_q, b_sf = Q.fusedQuantizeMx(b, R, method=method)
+    alpha = torch.tensor([1.0], device="cuda")
+    out = Q.matmul_mxf4_bf16_tn(a_q, b_q, Q.to_blocked(a_sf, use_triton_kernel=True),
+                                Q.to_blocked(b_sf, use_triton_kernel=True), alpha)
+    torch.cuda.synchronize()
+    a_dq = O.dequant_mx(H.u8_of(a_q), H.u8_of(a_sf)[:m, : k // 32])
+    b_dq = O.dequant_mx(H.u8_of(b_q), H.u8_of(b_sf)[:n, : k // 32])
+    np.testing.assert_array_equal(H.bf16_bits_of(out), O.gemm_ref(a_dq, b_dq, 1.0))
+
+
+@pytest.mark.parametrize("had", [16, 128])
+def test_reference_style_quantize_then_gemm_nv(had):
+    """mirrors tests/nvfp4_test.py:190-224 (smaller n)."""
+    m, n, k = 504, 1024, 4096
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(had))
+    gs = torch.tensor([6.0], device="cuda")
+    a = H.bf16_tensor_from_f32(H.random_bf16((m, k), seed=31))
+    b = H.bf16_tensor_from_f32(H.random_bf16((n, k), seed=32))
+    a_q, a_sf = Q.fusedQuantizeNv(a, R, gs)
+    b_q, b_sf = Q.fusedQuantizeNv(b, R, gs)
+    alpha = torch.tensor([1.0], device="cuda")
+    out = Q.matmul_nvf4_bf16_tn(a_q, b_q, Q.to_blocked(a_sf, True).view(-1, k // 16),
+                                Q.to_blocked(b_sf, True).view(-1, k // 16), alpha)
+    torch.cuda.synchronize()
+    a_dq = O.dequant_nv(H.u8_of(a_q), H.u8_of(a_sf)[:m, : k // 16])
+    b_dq = O.dequant_nv(H.u8_of(b_q), H.u8_of(b_sf)[:n, : k // 16])
+    mism, rel = H.compare_bits(H.bf16_bits_of(out), O.gemm_ref(a_dq, b_dq, 1.0))
+    assert rel <= REL_TOL and mism <= 1e-3, (mism, rel)
+
+
+def test_llama_shapes_small_batch():
+    """subset of tests/mxfp4_test.py:272-299 (rand*25, quest, batch 1 and 16)."""
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(64))
+    for (k, n) in ((4096, 4096), (4096, 14336), (8192, 1024)):
+        for m in (1, 16):
+            a = H.bf16_tensor_from_f32(H.random_bf16((m, k), seed=k + m, dist="rand"))
+            b = H.bf16_tensor_from_f32(H.random_bf16((n, k), seed=n + 3, dist="rand"))
+            a_q, a_sf = Q.fusedQuantizeMx(a, R, method="quest")
+            b_q, b_sf = Q.fusedQuantizeMx(b, R, method="quest")
+            out = Q.matmul_mxf4_bf16_tn(a_q, b_q, Q.to_blocked(a_sf), Q.to_blocked(b_sf),
+                                        torch.tensor([1.0], device="cuda"))
+            torch.cuda.synchronize()
+            a_dq = O.dequant_mx(H.u8_of(a_q), H.u8_of(a_sf)[:m, : k // 32])
+            b_dq = O.dequant_mx(H.u8_of(b_q), H.u8_of(b_sf)[:n, : k // 32])
+            np.testing.assert_array_equal(H.bf16_bits_of(out), O.gemm_ref(a_dq, b_dq, 1.0))
+
+
+def test_torch_ops_schema_path():
+    """external integrations call torch.ops._qutlass_C directly (bindings.cpp:498-507)."""
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(32))
+    a = H.bf16_tensor_from_f32(H.random_bf16((128, 256), seed=41))
+    out = torch.empty(128, 128, dtype=torch.uint8, device="cuda")
+    sf = torch.empty(128, 8, dtype=torch.float8_e8m0fnu, device="cuda")
+    r = torch.ops._qutlass_C.fusedQuantizeMxAbsMax(a, R, out, sf)
+    q2, sf2 = Q.fusedQuantizeMx(a, R, method="abs_max")
+    torch.cuda.synchronize()
+    assert r[0].data_ptr() == out.data_ptr()
+    np.testing.assert_array_equal(H.u8_of(out), H.u8_of(q2))
+    np.testing.assert_array_equal(H.u8_of(sf), H.u8_of(sf2))
+    blk = Q.to_blocked(sf, True)
+    al = torch.ones(1, device="cuda")
+    d1 = torch.ops._qutlass_C.matmul_mxf4_bf16_tn(out, out, blk, blk, al)
+    d2 = Q.matmul_mxf4_bf16_tn(q2, q2, Q.to_blocked(sf2), Q.to_blocked(sf2), al)
+    assert torch.equal(d1, d2)
+
+
+def test_cuda_graph_capture():
+    """the reference benchmarks time everything under CUDA-graph capture (bench_mxfp4_sm100.py:216-226)."""
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(128))
+    a = H.bf16_tensor_from_f32(H.random_bf16((256, 1024), seed=51))
+    b = H.bf16_tensor_from_f32(H.random_bf16((384, 1024), seed=52))
+    b_q, b_sf = Q.fusedQuantizeMx(b, R, method="abs_max")
+    b_blk = Q.to_blocked(b_sf)
+    al = torch.ones(1, device="cuda")
+
+    def run():
+        a_q, a_sf = Q.fusedQuantizeMx(a, R, method="abs_max")
+        return Q.matmul_mxf4_bf16_tn(a_q, b_q, Q.to_blocked(a_sf, True), b_blk, al)
+
+    eager = run()
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        run()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = run()
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
+
+
+def test_linear_host_entry_point():
+    """b200q_linear_fp4_host (what bench.py's e2e leg calls) == the composed device path."""
+    m, n, k, had = 200, 640, 1024, 64
+    lib = _lib.load()
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(had))
+    w = H.bf16_tensor_from_f32(H.random_bf16((n, k), seed=61))
+    wq, wsf = Q.fusedQuantizeMx(w, R, method="abs_max")
+    wblk = Q.to_blocked(wsf)
+    x_host = torch.from_numpy(O.bf16_bits(H.random_bf16((m, k), seed=62)).astype(np.int16)).view(torch.bfloat16).pin_memory()
+    d_host = torch.empty(m, n, dtype=torch.bfloat16).pin_memory()
+    ws = torch.empty(lib.b200q_linear_workspace_bytes(m, n, k, 0), dtype=torch.uint8, device="cuda")
+    al = torch.ones(1, device="cuda")
+    _lib.check(lib.b200q_linear_fp4_host(x_host.data_ptr(), R.data_ptr(), wq.data_ptr(), wblk.data_ptr(), al.data_ptr(),
+                                         None, d_host.data_ptr(), ws.data_ptr(), m, n, k, had, 0,
+                                         torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    xq, xsf = Q.fusedQuantizeMx(x_host.cuda(), R, method="abs_max")
+    want = Q.matmul_mxf4_bf16_tn(xq, wq, Q.to_blocked(xsf), wblk, al)
+    torch.cuda.synchronize()
+    assert torch.equal(d_host.cuda(), want)
+
+
+# ----------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("kind", ["mx", "nv"])
+def test_full_size_properties(kind):
+    """BASELINE.json configs[1]/[2]: M=4096, N=14336, K=4096 -- too big for a full CPU oracle, so:
+    (a) a random sample of rows against the oracle, (b) tile-independence (row subset == same rows of the
+    full product), (c) alpha linearity (x2 is exact in bf16), (d) every kernel configuration agrees bit for bit."""
+    m, n, k = 4096, 14336, 4096
+    aq, asf = H.random_fp4_operand(m, k, kind, seed=71, sf_mode="narrow")
+    bq, bsf = H.random_fp4_operand(n, k, kind, seed=72, sf_mode="narrow")
+    full = H.run_gemm(aq, asf, bq, bsf, kind, 1.0)
+    rows = np.random.default_rng(0).choice(m, size=48, replace=False)
+    want = H.gemm_oracle_bits(aq[rows], asf[rows], bq, bsf, kind, 1.0)
+    mism, rel = H.compare_bits(full[rows], want)
+    if kind == "mx":
+        assert mism == 0.0
+    else:
+        assert rel <= REL_TOL and mism <= 1e-3
+    sub = H.run_gemm(aq[256:384], asf[256:384], bq, bsf, kind, 1.0)
+    np.testing.assert_array_equal(sub, full[256:384])
+    twice = H.run_gemm(aq, asf, bq, bsf, kind, 2.0)
+    np.testing.assert_array_equal(O.bf16_from_bits(twice), 2.0 * O.bf16_from_bits(full))
+    for cfg in ((1, 128), (1, 192), (1, 256), (2, 128), (2, 192), (2, 256)):
+        np.testing.assert_array_equal(H.run_gemm(aq, asf, bq, bsf, kind, 1.0, cfg=cfg), full)
+
+
+def test_quantize_full_size_idempotent_layout():
+    """config 3 size (M=16384, K=4096): blocked scales == swizzle(row-major scales); codes decode to finite
+    values whose re-quantisation with the same scale is a fixed point (idempotence)."""
+    m, k = 16384, 4096
+    x = torch.randn(m, k, dtype=torch.bfloat16, device="cuda") * 25
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(128))
+    q, sf = Q.fusedQuantizeMx(x, R, method="quest")
+    blk = Q.to_blocked(sf)
+    sw = Q.to_blocked(sf.clone(), True)
+    torch.cuda.synchronize()
+    assert torch.equal(blk.view(torch.uint8), sw.view(torch.uint8))
+    codes = O.unpack_e2m1(H.u8_of(q[:64]))
+    np.testing.assert_array_equal(O.e2m1_encode(O.e2m1_decode(codes)) & 7, codes & 7)

@@ -129,9 +129,9 @@ def one_quant_generic(kind, had, rows, k):
 
 
 GEMM_CASES = lambda cg, bn: ((128 * cg, max(bn, 128), 256, "ones"), (128 * cg, max(bn, 128), 256, "one"),
-                             (128 * cg, max(bn, 128), 1024, "one"), (128 * cg, max(bn, 128), 1024, "sfa"),
-                             (128 * cg, max(bn, 128), 1024, "sfb"), (256, 512, 1024, "narrow"),
-                             (504, 504, 2048, "narrow"), (1, 504, 4096, "narrow"), (300, 1000, 2176, "wide"))
+                             (128 * cg, max(bn, 128), 1024, "one"), (256, 512, 1024, "narrow"),
+                             (504, 504, 2048, "narrow"), (1, 504, 4096, "narrow"), (300, 1000, 2176, "narrow"),
+                             (130, 100, 96, "narrow"), (1000, 1336, 512, "narrow"))
 
 
 def gemm_cfg(kind, cg, bn):
@@ -188,7 +188,7 @@ def ladder(which):
         run_sub(["quantall"])
     if "gemm" in which:
         for kind in ("mx", "nv"):
-            for (cg, bn) in ((1, 128), (1, 64), (1, 256), (2, 128), (2, 256)):
+            for (cg, bn) in ((1, 128), (1, 64), (1, 192), (1, 256), (2, 128), (2, 192), (2, 256)):
                 run_sub(["gemmcfg", kind, cg, bn])
 
 
