@@ -321,8 +321,29 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               bulk_commit_group();
             }
           }
+        } else if (p.tma_store == 0 && (p.N % 16) == 0) {
+          // direct 256-bit stores: thread = row, one full 32-byte sector per instruction
+          const int row = m0 + q * 32 + lane;
+          if (row < p.M) {
+            __nv_bfloat16* drow = p.d + (int64_t)row * p.N + n0 + col0;
+#pragma unroll
+            for (int v = 0; v < Cfg::EPI_COLS / 16; ++v) {
+              if (n0 + col0 + v * 16 < p.N) {
+                uint32_t w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[v * 16 + 2 * e]) * alpha,
+                                                            __uint_as_float(r[v * 16 + 2 * e + 1]) * alpha);
+                  w[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(drow + v * 16), "r"(w[0]),
+                             "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                             : "memory");
+              }
+            }
+          }
         } else {
-          // direct stores (row pitch not a multiple of 16 bytes, i.e. N % 8 != 0): thread = row
+          // scalar stores (row pitch not a multiple of 16 bytes, i.e. N % 8 != 0): thread = row
           const int row = m0 + q * 32 + lane;
           if (row < p.M) {
             uint16_t* drow = reinterpret_cast<uint16_t*>(p.d) + (int64_t)row * p.N + n0 + col0;

@@ -19,6 +19,7 @@
 // Algorithmic bytes / element: 2 (bf16 in) + 0.5 (e2m1) + 1/32 (+1/32 blocked)  [MX].
 #include "common.cuh"
 #include <cuda_fp8.h>
+#include <stdlib.h>
 
 namespace b200q {
 
@@ -83,11 +84,12 @@ __device__ __forceinline__ void fwht_inreg(float* v) {
 
 // Butterfly stage across lanes (index bit >= 5 lives in the lane id).
 __device__ __forceinline__ void fwht_lane_stage(float* v, int lane_bit) {
-  const bool upper = (threadIdx.x & lane_bit) != 0;
+  // lower lane: v + o, upper lane: o - v  ==  fma(sign, v, o) with sign = +-1 (exact)
+  const float sign = (threadIdx.x & lane_bit) ? -1.0f : 1.0f;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    float o = __shfl_xor_sync(0xffffffffu, v[i], lane_bit);
-    v[i] = upper ? (o - v[i]) : (v[i] + o);
+    const float o = __shfl_xor_sync(0xffffffffu, v[i], lane_bit);
+    v[i] = fmaf(sign, v[i], o);
   }
 }
 
@@ -243,12 +245,10 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
       const uint32_t e = (__float_as_uint(scale) >> 23) & 0xffu;   // floor to 2^(e-127)
       sf_bytes = e;
       // exact 1 / 2^(e-127)
-      const float inv = (e >= 254u) ? __uint_as_float(0x00400000u >> (e - 254u)) : __uint_as_float((254u - e) << 23);
+      float inv = (e >= 254u) ? __uint_as_float(0x00400000u >> (e - 254u)) : __uint_as_float((254u - e) << 23);
+      if constexpr (METHOD == B200Q_METHOD_ABSMAX) inv *= 3.0f;   // (x / 2^e) * 3 == x * (3 / 2^e): one rounding either way
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] *= inv;
-        if constexpr (METHOD == B200Q_METHOD_ABSMAX) v[i] *= 3.0f;
-      }
+      for (int i = 0; i < 32; ++i) v[i] *= inv;
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -300,14 +300,14 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
       if constexpr (!NV) {
         if (p.sf_rm) p.sf_rm[chunk] = (uint8_t)sf_bytes;
         if (p.sf_blk) {
-          const int64_t r = chunk / p.cols, c = chunk % p.cols;
+          const uint32_t r = (uint32_t)chunk / (uint32_t)p.cols, c = (uint32_t)chunk - r * (uint32_t)p.cols;
           p.sf_blk[sf_blocked_offset(r, c, p.padded_cols)] = (uint8_t)sf_bytes;
         }
       } else {
         if (p.sf_rm) reinterpret_cast<uint16_t*>(p.sf_rm)[chunk] = (uint16_t)sf_bytes;
         if (p.sf_blk) {
-          const int64_t g = chunk * 2;
-          const int64_t r = g / p.cols, c = g % p.cols;   // c is even: both bytes share a 4-byte cell
+          const uint32_t g = (uint32_t)chunk * 2u;
+          const uint32_t r = g / (uint32_t)p.cols, c = g - r * (uint32_t)p.cols;   // c is even: both bytes share a 4-byte cell
           *reinterpret_cast<uint16_t*>(p.sf_blk + sf_blocked_offset(r, c, p.padded_cols)) = (uint16_t)sf_bytes;
         }
       }
@@ -331,6 +331,308 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
   }
 }
 
+
+// =====================================================================================================
+// Tensor-core rotation path (HAD in {32, 64, 128}): the rotation x_group(1xH) @ R(HxH) runs on
+// mma.sync.m16n8k16 (bf16 x bf16 -> fp32), exactly the arithmetic of the reference's GEMM-with-quantising-
+// epilogue kernels, for ANY runtime R -- ~4 instructions / element instead of ~28 for the butterfly path.
+//
+//   global --cp.async 16 B, XOR-swizzled--> 4-stage shared-memory ring of 16 KB CTA tiles (8192 elements)
+//   --ldmatrix.x4--> A fragments;  B fragments (R) live in registers for the whole kernel
+//   H <= 64 : each of the 4 warps rotates its own quarter of the tile's rows against all of R
+//   H = 128 : the 128 output columns are split over the 4 warps (32 each = one scale group), every warp
+//             reads the whole A tile (R fragments would not fit one warp's registers)
+//   accumulators: lane (g = lane/4, q = lane%4) holds rows g, g+8 and columns 8j+2q, 8j+2q+1 of n-tile j;
+//   a 32-column scale group is 4 n-tiles, i.e. 8 values per lane and the quad holds the whole group:
+//   quad shuffles reduce abs-max / sums, cvt.e2m1x2 packs column pairs, a 2-round quad byte transpose
+//   gives every lane 4 consecutive output bytes (16 B per group per quad).
+// =====================================================================================================
+constexpr int kMmaThreads = 128;
+constexpr int kTileElems = 8192;
+constexpr int kTileBytes = kTileElems * 2;
+constexpr int kMmaStages = 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t cvt2_e2m1(float lo, float hi) {   // one byte: lo -> low nibble
+  uint32_t v;
+  asm volatile("{\n.reg .b8 b;\ncvt.rn.satfinite.e2m1x2.f32 b, %2, %1;\ncvt.u32.u8 %0, b;\n}" : "=r"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+template <int HAD>
+__device__ __forceinline__ int swz_chunk(int row, int chunk) {
+  if constexpr (HAD >= 64) return chunk ^ (row & 7);
+  else if constexpr (HAD == 32) return chunk ^ ((row >> 1) & 3);
+  else return chunk ^ ((row >> 2) & 1);
+}
+
+template <int HAD, bool NV, int METHOD, bool MASK>
+__global__ void __launch_bounds__(kMmaThreads) quantize_mma_kernel(const QuantParams p) {
+  static_assert(HAD == 32 || HAD == 64 || HAD == 128, "tensor-core path: H in {32, 64, 128}");
+  constexpr int NSPLIT = HAD == 128 ? 4 : 1;
+  constexpr int NT = HAD == 128 ? 4 : HAD / 8;          // n-tiles (8 columns) per warp
+  constexpr int KS = HAD / 16;                           // k-steps
+  constexpr int ROWS = kTileElems / HAD;                 // rotation groups per CTA tile
+  constexpr int MT = NSPLIT == 4 ? ROWS / 16 : ROWS / 4 / 16;   // 16-row m-tiles per warp per CTA tile
+  constexpr int CPR = HAD / 8;                           // 16-byte chunks per row
+  constexpr int NG = NT / 4;                             // 32-column groups per warp per row
+
+  extern __shared__ __align__(128) uint8_t q_smem[];
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(q_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int n_base = NSPLIT == 4 ? 32 * warp : 0;
+  const int64_t n_tiles = (p.n_chunks * 32 + kTileElems - 1) / kTileElems;
+  const int64_t numel = p.n_chunks * 32;
+
+  auto load_tile = [&](int64_t tile, int stage) {
+    if (tile < n_tiles) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.x) + tile * kTileBytes;
+      const int64_t elem0 = tile * kTileElems;
+#pragma unroll
+      for (int i = 0; i < kTileBytes / 16 / kMmaThreads; ++i) {
+        const int c = i * kMmaThreads + threadIdx.x;
+        const int row = c / CPR, col = c % CPR;
+        const uint32_t dst = ring + stage * kTileBytes + row * (HAD * 2) + swz_chunk<HAD>(row, col) * 16;
+        const bool ok = elem0 + (int64_t)c * 8 < numel;
+        cp_async16(dst, ok ? src + (int64_t)c * 16 : reinterpret_cast<const uint8_t*>(p.x), ok ? 16u : 0u);
+      }
+    }
+  };
+
+  // pipeline prologue first: the loads fly while the rotation fragments are fetched
+  const int64_t first = blockIdx.x;
+#pragma unroll
+  for (int s = 0; s < kMmaStages - 1; ++s) {
+    load_tile(first + (int64_t)s * gridDim.x, s);
+    cp_async_commit();
+  }
+
+  // B fragments of R (row-major [k][n]): b0 = {R[16s+2q][n], R[16s+2q+1][n]}, b1 = same at k+8; n = n_base + 8j + g
+  uint32_t bfrag[NT][KS][2];
+  {
+    const unsigned short* R = reinterpret_cast<const unsigned short*>(p.rot);
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = 16 * s + 8 * h + 2 * q, n = n_base + 8 * j + g;
+          bfrag[j][s][h] = (uint32_t)__ldg(R + k * HAD + n) | ((uint32_t)__ldg(R + (k + 1) * HAD + n) << 16);
+        }
+  }
+  float gs = 1.f, gs_rcp = 1.f;
+  if constexpr (NV) {
+    gs = *p.gs;
+    gs_rcp = rcp_approx_ftz(gs);
+  }
+
+  int it = 0;
+  for (int64_t tile = first; tile < n_tiles; tile += gridDim.x, ++it) {
+    cp_async_wait<kMmaStages - 2>();
+    __syncthreads();
+    load_tile(tile + (int64_t)(kMmaStages - 1) * gridDim.x, (it + kMmaStages - 1) % kMmaStages);
+    cp_async_commit();
+    const uint32_t tbase = ring + (it % kMmaStages) * kTileBytes;
+    const int64_t elem_tile = tile * kTileElems;
+
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int rb = NSPLIT == 4 ? mt * 16 : warp * (ROWS / 4) + mt * 16;   // first tile row of this m-tile
+      // A fragments for all k-steps
+      uint32_t afrag[KS][4];
+      {
+        const int sub = lane >> 3, rin = lane & 7;
+        const int row = rb + (sub & 1) * 8 + rin;
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+          ldmatrix_x4(tbase + row * (HAD * 2) + swz_chunk<HAD>(row, 2 * s + (sub >> 1)) * 16, afrag[s]);
+      }
+      float acc[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+      for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) mma_bf16_16816(acc[j], afrag[s], bfrag[j][s]);
+
+      // ---- quantise: two row halves (g, g+8) x NG 32-column groups
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int row = rb + g + 8 * half;
+#pragma unroll
+        for (int G = 0; G < NG; ++G) {
+          float v[8];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            v[2 * jj] = acc[4 * G + jj][2 * half];
+            v[2 * jj + 1] = acc[4 * G + jj][2 * half + 1];
+          }
+          uint32_t sf_bytes = 0;
+          if constexpr (!NV) {
+            float scale;
+            if constexpr (METHOD == B200Q_METHOD_QUEST) {
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+              const float mean = s1 / 32.f;
+              const float var = fmaf(-mean, mean, s2 / 32.f);
+              scale = 1.0f;
+              if (var >= 0.f) scale = (float)((double)sqrtf(var) * (2.92247856 / 6.) + 1e-8);
+            } else {
+              float amax = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));
+              amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+              amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+              scale = amax + 1e-8f;
+            }
+            const uint32_t e = (__float_as_uint(scale) >> 23) & 0xffu;
+            sf_bytes = e;
+            float inv = (e >= 254u) ? __uint_as_float(0x00400000u >> (e - 254u)) : __uint_as_float((254u - e) << 23);
+            if constexpr (METHOD == B200Q_METHOD_ABSMAX) inv *= 3.0f;   // (x / 2^e) * 3 == x * (3 / 2^e) exactly
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= inv;
+          } else {
+#pragma unroll
+            for (int h16 = 0; h16 < 2; ++h16) {          // two 16-column scale groups = n-tile pairs
+              float* vv = v + 4 * h16;
+              float out_scale;
+              uint8_t sfb;
+              if constexpr (METHOD == B200Q_METHOD_QUEST) {
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { s1 += vv[i]; s2 = fmaf(vv[i], vv[i], s2); }
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+                const float mean = s1 * 0.0625f;
+                const float scale = (float)((double)sqrtf(fmaf(-mean, mean, s2 * 0.0625f)) * (2.92247856 / 6.) + 1e-8);
+                const __nv_fp8_e4m3 t(scale);
+                sfb = *reinterpret_cast<const uint8_t*>(&t);
+                const float sq = float(t);
+                out_scale = (sq > 0.f) ? rcp_approx_ftz(sq) : 0.f;
+              } else {
+                float amax = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) amax = fmaxf(amax, fabsf(vv[i]));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                float sfv = gs * (amax * rcp_approx_ftz(6.0f));
+                const __nv_fp8_e4m3 t(sfv);
+                sfb = *reinterpret_cast<const uint8_t*>(&t);
+                sfv = float(t);
+                out_scale = (sfv != 0.f) ? rcp_approx_ftz(sfv * gs_rcp) : 0.f;
+              }
+              sf_bytes |= (uint32_t)sfb << (8 * h16);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) vv[i] *= out_scale;
+            }
+          }
+          // pack column pairs; W = bytes by n-tile jj (byte jj <-> group bytes jj*4 + q)
+          uint32_t W = cvt2_e2m1(v[0], v[1]) | (cvt2_e2m1(v[2], v[3]) << 8) | (cvt2_e2m1(v[4], v[5]) << 16) |
+                       (cvt2_e2m1(v[6], v[7]) << 24);
+          uint32_t mask_word = 0;
+          if constexpr (MASK) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+              for (int e2 = 0; e2 < 2; ++e2)
+                mask_word |= (fabsf(v[2 * jj + e2]) < 6.f) ? (1u << (8 * jj + 2 * q + e2)) : 0u;
+            mask_word |= __shfl_xor_sync(0xffffffffu, mask_word, 1);
+            mask_word |= __shfl_xor_sync(0xffffffffu, mask_word, 2);
+          }
+          // quad 4x4 byte transpose: lane q ends with group bytes [4q, 4q+4)
+          {
+            const uint32_t o1 = __shfl_xor_sync(0xffffffffu, W, 1);
+            // even q: [W.b0, o.b0, W.b2, o.b2]   odd q: [o.b1, W.b1, o.b3, W.b3]
+            const uint32_t X = (q & 1) ? __byte_perm(W, o1, 0x3715) : __byte_perm(W, o1, 0x6240);
+            const uint32_t o2 = __shfl_xor_sync(0xffffffffu, X, 2);
+            // q < 2: [X.b0, X.b1, o.b0, o.b1]   q >= 2: [o.b2, o.b3, X.b2, X.b3]
+            W = (q & 2) ? __byte_perm(X, o2, 0x3276) : __byte_perm(X, o2, 0x5410);
+          }
+          const int64_t elem = elem_tile + (int64_t)row * HAD + n_base + 32 * G;
+          if (elem < numel) {
+            const int64_t chunk = elem >> 5;
+            reinterpret_cast<uint32_t*>(p.q)[chunk * 4 + q] = W;
+            if (q == 0) {
+              if constexpr (MASK) { if (p.mask) p.mask[chunk] = mask_word; }
+              if constexpr (!NV) {
+                if (p.sf_rm) p.sf_rm[chunk] = (uint8_t)sf_bytes;
+                if (p.sf_blk) {
+                  const uint32_t r = (uint32_t)chunk / (uint32_t)p.cols, c = (uint32_t)chunk - r * (uint32_t)p.cols;
+                  p.sf_blk[sf_blocked_offset(r, c, p.padded_cols)] = (uint8_t)sf_bytes;
+                }
+              } else {
+                if (p.sf_rm) reinterpret_cast<uint16_t*>(p.sf_rm)[chunk] = (uint16_t)sf_bytes;
+                if (p.sf_blk) {
+                  const uint32_t gi = (uint32_t)chunk * 2u;
+                  const uint32_t r = gi / (uint32_t)p.cols, c = gi - r * (uint32_t)p.cols;
+                  *reinterpret_cast<uint16_t*>(p.sf_blk + sf_blocked_offset(r, c, p.padded_cols)) = (uint16_t)sf_bytes;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // zero-fill the padding of the blocked scale buffer
+  if (p.sf_blk) {
+    const int64_t tid = (int64_t)blockIdx.x * kMmaThreads + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * kMmaThreads;
+    const int64_t pad_rows = p.padded_rows - p.rows;
+    for (int64_t i = tid; i < pad_rows * p.padded_cols; i += nthr) {
+      const int64_t r = p.rows + i / p.padded_cols, c = i % p.padded_cols;
+      p.sf_blk[sf_blocked_offset(r, c, p.padded_cols)] = 0;
+    }
+    const int64_t pad_cols = p.padded_cols - p.cols;
+    for (int64_t i = tid; i < p.rows * pad_cols; i += nthr) {
+      const int64_t r = i / pad_cols, c = p.cols + i % pad_cols;
+      p.sf_blk[sf_blocked_offset(r, c, p.padded_cols)] = 0;
+    }
+  }
+}
+
+template <int HAD, bool NV, int METHOD, bool MASK>
+static int launch_mma(const QuantParams& p, cudaStream_t stream) {
+  auto kern = quantize_mma_kernel<HAD, NV, METHOD, MASK>;
+  constexpr int smem = kMmaStages * kTileBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int64_t n_tiles = (p.n_chunks * 32 + kTileElems - 1) / kTileElems;
+  int64_t ctas = n_tiles;
+  const int64_t max_ctas = (int64_t)num_sms() * 3;     // 64 KB ring -> 3 resident CTAs / SM: one persistent wave
+  if (ctas > max_ctas) ctas = max_ctas;
+  if (ctas < 1) ctas = 1;
+  kern<<<(unsigned)ctas, kMmaThreads, smem, stream>>>(p);
+  B200Q_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int HAD, bool NV, int METHOD, bool MASK>
 static int launch(const QuantParams& p, cudaStream_t stream) {
   int64_t ctas = ceil_div(p.n_tiles, kWarpsPerCta);
@@ -342,15 +644,22 @@ static int launch(const QuantParams& p, cudaStream_t stream) {
   return 0;
 }
 
+static bool use_butterfly() {
+  // Default: the CUDA-core butterfly kernel (measured faster on B200 for Hadamard rotations, profiles/).
+  // B200Q_QUANT_MMA=1 selects the tensor-core (mma.sync) kernel, which handles ANY rotation at full speed.
+  const char* e = getenv("B200Q_QUANT_MMA");
+  return !(e && e[0] == '1');
+}
+
 template <bool NV, int METHOD, bool MASK>
 static int dispatch_had(int had, const QuantParams& p, cudaStream_t stream) {
   switch (had) {
     case 16:
       if constexpr (NV) return launch<16, NV, METHOD, MASK>(p, stream);
       break;
-    case 32: return launch<32, NV, METHOD, MASK>(p, stream);
-    case 64: return launch<64, NV, METHOD, MASK>(p, stream);
-    case 128: return launch<128, NV, METHOD, MASK>(p, stream);
+    case 32: return use_butterfly() ? launch<32, NV, METHOD, MASK>(p, stream) : launch_mma<32, NV, METHOD, MASK>(p, stream);
+    case 64: return use_butterfly() ? launch<64, NV, METHOD, MASK>(p, stream) : launch_mma<64, NV, METHOD, MASK>(p, stream);
+    case 128: return use_butterfly() ? launch<128, NV, METHOD, MASK>(p, stream) : launch_mma<128, NV, METHOD, MASK>(p, stream);
   }
   set_error(NV ? "Unsupported rotation size %d; expected 16, 32, 64, or 128."
                : "Unsupported rotation size %d; expected 32, 64, or 128.", had);
@@ -364,6 +673,7 @@ static int fill_params(QuantParams& p, const void* x, const void* rot, void* q, 
                 (long long)numel, (long long)row_len);
   B200Q_REQUIRE(numel % had == 0, "A must be divisible by %d", had);
   B200Q_REQUIRE(row_len % 32 == 0, "last dimension (%lld) must be a multiple of 32", (long long)row_len);
+  B200Q_REQUIRE(numel < ((int64_t)1 << 36), "tensor too large (%lld elements)", (long long)numel);
   B200Q_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)q & 15) == 0, "x and q must be 16-byte aligned");
   p.x = (const uint4*)x;
   p.rot = (const __nv_bfloat16*)rot;

@@ -77,6 +77,31 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "quant"]
     if "quant" in which:
         quant_sweep()
+    if "gemmq" in which:
+        gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (1, 2), (4, 2)])
+        gemm_sweep("nv", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (4, 2)])
+    if "quantk" in which:
+        # kernel-only quantise timing through the C-ABI (no torch allocations in the loop)
+        for (M, K) in ((4096, 4096), (16384, 4096)):
+            x = torch.randn(M, K, dtype=torch.bfloat16, device=dev)
+            qo = torch.empty(M, K // 2, dtype=torch.uint8, device=dev)
+            for kind, group in (("mx", 32), ("nv", 16)):
+                sfo = torch.empty(M * K // group + 65536, dtype=torch.uint8, device=dev)
+                sfb = torch.empty(M * K // group + 65536, dtype=torch.uint8, device=dev)
+                gs = torch.ones(1, device=dev)
+                for had in (32, 64, 128):
+                    H = torch.from_numpy(O.bf16_bits(O.hadamard_matrix(had)).astype(np.int16)).view(torch.bfloat16).to(dev)
+                    for bf in ("0", "1"):
+                        os.environ["B200Q_QUANT_MMA"] = "0" if bf == "1" else "1"
+                        st = torch.cuda.current_stream().cuda_stream
+                        if kind == "mx":
+                            fn = lambda: lib.b200q_quantize_mx(x.data_ptr(), H.data_ptr(), qo.data_ptr(), sfo.data_ptr(), sfb.data_ptr(), None, M * K, K, had, 1, st)
+                        else:
+                            fn = lambda: lib.b200q_quantize_nv(x.data_ptr(), H.data_ptr(), qo.data_ptr(), sfo.data_ptr(), sfb.data_ptr(), gs.data_ptr(), M * K, K, had, 1, st)
+                        us = timeit(fn, iters=50)
+                        byts = M * K * (2.5 + 2.0 / group)
+                        emit(check="quantk", kind=kind, M=M, K=K, had=had, butterfly=bf, us=round(us, 1), gbs=round(byts / us / 1e3, 0))
+        os.environ["B200Q_QUANT_MMA"] = "0"
     if "gemm" in which:
         cfgs = [(1, 128), (1, 256), (2, 128), (2, 192), (2, 256)]
         gemm_sweep("mx", [(4096, 14336, 4096)], cfgs, [(0, 2), (1, 2), (3, 2), (4, 2)])
