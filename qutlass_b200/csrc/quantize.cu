@@ -66,18 +66,36 @@ __device__ __forceinline__ uint32_t cvt8_e2m1(const float* a) {
   return val;
 }
 
+// Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 on sm_100): the 32 values of a chunk are treated as 16 pairs
+// (v[i], v[i+16]); every packed op below uses that pairing so the register allocator keeps them adjacent.
+#define B200Q_PK(v, i) make_float2((v)[(i)], (v)[(i) + 16])
+#define B200Q_UNPK(v, i, f) \
+  do {                      \
+    const float2 _t = (f);  \
+    (v)[(i)] = _t.x;        \
+    (v)[(i) + 16] = _t.y;   \
+  } while (0)
+
 // In-register Walsh-Hadamard butterflies over index bits [0, log2(N)) of v[0..31].
 template <int N>
 __device__ __forceinline__ void fwht_inreg(float* v) {
 #pragma unroll
-  for (int s = 1; s < N; s <<= 1) {
+  for (int s = 1; s < 16 && s < N; s <<= 1) {           // bits 0..3: packed, both 16-halves at once
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < 16; ++i) {
       if ((i & s) == 0) {
-        float a = v[i], b = v[i | s];
-        v[i] = a + b;
-        v[i | s] = a - b;
+        const float2 a = B200Q_PK(v, i), b = B200Q_PK(v, i | s);
+        B200Q_UNPK(v, i, __fadd2_rn(a, b));
+        B200Q_UNPK(v, i | s, __fadd2_rn(a, make_float2(-b.x, -b.y)));
       }
+    }
+  }
+  if constexpr (N >= 32) {                                // bit 4: within each pair
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float a = v[i], b = v[i + 16];
+      v[i] = a + b;
+      v[i + 16] = a - b;
     }
   }
 }
@@ -85,11 +103,13 @@ __device__ __forceinline__ void fwht_inreg(float* v) {
 // Butterfly stage across lanes (index bit >= 5 lives in the lane id).
 __device__ __forceinline__ void fwht_lane_stage(float* v, int lane_bit) {
   // lower lane: v + o, upper lane: o - v  ==  fma(sign, v, o) with sign = +-1 (exact)
-  const float sign = (threadIdx.x & lane_bit) ? -1.0f : 1.0f;
+  const float sg = (threadIdx.x & lane_bit) ? -1.0f : 1.0f;
+  const float2 sign = make_float2(sg, sg);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float o = __shfl_xor_sync(0xffffffffu, v[i], lane_bit);
-    v[i] = fmaf(sign, v[i], o);
+  for (int i = 0; i < 16; ++i) {
+    const float2 o = make_float2(__shfl_xor_sync(0xffffffffu, v[i], lane_bit),
+                                 __shfl_xor_sync(0xffffffffu, v[i + 16], lane_bit));
+    B200Q_UNPK(v, i, __ffma2_rn(sign, B200Q_PK(v, i), o));
   }
 }
 
@@ -177,8 +197,11 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
       fwht_inreg<(HAD < 32 ? HAD : 32)>(v);
       if constexpr (HAD >= 64) fwht_lane_stage(v, 1);
       if constexpr (HAD >= 128) fwht_lane_stage(v, 2);
+      {
+        const float2 c2 = make_float2(c_scale, c_scale);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= c_scale;
+        for (int i = 0; i < 16; ++i) B200Q_UNPK(v, i, __fmul2_rn(B200Q_PK(v, i), c2));
+      }
     } else {
       // generic x_group(1xH) @ R(HxH) for arbitrary runtime rotations (e.g. identity):
       // stage the fp32 x of the whole warp-tile in shared memory, fp32 FMA on CUDA cores.
@@ -247,9 +270,13 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
       // exact 1 / 2^(e-127)
       float inv = (e >= 254u) ? __uint_as_float(0x00400000u >> (e - 254u)) : __uint_as_float((254u - e) << 23);
       if constexpr (METHOD == B200Q_METHOD_ABSMAX) inv *= 3.0f;   // (x / 2^e) * 3 == x * (3 / 2^e): one rounding either way
+      {
+        const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= inv;
+        for (int i = 0; i < 16; ++i) B200Q_UNPK(v, i, __fmul2_rn(B200Q_PK(v, i), inv2));
+      }
     } else {
+      float os[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float* vv = v + 16 * h;
@@ -280,8 +307,12 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
           out_scale = (sfv != 0.f) ? rcp_approx_ftz(sfv * gs_rcp) : 0.f;
         }
         sf_bytes |= (uint32_t)sfb << (8 * h);
+        os[h] = out_scale;
+      }
+      {
+        const float2 os2 = make_float2(os[0], os[1]);   // v[i] belongs to 16-group 0, v[i+16] to group 1
 #pragma unroll
-        for (int i = 0; i < 16; ++i) vv[i] *= out_scale;
+        for (int i = 0; i < 16; ++i) B200Q_UNPK(v, i, __fmul2_rn(B200Q_PK(v, i), os2));
       }
     }
 #pragma unroll
