@@ -42,14 +42,18 @@ constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 320
 constexpr int kSmemBudget = 227 * 1024;
 
-template <int kCtaGroup, int BN, bool kNV>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128>
 struct GemmCfg {
+  // A_ROWS < 128 (small M): only A_ROWS rows of the A tile are loaded and kept per stage; the MMA still reads a
+  // 128-row operand (the bytes that follow) -- those accumulator rows are garbage and never stored.  Smaller
+  // stages = more k-tiles of B in flight, which is what bounds the weight-streaming (decode) regime.
+  static_assert(A_ROWS % 8 == 0 && A_ROWS >= 8 && A_ROWS <= 128 && (A_ROWS == 128 || kCtaGroup == 1), "A_ROWS");
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 64 in [64, 256]");
   static constexpr int SFKB = kNV ? 4 : 2;                       // 512-B scale blocks per 128 rows per k-tile
   // a BN-wide tile starts at a multiple of 64 rows of B: its scales begin 0 or 2 TMEM columns into a block
   static constexpr int NB = (BN % 128 == 0) ? BN / 128 : (BN + 64 + 127) / 128;   // SFB row-blocks a tile can touch
   static constexpr int B_ROWS = BN / kCtaGroup;                  // B rows this CTA stages
-  static constexpr int A_BYTES = BM * BK_BYTES;
+  static constexpr int A_BYTES = A_ROWS * BK_BYTES;
   static constexpr int B_BYTES = B_ROWS * BK_BYTES;
   static constexpr int SFA_BYTES = SFKB * 512;
   static constexpr int SFB_BYTES = NB * SFKB * 512;
@@ -68,7 +72,7 @@ struct GemmCfg {
   static constexpr int STG_TOTAL = kEpiWarps * STG_BYTES;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int STAGES_RAW = (kSmemBudget - BAR_BYTES - 1024 - STG_TOTAL) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_TOTAL + BAR_BYTES + 1024;  // +1024 alignment slack
   static constexpr uint32_t TX_BYTES = (uint32_t)STAGE_BYTES * kCtaGroup;   // what the (leader's) full barrier expects
   static_assert(TMEM_USED <= 512, "TMEM overflow");
@@ -88,12 +92,12 @@ struct GemmParams {
   int flags;          // profiling: bit0 skip stores, bit1 skip TMEM loads
 };
 
-template <int kCtaGroup, int BN, bool kNV>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb,
                 const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
-  using Cfg = GemmCfg<kCtaGroup, BN, kNV>;
+  using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ACC = Cfg::ACC_STAGES;
   constexpr int SFKB = Cfg::SFKB;
@@ -435,11 +439,11 @@ static int make_d_tmap(CUtensorMap* tm, const void* ptr, int64_t M, int64_t N, i
                 chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "D");
 }
 
-template <int kCtaGroup, int BN, bool kNV>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128>
 static int launch_gemm(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D,
                        int M, int N, int K, cudaStream_t stream) {
-  using Cfg = GemmCfg<kCtaGroup, BN, kNV>;
-  auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV>;
+  using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS>;
+  auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV, A_ROWS>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -449,7 +453,7 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   const int64_t sf_col_blocks = ceil_div(ceil_div(K, group), 4);
   CUtensorMap ta, tb, tsa, tsb, td;
   int rc;
-  if ((rc = make_operand_tmap(&ta, A, M, K / 2, BM, "A"))) return rc;
+  if ((rc = make_operand_tmap(&ta, A, M, K / 2, A_ROWS, "A"))) return rc;
   if ((rc = make_operand_tmap(&tb, B, N, K / 2, Cfg::B_ROWS, "B"))) return rc;
   if ((rc = make_sf_tmap(&tsa, SFA, ceil_div(M, 128), sf_col_blocks, Cfg::SFKB, 1, "SFA"))) return rc;
   if ((rc = make_sf_tmap(&tsb, SFB, ceil_div(N, 128), sf_col_blocks, Cfg::SFKB, Cfg::NB, "SFB"))) return rc;
@@ -495,6 +499,9 @@ static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B
                         const float* alpha, void* D, int M, int N, int K, cudaStream_t s) {
 #define B200Q_CASE(CG, BNV) \
   if (cta_group == CG && block_n == BNV) return launch_gemm<CG, BNV, kNV>(A, B, SFA, SFB, alpha, D, M, N, K, s);
+  if (cta_group == 1 && block_n == 128 && M <= 16) return launch_gemm<1, 128, kNV, 16>(A, B, SFA, SFB, alpha, D, M, N, K, s);
+  if (cta_group == 1 && block_n == 128 && M <= 32) return launch_gemm<1, 128, kNV, 32>(A, B, SFA, SFB, alpha, D, M, N, K, s);
+  if (cta_group == 1 && block_n == 128 && M <= 64) return launch_gemm<1, 128, kNV, 64>(A, B, SFA, SFB, alpha, D, M, N, K, s);
   B200Q_CASE(1, 64)
   B200Q_CASE(1, 128)
   B200Q_CASE(1, 192)
