@@ -154,9 +154,15 @@ def main():
     group = 32 if kind == "mx" else 16
 
     # ---------------- setup (untimed): rotation, weights quantised once on rank 0, ONE broadcast
-    import oracle as O  # only for the Hadamard matrix helper
     torch.manual_seed(1234 + rank)
-    H = torch.from_numpy(O.bf16_bits(O.hadamard_matrix(args.had)).astype(np.int16)).view(torch.bfloat16).to(dev)
+    # Sylvester Hadamard * H^-1/2 in bf16 (what scipy.linalg.hadamard gives the reference benchmark, bench_mxfp4_sm100.py:51-54)
+    idx = torch.arange(args.had)
+    bits = (idx[:, None] & idx[None, :])
+    par = torch.zeros_like(bits)
+    while bits.any():
+        par ^= bits & 1
+        bits = bits >> 1
+    H = ((1.0 - 2.0 * par.double()) * args.had ** -0.5).to(torch.bfloat16).to(dev)
     gs = torch.tensor([1.0], dtype=torch.float32, device=dev)
     alpha = torch.tensor([1.0], dtype=torch.float32, device=dev)
     NSETS = 4  # rotate buffer sets so every timed iteration reads/writes data that is not L2 resident

@@ -349,10 +349,12 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
   if (p.sf_blk) {
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * kThreads;
-    const int64_t pad_rows = p.padded_rows - p.rows;
-    for (int64_t i = tid; i < pad_rows * p.padded_cols; i += nthr) {
-      const int64_t r = p.rows + i / p.padded_cols, c = i % p.padded_cols;
-      p.sf_blk[sf_blocked_offset(r, c, p.padded_cols)] = 0;
+    // pad rows: one 4-byte cell (4 K-scales of one row) per iteration, 32-bit index math
+    const uint32_t pad_rows = (uint32_t)(p.padded_rows - p.rows);
+    const uint32_t cpr = (uint32_t)(p.padded_cols >> 2);
+    for (uint32_t i = (uint32_t)tid; i < pad_rows * cpr; i += (uint32_t)nthr) {
+      const uint32_t r = (uint32_t)p.rows + i / cpr, c4 = i - (i / cpr) * cpr;
+      *reinterpret_cast<uint32_t*>(p.sf_blk + sf_blocked_offset(r, 4 * c4, p.padded_cols)) = 0u;
     }
     const int64_t pad_cols = p.padded_cols - p.cols;
     for (int64_t i = tid; i < p.rows * pad_cols; i += nthr) {
@@ -632,10 +634,12 @@ __global__ void __launch_bounds__(kMmaThreads) quantize_mma_kernel(const QuantPa
   if (p.sf_blk) {
     const int64_t tid = (int64_t)blockIdx.x * kMmaThreads + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * kMmaThreads;
-    const int64_t pad_rows = p.padded_rows - p.rows;
-    for (int64_t i = tid; i < pad_rows * p.padded_cols; i += nthr) {
-      const int64_t r = p.rows + i / p.padded_cols, c = i % p.padded_cols;
-      p.sf_blk[sf_blocked_offset(r, c, p.padded_cols)] = 0;
+    // pad rows: one 4-byte cell (4 K-scales of one row) per iteration, 32-bit index math
+    const uint32_t pad_rows = (uint32_t)(p.padded_rows - p.rows);
+    const uint32_t cpr = (uint32_t)(p.padded_cols >> 2);
+    for (uint32_t i = (uint32_t)tid; i < pad_rows * cpr; i += (uint32_t)nthr) {
+      const uint32_t r = (uint32_t)p.rows + i / cpr, c4 = i - (i / cpr) * cpr;
+      *reinterpret_cast<uint32_t*>(p.sf_blk + sf_blocked_offset(r, 4 * c4, p.padded_cols)) = 0u;
     }
     const int64_t pad_cols = p.padded_cols - p.cols;
     for (int64_t i = tid; i < p.rows * pad_cols; i += nthr) {
