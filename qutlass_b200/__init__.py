@@ -37,7 +37,29 @@ def _check(cond: bool, msg: str) -> None:
 
 
 def _stream(t: torch.Tensor) -> int:
-    return torch.cuda.current_stream(t.device).cuda_stream
+    # raw cudaStream_t of torch's current stream on the tensor's device (no Stream object construction)
+    return torch._C._cuda_getCurrentRawStream(t.device.index)
+
+
+class _DeviceGuard:
+    """Cheap device guard: only switches when the tensor lives on a non-current device (the reference's
+    launchers wrap every launch in a DeviceGuard, gemm.cu:164)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _check_cuda_same(name: str, tensors) -> None:
@@ -76,7 +98,7 @@ def _matmul_fp4(name: str, a, b, a_sf, b_sf, alpha, kind: int, sf_dtype, min_k_b
     _check(a_sf.numel() >= need_a, f"A_sf has {a_sf.numel()} scales, the blocked layout needs {need_a}")
     _check(b_sf.numel() >= need_b, f"B_sf has {b_sf.numel()} scales, the blocked layout needs {need_b}")
     out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
-    with torch.cuda.device(a.device):
+    with _DeviceGuard(a.device):
         _lib.check(_lib.load().b200q_gemm_fp4_cfg(
             a.data_ptr(), b.data_ptr(), a_sf.data_ptr(), b_sf.data_ptr(), alpha.data_ptr(), out.data_ptr(),
             m, n, k, kind, cfg[0], cfg[1], _stream(a)))
@@ -123,7 +145,7 @@ def _quantize_mx_into(a, r, out, out_sf, out_sf_blocked, out_mask, method: int):
     had = _quant_checks("fusedQuantizeMx", a, r, [out, out_sf])
     _check(had in (32, 64, 128), f"Unsupported rotation size {had}; expected 32, 64, or 128.")
     _check(a.size(-1) % 32 == 0, "last dimension of A must be a multiple of 32")
-    with torch.cuda.device(a.device):
+    with _DeviceGuard(a.device):
         _lib.check(_lib.load().b200q_quantize_mx(
             a.data_ptr(), r.data_ptr(), out.data_ptr(), out_sf.data_ptr() if out_sf is not None else None,
             out_sf_blocked.data_ptr() if out_sf_blocked is not None else None,
@@ -137,7 +159,7 @@ def _quantize_nv_into(a, r, out, out_sf, out_sf_blocked, global_scale, method: i
     _check(global_scale.dim() == 1 and global_scale.size(0) == 1, "global_scale must be a scalar")
     _check(had in (16, 32, 64, 128), f"Unsupported rotation size {had}; expected 16, 32, 64, or 128.")
     _check(a.size(-1) % 32 == 0, "last dimension of A must be a multiple of 32")
-    with torch.cuda.device(a.device):
+    with _DeviceGuard(a.device):
         _lib.check(_lib.load().b200q_quantize_nv(
             a.data_ptr(), r.data_ptr(), out.data_ptr(), out_sf.data_ptr() if out_sf is not None else None,
             out_sf_blocked.data_ptr() if out_sf_blocked is not None else None, global_scale.data_ptr(),

@@ -229,22 +229,28 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const uint32_t sfa_lo = sfa_lo0 + stage * kStage16;
           const uint32_t sfb_lo = sfa_lo + (Cfg::SFA_BYTES >> 4);
           if (elected) {
-          // scales: smem -> TMEM (each 512-B block -> 4 columns, replicated over the 4 lane quarters)
-#pragma unroll
-          for (int b = 0; b < SFKB; ++b)
+          // scales: smem -> TMEM (each 512-B block -> 4 columns, replicated over the 4 lane quarters).
+          // Order: the copies for K-chunk c are issued right before the first MMA that needs them
+          // (profiling flags: 32 = skip the copies, 64 = all copies up front).
+          auto copy_chunk = [&](int b) {
             tmem_cp_32x128b_warpx4<kCtaGroup>(tmem_sfa + b * 4, mk(sfa_lo + b * 32, kDescHiSF));
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-            for (int b = 0; b < SFKB; ++b)
+            for (int nb = 0; nb < NB; ++nb)
               tmem_cp_32x128b_warpx4<kCtaGroup>(tmem_sfb + b * (4 * NB) + nb * 4,
                                                 mk(sfb_lo + (nb * SFKB + b) * 32, kDescHiSF));
+          };
+          const bool skip_cp = (p.flags & 32) != 0;
+          const bool upfront = (p.flags & 64) != 0;
+          if (upfront && !skip_cp) {
+#pragma unroll
+            for (int b = 0; b < SFKB; ++b) copy_chunk(b);
+          }
           // 4 MMAs of K = 64 (32 bytes = 2 x 16 B along the swizzled row each); K tail issues fewer
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
+            const uint32_t chunk = kNV ? kb : (kb >> 1);
+            if (!upfront && !skip_cp && (kNV || (kb & 1) == 0)) copy_chunk((int)chunk);
             if (k_left > kb * 64) {
-              constexpr uint32_t dummy = 0; (void)dummy;
-              const uint32_t chunk = kNV ? kb : (kb >> 1);
               const uint32_t sf_id = kNV ? 0u : (uint32_t)((kb & 1) * 2);
               mma_fp4_block_scaled<kCtaGroup, kNV>(tmem_acc, mk(a_lo + kb * 2, kDescHiAB), mk(b_lo + kb * 2, kDescHiAB),
                                                    idesc_base | (sf_id << 4) | (sf_id << 29), tmem_sfa + chunk * 4,
@@ -320,8 +326,11 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmap_d, stg, n0 + col0 + ch * Cfg::EPI_CHUNK, m0 + q * 32);
+            if (lane == 0 && !(p.flags & 16)) {
+              // profiling flag 8: every store lands on the first tile (same lines over and over: L2-resident)
+              const int cx = (p.flags & 8) ? (col0 + ch * Cfg::EPI_CHUNK) : (n0 + col0 + ch * Cfg::EPI_CHUNK);
+              const int cy = (p.flags & 8) ? (q * 32) : (m0 + q * 32);
+              tma_store_2d(&tmap_d, stg, cx, cy);
               bulk_commit_group();
             }
           }

@@ -53,7 +53,7 @@ def to_blocked(input_matrix: torch.Tensor, use_triton_kernel: bool = False) -> t
     out = torch.empty(ceil_div(rows, 128) * 128 * ceil_div(cols, 4) * 4, dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().b200q_swizzle_sf(x.data_ptr(), out.data_ptr(), rows, cols,
-                                                torch.cuda.current_stream().cuda_stream))
+                                                torch._C._cuda_getCurrentRawStream(x.device.index)))
     return out
 
 

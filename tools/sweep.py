@@ -77,6 +77,9 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "quant"]
     if "quant" in which:
         quant_sweep()
+    if "gemmst" in which:
+        gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 256), (2, 192)], [(0, 2), (64, 2), (1, 2), (65, 2), (33, 2)])
+        gemm_sweep("nv", [(4096, 14336, 4096)], [(2, 256)], [(0, 2), (64, 2), (33, 2)])
     if "gemmq" in which:
         gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (1, 2), (4, 2)])
         gemm_sweep("nv", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (4, 2)])
