@@ -190,7 +190,7 @@ def main():
     outs = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(NSETS)]
     lib = _lib.load()
     stream = torch.cuda.current_stream().cuda_stream
-    method = Q.METHOD_ABSMAX
+    method = Q.METHOD_ABSMAX | Q.ROT_TRUSTED_HADAMARD   # H is built right above: the caller-side hint of b200q.h
 
     def quant(i):
         s = i % NSETS

@@ -36,6 +36,11 @@ typedef struct CUstream_st* b200q_stream_t;
 
 #define B200Q_METHOD_QUEST 0   /* Quartet / "quest": std-based scale           */
 #define B200Q_METHOD_ABSMAX 1  /* abs-max scale                                */
+/* OR into `method`: the caller asserts rot == c * Sylvester-Hadamard (c any bf16 scalar, e.g.
+ * scipy.linalg.hadamard(H) * H**-0.5 as every reference test/benchmark builds it).  The kernel then skips its
+ * device-side structure check.  Without the flag the kernel verifies R itself (exact, on the device, graph-safe)
+ * and falls back to a generic x @ R for any other matrix. */
+#define B200Q_ROT_TRUSTED_HADAMARD 0x100
 
 #define B200Q_KIND_MXF4 0      /* e2m1 x e2m1, ue8m0 scales, group 32          */
 #define B200Q_KIND_NVF4 1      /* e2m1 x e2m1, ue4m3 scales, group 16          */

@@ -28,6 +28,7 @@ __all__ = [
 ]
 
 METHOD_QUEST, METHOD_ABSMAX = 0, 1
+ROT_TRUSTED_HADAMARD = 0x100   # include/b200q.h: B200Q_ROT_TRUSTED_HADAMARD
 KIND_MXF4, KIND_NVF4 = 0, 1
 
 
@@ -129,6 +130,43 @@ def matmul_nvf4_bf16_tn(a: torch.Tensor, b: torch.Tensor, a_sf: torch.Tensor, b_
 
 
 # --------------------------------------------------------------------------------------- quantise
+_ROT_CACHE = {}   # id(tensor) -> (weakref, _version, is_hadamard)
+
+
+def _rotation_hint(r: torch.Tensor) -> int:
+    """Exact host-side classification of the rotation matrix, cached per tensor object + version.
+
+    The reference's API takes *any* matrix at run time (README "loaded at runtime"); the kernel can verify the
+    Sylvester-Hadamard structure itself on the device (graph-safe) but that check is redundant work on every
+    call.  Here the (<= 32 KB) matrix is inspected ONCE on the host -- one small D2H copy -- and the result is
+    remembered for as long as that tensor object lives unmodified.  During CUDA-graph capture (no host sync
+    allowed) an unseen matrix simply gets no hint and the device-side check runs."""
+    import weakref
+    key = id(r)
+    ent = _ROT_CACHE.get(key)
+    if ent is not None and ent[0]() is r and ent[1] == r._version:
+        return ROT_TRUSTED_HADAMARD if ent[2] else 0
+    if r.is_cuda and torch.cuda.is_current_stream_capturing():
+        return 0
+    h = r.size(0)
+    m = r.detach().to("cpu").view(torch.int16)                 # bit patterns (synchronises once)
+    idx = torch.arange(h)
+    bits = idx[:, None] & idx[None, :]
+    par = torch.zeros_like(bits)
+    while bits.any():
+        par ^= bits & 1
+        bits = bits >> 1
+    c = int(m[0, 0])
+    want = torch.where(par.bool(), torch.tensor(c ^ -0x8000, dtype=torch.int32), torch.tensor(c, dtype=torch.int32))
+    want = ((want + 0x8000) % 0x10000 - 0x8000).to(torch.int16)
+    is_h = bool(torch.equal(m, want))
+    if len(_ROT_CACHE) > 64:
+        for k in [k for k, v in _ROT_CACHE.items() if v[0]() is None]:
+            _ROT_CACHE.pop(k, None)
+    _ROT_CACHE[key] = (weakref.ref(r), r._version, is_h)
+    return ROT_TRUSTED_HADAMARD if is_h else 0
+
+
 def _quant_checks(name: str, a, r, outs, extra=()):
     """reference checks: qutlass/csrc/bindings.cpp:218-252,292-333,335-426"""
     _check_contig(name, [("A", a), ("B", r)] + [(f"OUT{i}", o) for i, o in enumerate(outs)])
@@ -150,7 +188,7 @@ def _quantize_mx_into(a, r, out, out_sf, out_sf_blocked, out_mask, method: int):
             a.data_ptr(), r.data_ptr(), out.data_ptr(), out_sf.data_ptr() if out_sf is not None else None,
             out_sf_blocked.data_ptr() if out_sf_blocked is not None else None,
             out_mask.data_ptr() if out_mask is not None else None,
-            a.numel(), a.size(-1), had, method, _stream(a)))
+            a.numel(), a.size(-1), had, method | _rotation_hint(r), _stream(a)))
 
 
 def _quantize_nv_into(a, r, out, out_sf, out_sf_blocked, global_scale, method: int):
@@ -163,7 +201,7 @@ def _quantize_nv_into(a, r, out, out_sf, out_sf_blocked, global_scale, method: i
         _lib.check(_lib.load().b200q_quantize_nv(
             a.data_ptr(), r.data_ptr(), out.data_ptr(), out_sf.data_ptr() if out_sf is not None else None,
             out_sf_blocked.data_ptr() if out_sf_blocked is not None else None, global_scale.data_ptr(),
-            a.numel(), a.size(-1), had, method, _stream(a)))
+            a.numel(), a.size(-1), had, method | _rotation_hint(r), _stream(a)))
 
 
 def fusedQuantizeMx(a: torch.Tensor, b: torch.Tensor, *, method: Literal["quest", "abs_max"] = "quest",

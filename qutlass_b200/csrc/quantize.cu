@@ -40,6 +40,7 @@ struct QuantParams {
   int64_t padded_cols;
   int64_t rows;
   int64_t padded_rows;
+  int trust_hadamard;      // caller asserted R = c * Sylvester-Hadamard (B200Q_ROT_TRUSTED_HADAMARD)
 };
 
 __device__ __forceinline__ float rcp_approx_ftz(float a) {
@@ -113,7 +114,7 @@ __device__ __forceinline__ void fwht_lane_stage(float* v, int lane_bit) {
   }
 }
 
-template <int HAD, bool NV, int METHOD, bool MASK>
+template <int HAD, bool NV, int METHOD, bool MASK, bool TRUST>
 __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p) {
   // per-warp staging: 2 KB of bf16 (swizzled 16-B units) -- reused as fp32 scratch by the generic path
   __shared__ __align__(16) uint4 s_stage[kWarpsPerCta][128];
@@ -134,11 +135,12 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
     }
   }
 
+  bool ok = true;
+  if constexpr (!TRUST) {
   // ---- 1. rotation-structure check: R == c * (-1)^popcount(k & n) ?  (bitwise, bf16).  All 16-byte loads are
   //         issued before the first compare (one L2 round trip instead of one per iteration: the check was
   //         45 % of the kernel's stall samples at 4096 x 4096 when it ran as a dependent loop).
   const unsigned short c_bits = reinterpret_cast<const unsigned short*>(p.rot)[0];
-  bool ok = true;
   {
     constexpr int NU = HAD * HAD / 8;                         // 16-byte units in R
     constexpr int NCHK = (NU + kThreads - 1) / kThreads;
@@ -165,7 +167,9 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
       }
     }
   }
-  const bool is_hadamard = __syncthreads_and(ok) != 0;
+  }
+  // TRUST: the caller asserted (B200Q_ROT_TRUSTED_HADAMARD) that R is c * Sylvester-Hadamard -> no check, no generic path
+  const bool is_hadamard = TRUST ? true : (__syncthreads_and(ok) != 0);
   const float c_scale = __bfloat162float(p.rot[0]);
 
   float gs = 1.f, gs_rcp = 1.f;
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
     }
 
     // ---- rotation
-    if (is_hadamard) {
+    if (TRUST || is_hadamard) {
       fwht_inreg<(HAD < 32 ? HAD : 32)>(v);
       if constexpr (HAD >= 64) fwht_lane_stage(v, 1);
       if constexpr (HAD >= 128) fwht_lane_stage(v, 2);
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p)
 #pragma unroll
         for (int i = 0; i < 16; ++i) B200Q_UNPK(v, i, __fmul2_rn(B200Q_PK(v, i), c2));
       }
-    } else {
+    } else if constexpr (!TRUST) {
       // generic x_group(1xH) @ R(HxH) for arbitrary runtime rotations (e.g. identity):
       // stage the fp32 x of the whole warp-tile in shared memory, fp32 FMA on CUDA cores.
       __shared__ float s_x[kWarpsPerCta][32 * 32];
@@ -685,13 +689,29 @@ static int launch_mma(const QuantParams& p, cudaStream_t stream) {
   return 0;
 }
 
+template <typename K>
+static int resident_ctas_per_sm(K kern, int threads, int dyn_smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, dyn_smem) != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+
 template <int HAD, bool NV, int METHOD, bool MASK>
 static int launch(const QuantParams& p, cudaStream_t stream) {
+  // exactly one persistent wave: SMs x (resident CTAs per SM as the occupancy calculator reports it)
+  static int occ_trust = 0, occ_check = 0;
+  if (!occ_trust) {
+    occ_trust = resident_ctas_per_sm(quantize_kernel<HAD, NV, METHOD, MASK, true>, kThreads, 0);
+    occ_check = resident_ctas_per_sm(quantize_kernel<HAD, NV, METHOD, MASK, false>, kThreads, 0);
+  }
   int64_t ctas = ceil_div(p.n_tiles, kWarpsPerCta);
-  const int64_t max_ctas = (int64_t)num_sms() * 4;   // 48 KB static smem -> 4 resident CTAs / SM: one persistent wave
+  const int64_t max_ctas = (int64_t)num_sms() * (p.trust_hadamard ? occ_trust : occ_check);
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
-  quantize_kernel<HAD, NV, METHOD, MASK><<<(unsigned)ctas, kThreads, 0, stream>>>(p);
+  if (p.trust_hadamard)
+    quantize_kernel<HAD, NV, METHOD, MASK, true><<<(unsigned)ctas, kThreads, 0, stream>>>(p);
+  else
+    quantize_kernel<HAD, NV, METHOD, MASK, false><<<(unsigned)ctas, kThreads, 0, stream>>>(p);
   B200Q_CUDA(cudaGetLastError());
   return 0;
 }
@@ -740,6 +760,7 @@ static int fill_params(QuantParams& p, const void* x, const void* rot, void* q, 
   p.cols = row_len / group;
   p.padded_rows = round_up(p.rows, 128);
   p.padded_cols = round_up(p.cols, 4);
+  p.trust_hadamard = 0;
   return 0;
 }
 
@@ -757,6 +778,8 @@ extern "C" int b200q_quantize_mx(const void* x_bf16, const void* rot_bf16, void*
   if (rc) return rc;
   B200Q_REQUIRE(sf_rowmajor || sf_blocked, "at least one scale output is required");
   p.mask = (uint32_t*)clip_mask;
+  p.trust_hadamard = (method & B200Q_ROT_TRUSTED_HADAMARD) ? 1 : 0;
+  method &= ~B200Q_ROT_TRUSTED_HADAMARD;
   cudaStream_t s = (cudaStream_t)stream;
   if (method == B200Q_METHOD_QUEST) {
     if (clip_mask) return dispatch_had<false, B200Q_METHOD_QUEST, true>(had, p, s);
@@ -780,6 +803,8 @@ extern "C" int b200q_quantize_nv(const void* x_bf16, const void* rot_bf16, void*
   B200Q_REQUIRE(sf_rowmajor || sf_blocked, "at least one scale output is required");
   B200Q_REQUIRE(global_scale_dev, "global_scale must be a device pointer to one float");
   p.gs = global_scale_dev;
+  p.trust_hadamard = (method & B200Q_ROT_TRUSTED_HADAMARD) ? 1 : 0;
+  method &= ~B200Q_ROT_TRUSTED_HADAMARD;
   cudaStream_t s = (cudaStream_t)stream;
   if (method == B200Q_METHOD_QUEST) return dispatch_had<true, B200Q_METHOD_QUEST, false>(had, p, s);
   if (method == B200Q_METHOD_ABSMAX) return dispatch_had<true, B200Q_METHOD_ABSMAX, false>(had, p, s);

@@ -140,6 +140,39 @@ def test_quantize_edge_cases():
     np.testing.assert_array_equal(dq, O.dequant_mx(ref["q"].reshape(64, 128), ref["sf"].reshape(64, 8)))
 
 
+@pytest.mark.parametrize("kind", ["mx", "nv"])
+@pytest.mark.parametrize("had", [32, 64, 128])
+def test_quantize_device_check_equals_trusted_hint(kind, had):
+    """C-ABI: with B200Q_ROT_TRUSTED_HADAMARD the kernel skips its device-side structure check; without it the
+    kernel verifies R itself.  Both must give identical bytes (the Python API passes the hint after an exact,
+    cached host-side inspection of R; a CUDA-graph capture of an unseen R takes the device-check path)."""
+    lib = _lib.load()
+    rows, k = 200, 1024
+    x = H.bf16_tensor_from_f32(H.random_bf16((rows, k), seed=had + 7))
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(had))
+    group = 32 if kind == "mx" else 16
+    outs = []
+    st = torch.cuda.current_stream().cuda_stream
+    gs = torch.tensor([1.0], device="cuda")
+    for flag in (0, Q.ROT_TRUSTED_HADAMARD):
+        q = torch.zeros(rows, k // 2, dtype=torch.uint8, device="cuda")
+        sf = torch.zeros(256 * (k // group), dtype=torch.uint8, device="cuda")
+        blk = torch.zeros(256 * (k // group), dtype=torch.uint8, device="cuda")
+        if kind == "mx":
+            rc = lib.b200q_quantize_mx(x.data_ptr(), R.data_ptr(), q.data_ptr(), sf.data_ptr(), blk.data_ptr(), None,
+                                       rows * k, k, had, Q.METHOD_QUEST | flag, st)
+        else:
+            rc = lib.b200q_quantize_nv(x.data_ptr(), R.data_ptr(), q.data_ptr(), sf.data_ptr(), blk.data_ptr(),
+                                       gs.data_ptr(), rows * k, k, had, Q.METHOD_ABSMAX | flag, st)
+        assert rc == 0, lib.b200q_last_error()
+        torch.cuda.synchronize()
+        outs.append((q.cpu(), sf.cpu(), blk.cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert Q._rotation_hint(R) == Q.ROT_TRUSTED_HADAMARD
+    assert Q._rotation_hint(torch.eye(had, dtype=torch.bfloat16, device="cuda")) == 0
+
+
 def test_error_behaviour():
     R = torch.eye(32, dtype=torch.bfloat16, device="cuda")
     x = torch.zeros(4, 64, dtype=torch.bfloat16, device="cuda")

@@ -41,9 +41,9 @@ def sweep(kind, N, K, Ms, had=128):
         d = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
         def quant(st):
             if kind == "mx":
-                rc = lib.b200q_quantize_mx(x.data_ptr(), H.data_ptr(), a.data_ptr(), None, sfa.data_ptr(), None, M * K, K, had, 1, st)
+                rc = lib.b200q_quantize_mx(x.data_ptr(), H.data_ptr(), a.data_ptr(), None, sfa.data_ptr(), None, M * K, K, had, 1 | 0x100, st)
             else:
-                rc = lib.b200q_quantize_nv(x.data_ptr(), H.data_ptr(), a.data_ptr(), None, sfa.data_ptr(), gs.data_ptr(), M * K, K, had, 1, st)
+                rc = lib.b200q_quantize_nv(x.data_ptr(), H.data_ptr(), a.data_ptr(), None, sfa.data_ptr(), gs.data_ptr(), M * K, K, had, 1 | 0x100, st)
             assert rc == 0, lib.b200q_last_error()
         def gemm(st):
             rc = lib.b200q_gemm_fp4(a.data_ptr(), b.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), alpha.data_ptr(), d.data_ptr(), M, N, K, knd, st)

@@ -94,13 +94,14 @@ if __name__ == "__main__":
                 gs = torch.ones(1, device=dev)
                 for had in (32, 64, 128):
                     H = torch.from_numpy(O.bf16_bits(O.hadamard_matrix(had)).astype(np.int16)).view(torch.bfloat16).to(dev)
-                    for bf in ("0", "1"):
-                        os.environ["B200Q_QUANT_MMA"] = "0" if bf == "1" else "1"
+                    for bf in ("1", "T"):
+                        os.environ["B200Q_QUANT_MMA"] = "0"
+                        TRUST = 0x100 if bf == "T" else 0
                         st = torch.cuda.current_stream().cuda_stream
                         if kind == "mx":
-                            fn = lambda: lib.b200q_quantize_mx(x.data_ptr(), H.data_ptr(), qo.data_ptr(), sfo.data_ptr(), sfb.data_ptr(), None, M * K, K, had, 1, st)
+                            fn = lambda: lib.b200q_quantize_mx(x.data_ptr(), H.data_ptr(), qo.data_ptr(), sfo.data_ptr(), sfb.data_ptr(), None, M * K, K, had, 1 | TRUST, st)
                         else:
-                            fn = lambda: lib.b200q_quantize_nv(x.data_ptr(), H.data_ptr(), qo.data_ptr(), sfo.data_ptr(), sfb.data_ptr(), gs.data_ptr(), M * K, K, had, 1, st)
+                            fn = lambda: lib.b200q_quantize_nv(x.data_ptr(), H.data_ptr(), qo.data_ptr(), sfo.data_ptr(), sfb.data_ptr(), gs.data_ptr(), M * K, K, had, 1 | TRUST, st)
                         us = timeit(fn, iters=50)
                         byts = M * K * (2.5 + 2.0 / group)
                         emit(check="quantk", kind=kind, M=M, K=K, had=had, butterfly=bf, us=round(us, 1), gbs=round(byts / us / 1e3, 0))
