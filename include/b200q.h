@@ -44,6 +44,9 @@ typedef struct CUstream_st* b200q_stream_t;
 
 #define B200Q_KIND_MXF4 0      /* e2m1 x e2m1, ue8m0 scales, group 32          */
 #define B200Q_KIND_NVF4 1      /* e2m1 x e2m1, ue4m3 scales, group 16          */
+#define B200Q_KIND_MXF8 2      /* e4m3 x e4m3 (one byte / element), ue8m0 scales, group 32 -- the "next"
+                                  row of the scope table: replaces matmul_host_mxf8_bf16_tn (gemm.cu:328-380);
+                                  A [M, K], B [N, K] bytes, same blocked scale layout                         */
 
 /* ABI version of this header (bumped on incompatible change). */
 int b200q_abi_version(void);

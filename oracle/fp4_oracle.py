@@ -31,7 +31,7 @@ __all__ = [
     "e8m0_decode", "e4m3_encode", "e4m3_decode",
     "rotate", "quantize_mx", "quantize_nv", "padded_sf_shape", "sf_rowmajor_padded",
     "to_blocked", "from_blocked", "swizzle_offset", "dequant_mx", "dequant_nv",
-    "gemm_ref", "is_sylvester_hadamard",
+    "gemm_ref", "is_sylvester_hadamard", "dequant_mxf8", "pseudoquant_mxfp8",
 ]
 
 # e2m1 code -> value; code = sign<<3 | {0,.5,1,1.5,2,3,4,6}   (tests/mxfp4_test.py:92-110)
@@ -394,3 +394,27 @@ def gemm_ref(a_dq, b_dq, alpha: float = 1.0) -> np.ndarray:
     acc = np.asarray(a_dq, dtype=np.float64) @ np.asarray(b_dq, dtype=np.float64).T
     acc = acc * float(alpha)
     return bf16_bits(bf16_round(acc))
+
+
+# --------------------------------------------------------------------------- MXFP8 ("next" row: matmul_mxf8_bf16_tn)
+def dequant_mxf8(q_e4m3, sf) -> np.ndarray:
+    """e4m3 bytes [..., K] * ue8m0 scale per 32 -> float64 (tests/mxfp8_test.py:42 `xq * shared_exps`)."""
+    vals = e4m3_decode(q_e4m3)
+    s = e8m0_decode(sf)
+    shp = vals.shape
+    return (vals.reshape(shp[:-1] + (-1, 32)) * s[..., None]).reshape(shp)
+
+
+def pseudoquant_mxfp8(x):
+    """_pseudoquant_mxfp8 (tests/mxfp8_test.py:27-46): shared exponent = floor(log2(amax)) - 8 (+127 bias, 2**0 when
+    the group is all zero), values = e4m3(clamp(x / 2**e, +-448)).  x holds bf16-representable values; the division
+    by a power of two is exact and the bf16 quotient converts to e4m3 with one RNE."""
+    x = np.asarray(x, dtype=np.float64)
+    g = x.reshape(-1, 32)
+    amax = np.abs(g).max(axis=-1)
+    with np.errstate(divide="ignore"):
+        e = np.where(amax > 0, np.floor(np.log2(np.where(amax > 0, amax, 1.0))) - 8 + 128, 128).astype(np.int64)
+    sf = (e & 0xFF).astype(np.uint8)       # the test stores the biased value as uint8 and views it as e8m0
+    scale = e8m0_decode(sf)
+    q = e4m3_encode(np.clip(g / scale[:, None], -448.0, 448.0).astype(np.float32))
+    return q.reshape(x.shape), sf.reshape(x.shape[:-1] + (x.shape[-1] // 32,))

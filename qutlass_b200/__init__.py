@@ -29,7 +29,7 @@ __all__ = [
 
 METHOD_QUEST, METHOD_ABSMAX = 0, 1
 ROT_TRUSTED_HADAMARD = 0x100   # include/b200q.h: B200Q_ROT_TRUSTED_HADAMARD
-KIND_MXF4, KIND_NVF4 = 0, 1
+KIND_MXF4, KIND_NVF4, KIND_MXF8 = 0, 1, 2
 
 
 def _check(cond: bool, msg: str) -> None:
@@ -82,9 +82,10 @@ def _matmul_fp4(name: str, a, b, a_sf, b_sf, alpha, kind: int, sf_dtype, min_k_b
     """reference checks: qutlass/csrc/bindings.cpp:32-102"""
     _check_contig(name, [("A", a), ("B", b), ("A_sf", a_sf), ("B_sf", b_sf)])
     _check_cuda_same(name, [("A", a), ("B", b), ("A_sf", a_sf), ("B_sf", b_sf), ("alpha", alpha)])
-    _check(a.dtype == torch.uint8, "A must be uint8")
-    _check(b.dtype == torch.uint8, "B must be uint8")
-    sf_name = "float8_e8m0fnu" if kind == KIND_MXF4 else "float8_e4m3fn"
+    op_dtype, op_name = (torch.float8_e4m3fn, "float8_e4m3fn") if kind == KIND_MXF8 else (torch.uint8, "uint8")
+    _check(a.dtype == op_dtype, f"A must be {op_name}")
+    _check(b.dtype == op_dtype, f"B must be {op_name}")
+    sf_name = "float8_e4m3fn" if kind == KIND_NVF4 else "float8_e8m0fnu"
     _check(a_sf.dtype == sf_dtype, f"A_sf must be {sf_name}")
     _check(b_sf.dtype == sf_dtype, f"B_sf must be {sf_name}")
     _check(a.dim() == 2 and b.dim() == 2, "A and B must be 2D")
@@ -92,8 +93,9 @@ def _matmul_fp4(name: str, a, b, a_sf, b_sf, alpha, kind: int, sf_dtype, min_k_b
     _check(a.size(1) >= min_k_bytes, f"A K-dim must be >= {min_k_bytes}")
     _check(b.size(1) >= min_k_bytes, f"B K-dim must be >= {min_k_bytes}")
     _check(alpha.dtype == torch.float32 and alpha.numel() >= 1, "alpha must be a float32 tensor with one element")
-    m, n, k = a.size(0), b.size(0), a.size(1) * 2
-    group = 32 if kind == KIND_MXF4 else 16
+    m, n, k = a.size(0), b.size(0), a.size(1) * (1 if kind == KIND_MXF8 else 2)
+    group = 16 if kind == KIND_NVF4 else 32
+    _check(k % 32 == 0, f"K ({k}) must be a multiple of 32")
     need_a = ((m + 127) // 128) * 128 * (((k // group) + 3) // 4) * 4
     need_b = ((n + 127) // 128) * 128 * (((k // group) + 3) // 4) * 4
     _check(a_sf.numel() >= need_a, f"A_sf has {a_sf.numel()} scales, the blocked layout needs {need_a}")
@@ -127,6 +129,15 @@ def matmul_nvf4_bf16_tn(a: torch.Tensor, b: torch.Tensor, a_sf: torch.Tensor, b_
     """D = bf16(alpha * dq(a) @ dq(b).T), NVFP4 (reference: qutlass/__init__.py:89-131)."""
     _backend_gate(backend)
     return _matmul_fp4("matmul_nvf4_bf16_tn", a, b, a_sf, b_sf, alpha, KIND_NVF4, torch.float8_e4m3fn, 16)
+
+
+def matmul_mxf8_bf16_tn(a: torch.Tensor, b: torch.Tensor, block_scale_a: torch.Tensor, block_scale_b: torch.Tensor,
+                        alpha: torch.Tensor) -> torch.Tensor:
+    """D = bf16(alpha * dq(a) @ dq(b).T), MXFP8: e4m3 operands [M,K] / [N,K], e8m0 blocked scales per 32
+    (reference: qutlass/__init__.py:134-139, bindings.cpp:140-176, gemm.cu:328-380) -- the first "next" row after
+    the FP4 path, same tcgen05 kernel with kind::mxf8f6f4."""
+    return _matmul_fp4("matmul_mxf8_bf16_tn", a, b, block_scale_a, block_scale_b, alpha, KIND_MXF8,
+                       torch.float8_e8m0fnu, 32)
 
 
 # --------------------------------------------------------------------------------------- quantise
@@ -257,8 +268,7 @@ def _out_of_scope(name: str):
 
 
 matmul_ada_mxf4_bf16_tn = _out_of_scope("matmul_ada_mxf4_bf16_tn")      # sm_120-only prototype (gemm_ada.cu)
-matmul_mxf8_bf16_tn = _out_of_scope("matmul_mxf8_bf16_tn")              # QAT backward GEMMs
-matmul_mxf8_bf16_nn = _out_of_scope("matmul_mxf8_bf16_nn")
+matmul_mxf8_bf16_nn = _out_of_scope("matmul_mxf8_bf16_nn")              # MN-major A operand (QAT backward)
 backward_t_bf16 = _out_of_scope("backward_t_bf16")
 backward_qt_bf16 = _out_of_scope("backward_qt_bf16")
 backward_bf16_square_double_mxfp8 = _out_of_scope("backward_bf16_square_double_mxfp8")
@@ -276,6 +286,7 @@ def _register_ops() -> None:
     defs = {
         "matmul_mxf4_bf16_tn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
         "matmul_nvf4_bf16_tn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
+        "matmul_mxf8_bf16_tn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
         "fusedQuantizeMxQuest": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf) -> (Tensor, Tensor)",
         "fusedQuantizeMxAbsMax": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf) -> (Tensor, Tensor)",
         "fusedQuantizeNvQuest": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf, Tensor global_scale) -> (Tensor, Tensor)",
@@ -285,6 +296,7 @@ def _register_ops() -> None:
     impls = {
         "matmul_mxf4_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_mxf4_bf16_tn(A, B, A_sf, B_sf, alpha),
         "matmul_nvf4_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_nvf4_bf16_tn(A, B, A_sf, B_sf, alpha),
+        "matmul_mxf8_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_mxf8_bf16_tn(A, B, A_sf, B_sf, alpha),
         "fusedQuantizeMxQuest": lambda A, R, OUT, OUT_sf: (_quantize_mx_into(A, R, OUT, OUT_sf, None, None, METHOD_QUEST), (OUT, OUT_sf))[1],
         "fusedQuantizeMxAbsMax": lambda A, R, OUT, OUT_sf: (_quantize_mx_into(A, R, OUT, OUT_sf, None, None, METHOD_ABSMAX), (OUT, OUT_sf))[1],
         "fusedQuantizeNvQuest": lambda A, R, OUT, OUT_sf, gs: (_quantize_nv_into(A, R, OUT, OUT_sf, None, gs, METHOD_QUEST), (OUT, OUT_sf))[1],

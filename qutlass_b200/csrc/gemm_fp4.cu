@@ -37,19 +37,21 @@ using namespace ptx;
 
 constexpr int BM = 128;          // rows of A per CTA
 constexpr int BK_BYTES = 128;    // one k-tile = 256 e2m1 = 128 bytes per row (one 128B-swizzle row)
-constexpr int BK = 256;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 320
 constexpr int kSmemBudget = 227 * 1024;
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false>
 struct GemmCfg {
   // A_ROWS < 128 (small M): only A_ROWS rows of the A tile are loaded and kept per stage; the MMA still reads a
   // 128-row operand (the bytes that follow) -- those accumulator rows are garbage and never stored.  Smaller
   // stages = more k-tiles of B in flight, which is what bounds the weight-streaming (decode) regime.
   static_assert(A_ROWS % 8 == 0 && A_ROWS >= 8 && A_ROWS <= 128 && (A_ROWS == 128 || kCtaGroup == 1), "A_ROWS");
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 64 in [64, 256]");
-  static constexpr int SFKB = kNV ? 4 : 2;                       // 512-B scale blocks per 128 rows per k-tile
+  // kF8: 8-bit e4m3 operands (MXFP8, ue8m0 scales per 32): a 128-byte k-tile is 128 elements = 4 scales = one block
+  static constexpr int SFKB = kNV ? 4 : (kF8 ? 1 : 2);           // 512-B scale blocks per 128 rows per k-tile
+  static constexpr int BK_ELEMS = kF8 ? 128 : 256;               // K elements per k-tile (128 bytes per row)
+  static constexpr int MMA_K = kF8 ? 32 : 64;                    // K elements per tcgen05.mma (32 bytes per row)
   // a BN-wide tile starts at a multiple of 64 rows of B: its scales begin 0 or 2 TMEM columns into a block
   static constexpr int NB = (BN % 128 == 0) ? BN / 128 : (BN + 64 + 127) / 128;   // SFB row-blocks a tile can touch
   static constexpr int B_ROWS = BN / kCtaGroup;                  // B rows this CTA stages
@@ -57,7 +59,8 @@ struct GemmCfg {
   static constexpr int B_BYTES = B_ROWS * BK_BYTES;
   static constexpr int SFA_BYTES = SFKB * 512;
   static constexpr int SFB_BYTES = NB * SFKB * 512;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + SFA_BYTES + SFB_BYTES;
+  static constexpr int LOAD_BYTES = A_BYTES + B_BYTES + SFA_BYTES + SFB_BYTES;      // bytes one CTA's TMA loads deliver per stage
+  static constexpr int STAGE_BYTES = (LOAD_BYTES + 1023) / 1024 * 1024;            // stage pitch keeps the 128B-swizzle alignment
   static constexpr int SFA_COLS = SFKB * 4;
   static constexpr int SFB_COLS = SFKB * 4 * NB;
   static constexpr int SF_COLS = SFA_COLS + SFB_COLS;
@@ -74,7 +77,7 @@ struct GemmCfg {
   static constexpr int STAGES_RAW = (kSmemBudget - BAR_BYTES - 1024 - STG_TOTAL) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_TOTAL + BAR_BYTES + 1024;  // +1024 alignment slack
-  static constexpr uint32_t TX_BYTES = (uint32_t)STAGE_BYTES * kCtaGroup;   // what the (leader's) full barrier expects
+  static constexpr uint32_t TX_BYTES = (uint32_t)LOAD_BYTES * kCtaGroup;   // what the (leader's) full barrier expects
   static_assert(TMEM_USED <= 512, "TMEM overflow");
   static_assert(STAGES >= 2, "not enough shared memory for 2 stages");
   static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-byte alignment for the 128B swizzle");
@@ -92,12 +95,12 @@ struct GemmParams {
   int flags;          // profiling: bit0 skip stores, bit1 skip TMEM loads
 };
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS, bool kF8>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb,
                 const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
-  using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS>;
+  using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ACC = Cfg::ACC_STAGES;
   constexpr int SFKB = Cfg::SFKB;
@@ -197,7 +200,9 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // descriptors are pre-split into a constant high word and a low word that is one add away per op.
       // (Measured: issuing the scale copies of k-tile g+1 ahead of the MMAs of k-tile g is SLOWER -- the
       // tensor pipe runs cp/mma in order -- so the order is cp(g), mma(g).)
-      constexpr uint32_t idesc_base = make_idesc_fp4(BM * kCtaGroup, BN, !kNV);
+      // instruction descriptor: e2m1 operands (format 1) for the mxf4 kinds, e4m3 (format 0) for mxf8f6f4
+      constexpr uint32_t idesc_base = kF8 ? (make_idesc_fp4(BM * kCtaGroup, BN, true) & ~((1u << 7) | (1u << 10)))
+                                          : make_idesc_fp4(BM * kCtaGroup, BN, !kNV);
       constexpr uint32_t kDescHiAB = (1024u >> 4) | (1u << 14) | (kLayoutSw128 << 29);   // SBO 1024 B, version 1, 128B swizzle
       constexpr uint32_t kDescHiSF = (128u >> 4) | (1u << 14);                            // SBO 128 B, version 1, no swizzle
       constexpr uint32_t kStage16 = Cfg::STAGE_BYTES >> 4;
@@ -221,7 +226,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const uint32_t tmem_acc = tmem_base + acc * BN;
         const uint32_t tsfb = tmem_sfb + sfb_shift;
         int k_left = p.K;
-        for (int kt = 0; kt < p.k_tiles; ++kt, k_left -= BK) {
+        for (int kt = 0; kt < p.k_tiles; ++kt, k_left -= Cfg::BK_ELEMS) {
           mbar_wait(bar_base + 8u * stage, phase, 3);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + stage * kStage16;
@@ -248,11 +253,12 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           // 4 MMAs of K = 64 (32 bytes = 2 x 16 B along the swizzled row each); K tail issues fewer
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
-            const uint32_t chunk = kNV ? kb : (kb >> 1);
-            if (!upfront && !skip_cp && (kNV || (kb & 1) == 0)) copy_chunk((int)chunk);
-            if (k_left > kb * 64) {
-              const uint32_t sf_id = kNV ? 0u : (uint32_t)((kb & 1) * 2);
-              mma_fp4_block_scaled<kCtaGroup, kNV>(tmem_acc, mk(a_lo + kb * 2, kDescHiAB), mk(b_lo + kb * 2, kDescHiAB),
+            // scales per MMA: MXF4 2 bytes (sf_id 0/2 of a 4-byte cell), NVF4 a whole cell, MXF8 1 byte (sf_id = kb)
+            const uint32_t chunk = kNV ? kb : (kF8 ? 0 : (kb >> 1));
+            if (!upfront && !skip_cp && (kNV || (kF8 ? kb == 0 : (kb & 1) == 0))) copy_chunk((int)chunk);
+            if (k_left > kb * Cfg::MMA_K) {
+              const uint32_t sf_id = kNV ? 0u : (kF8 ? (uint32_t)kb : (uint32_t)((kb & 1) * 2));
+              mma_fp4_block_scaled<kCtaGroup, kNV, kF8>(tmem_acc, mk(a_lo + kb * 2, kDescHiAB), mk(b_lo + kb * 2, kDescHiAB),
                                                    idesc_base | (sf_id << 4) | (sf_id << 29), tmem_sfa + chunk * 4,
                                                    tsfb + chunk * (4 * NB), (kt > 0 || kb > 0) ? 1u : 0u);
             }
@@ -448,11 +454,11 @@ static int make_d_tmap(CUtensorMap* tm, const void* ptr, int64_t M, int64_t N, i
                 chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "D");
 }
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false>
 static int launch_gemm(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D,
                        int M, int N, int K, cudaStream_t stream) {
-  using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS>;
-  auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV, A_ROWS>;
+  using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8>;
+  auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV, A_ROWS, kF8>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -462,8 +468,9 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   const int64_t sf_col_blocks = ceil_div(ceil_div(K, group), 4);
   CUtensorMap ta, tb, tsa, tsb, td;
   int rc;
-  if ((rc = make_operand_tmap(&ta, A, M, K / 2, A_ROWS, "A"))) return rc;
-  if ((rc = make_operand_tmap(&tb, B, N, K / 2, Cfg::B_ROWS, "B"))) return rc;
+  const int64_t row_bytes = kF8 ? K : K / 2;
+  if ((rc = make_operand_tmap(&ta, A, M, row_bytes, A_ROWS, "A"))) return rc;
+  if ((rc = make_operand_tmap(&tb, B, N, row_bytes, Cfg::B_ROWS, "B"))) return rc;
   if ((rc = make_sf_tmap(&tsa, SFA, ceil_div(M, 128), sf_col_blocks, Cfg::SFKB, 1, "SFA"))) return rc;
   if ((rc = make_sf_tmap(&tsb, SFB, ceil_div(N, 128), sf_col_blocks, Cfg::SFKB, Cfg::NB, "SFB"))) return rc;
   GemmParams p;
@@ -472,7 +479,7 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   p.M = M; p.N = N; p.K = K;
   p.tiles_m = (int)ceil_div(M, BM * kCtaGroup);
   p.tiles_n = (int)ceil_div(N, BN);
-  p.k_tiles = (int)ceil_div(K, BK);
+  p.k_tiles = (int)ceil_div(K, Cfg::BK_ELEMS);
   p.tma_store = (N % 8 == 0) ? 1 : 0;
   {
     const char* f = getenv("B200Q_GEMM_DEBUG_FLAGS");
@@ -503,21 +510,24 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   return 0;
 }
 
-template <bool kNV>
+template <bool kNV, bool kF8>
 static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B, const void* SFA, const void* SFB,
                         const float* alpha, void* D, int M, int N, int K, cudaStream_t s) {
+  // small M: same 128-wide single-CTA tile, fewer A rows staged (more weight k-tiles in flight)
+  if (cta_group == 1 && block_n == 128 && M <= 16) return launch_gemm<1, 128, kNV, 16, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, s);
+  if (cta_group == 1 && block_n == 128 && M <= 32) return launch_gemm<1, 128, kNV, 32, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, s);
+  if (cta_group == 1 && block_n == 128 && M <= 64) return launch_gemm<1, 128, kNV, 64, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, s);
 #define B200Q_CASE(CG, BNV) \
-  if (cta_group == CG && block_n == BNV) return launch_gemm<CG, BNV, kNV>(A, B, SFA, SFB, alpha, D, M, N, K, s);
-  if (cta_group == 1 && block_n == 128 && M <= 16) return launch_gemm<1, 128, kNV, 16>(A, B, SFA, SFB, alpha, D, M, N, K, s);
-  if (cta_group == 1 && block_n == 128 && M <= 32) return launch_gemm<1, 128, kNV, 32>(A, B, SFA, SFB, alpha, D, M, N, K, s);
-  if (cta_group == 1 && block_n == 128 && M <= 64) return launch_gemm<1, 128, kNV, 64>(A, B, SFA, SFB, alpha, D, M, N, K, s);
-  B200Q_CASE(1, 64)
+  if (cta_group == CG && block_n == BNV) return launch_gemm<CG, BNV, kNV, 128, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, s);
   B200Q_CASE(1, 128)
-  B200Q_CASE(1, 192)
   B200Q_CASE(1, 256)
   B200Q_CASE(2, 128)
   B200Q_CASE(2, 192)
   B200Q_CASE(2, 256)
+  if constexpr (!kF8) {
+    B200Q_CASE(1, 64)
+    B200Q_CASE(1, 192)
+  }
 #undef B200Q_CASE
   set_error("unsupported GEMM configuration cta_group=%d block_n=%d", cta_group, block_n);
   return B200Q_EINVAL;
@@ -533,7 +543,7 @@ extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA,
   int rc = check_device_sm100();
   if (rc) return rc;
   B200Q_REQUIRE(A && B && SFA && SFB && alpha_dev && D_bf16, "null pointer argument");
-  B200Q_REQUIRE(kind == B200Q_KIND_MXF4 || kind == B200Q_KIND_NVF4, "invalid kind %d", kind);
+  B200Q_REQUIRE(kind == B200Q_KIND_MXF4 || kind == B200Q_KIND_NVF4 || kind == B200Q_KIND_MXF8, "invalid kind %d", kind);
   B200Q_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive (got %d, %d, %d)", M, N, K);
   B200Q_REQUIRE(K % 32 == 0, "K (%d) must be a multiple of 32", K);
   B200Q_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)SFA | (uintptr_t)SFB) & 15) == 0,
@@ -559,8 +569,9 @@ extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA,
     }
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (kind == B200Q_KIND_NVF4) return dispatch_cfg<true>(cta_group, block_n, A, B, SFA, SFB, alpha_dev, D_bf16, M, N, K, s);
-  return dispatch_cfg<false>(cta_group, block_n, A, B, SFA, SFB, alpha_dev, D_bf16, M, N, K, s);
+  if (kind == B200Q_KIND_NVF4) return dispatch_cfg<true, false>(cta_group, block_n, A, B, SFA, SFB, alpha_dev, D_bf16, M, N, K, s);
+  if (kind == B200Q_KIND_MXF8) return dispatch_cfg<false, true>(cta_group, block_n, A, B, SFA, SFB, alpha_dev, D_bf16, M, N, K, s);
+  return dispatch_cfg<false, false>(cta_group, block_n, A, B, SFA, SFB, alpha_dev, D_bf16, M, N, K, s);
 }
 
 extern "C" int b200q_gemm_fp4(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha_dev,

@@ -217,37 +217,27 @@ __device__ __forceinline__ uint32_t idesc_with_sf_id(uint32_t idesc, uint32_t a_
 
 // ------------------------------------------------------------------ tcgen05: MMA / cp / commit / ld
 // D[tmem] (+)= A[smem] * B[smem] with per-block scales from TMEM.  One thread issues.
-template <int kCtaGroup, bool kNV>
+//   kNV: kind::mxf4nvf4 block16 (ue4m3 scales);  kF8: kind::mxf8f6f4 block32 (8-bit operands, K = 32);
+//   otherwise kind::mxf4 block32 (ue8m0 scales, K = 64).
+#define B200Q_MMA_BS(CG, KINDSTR)                                                                                  \
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"                                                        \
+               "tcgen05.mma.cta_group::" CG ".kind::" KINDSTR " [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d), \
+               "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)                   \
+               : "memory")
+template <int kCtaGroup, bool kNV, bool kF8 = false>
 __device__ __forceinline__ void mma_fp4_block_scaled(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                      uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate) {
   if constexpr (kCtaGroup == 1) {
-    if constexpr (kNV)
-      asm volatile(
-          "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-          "tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.block16 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
-          "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
-          : "memory");
-    else
-      asm volatile(
-          "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-          "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
-          "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
-          : "memory");
+    if constexpr (kF8) B200Q_MMA_BS("1", "mxf8f6f4.block_scale");
+    else if constexpr (kNV) B200Q_MMA_BS("1", "mxf4nvf4.block_scale.block16");
+    else B200Q_MMA_BS("1", "mxf4.block_scale.block32");
   } else {
-    if constexpr (kNV)
-      asm volatile(
-          "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-          "tcgen05.mma.cta_group::2.kind::mxf4nvf4.block_scale.block16 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
-          "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
-          : "memory");
-    else
-      asm volatile(
-          "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-          "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
-          "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
-          : "memory");
+    if constexpr (kF8) B200Q_MMA_BS("2", "mxf8f6f4.block_scale");
+    else if constexpr (kNV) B200Q_MMA_BS("2", "mxf4nvf4.block_scale.block16");
+    else B200Q_MMA_BS("2", "mxf4.block_scale.block32");
   }
 }
+#undef B200Q_MMA_BS
 
 // bf16 x bf16 -> fp32 (kind::f16), used by the probe / rotation experiments
 template <int kCtaGroup>

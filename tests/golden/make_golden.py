@@ -11,6 +11,7 @@ copied into this repo):
   * /root/reference/tests/nvfp4_test.py : the NV flavours of the same (lines 36-170)
   * /root/reference/qutlass/utils.py    : ceil_div, get_padded_shape_mx/_nv, to_blocked
     (torch path, lines 136-193)
+  * /root/reference/tests/mxfp8_test.py : _pseudoquant_mxfp8 (lines 27-46, decorator stripped)
 
 Usage:  python tests/golden/make_golden.py
 """
@@ -32,6 +33,7 @@ def lift(path, names):
     ns = {"torch": torch, "np": np, "hadamard": hadamard}
     for node in tree.body:
         if isinstance(node, ast.FunctionDef) and node.name in names:
+            node.decorator_list = []      # e.g. @torch.compile on _pseudoquant_mxfp8: run it eagerly
             mod = ast.Module(body=[node], type_ignores=[])
             exec(compile(mod, path, "exec"), ns)
     missing = [n for n in names if n not in ns]
@@ -149,6 +151,21 @@ def main():
     out["nvg_a_q"] = a_q.numpy(); out["nvg_a_s"] = u8(a_s)
     out["nvg_b_q"] = b_q.numpy(); out["nvg_b_s"] = u8(b_s)
     out["nvg_out_bits"] = bits((a_dq @ b_dq.transpose(-2, -1)).to(torch.bfloat16))
+
+    # ---- MXFP8 ("next" row): the reference's pseudo-quantiser + GEMM reference (tests/mxfp8_test.py:27-78)
+    f8 = lift(f"{REF}/tests/mxfp8_test.py", ["_pseudoquant_mxfp8"])
+    torch.manual_seed(2)
+    m, n, k = 24, 40, 256
+    a = torch.rand(m, k, dtype=torch.bfloat16) * 25.0
+    b = torch.rand(n, k, dtype=torch.bfloat16) * 25.0
+    a[0, :32] = 0
+    a_dq, (a_q, a_s) = f8["_pseudoquant_mxfp8"](a)
+    b_dq, (b_q, b_s) = f8["_pseudoquant_mxfp8"](b)
+    out["f8_a_bits"] = bits(a); out["f8_b_bits"] = bits(b)
+    out["f8_a_q"] = u8(a_q); out["f8_a_s"] = u8(a_s)
+    out["f8_b_q"] = u8(b_q); out["f8_b_s"] = u8(b_s)
+    out["f8_out_bits"] = bits((a_dq @ b_dq.transpose(-2, -1)).to(torch.bfloat16))
+    out["f8_out64_bits"] = bits((a_dq.double() @ b_dq.double().transpose(-2, -1)).to(torch.bfloat16))
 
     path = os.path.join(OUT, "reference_vectors.npz")
     np.savez_compressed(path, **out)

@@ -65,8 +65,20 @@ def blocked_sf(sf_rowmajor: np.ndarray, fill: int = 0) -> np.ndarray:
     return O.to_blocked(padded)
 
 
+def random_f8_operand(rows: int, k: int, seed: int, sf_mode: str = "narrow"):
+    """random e4m3 bytes [rows, k] (finite) + ue8m0 scale bytes [rows, k/32]."""
+    rng = np.random.default_rng(seed)
+    q = rng.integers(0, 256, size=(rows, k), dtype=np.uint8)
+    q = np.where((q & 0x7F) == 0x7F, q & 0xF0, q).astype(np.uint8)      # no NaN encodings
+    if sf_mode == "narrow":
+        sf = rng.integers(126, 129, size=(rows, k // 32)).astype(np.uint8)
+    else:
+        sf = rng.integers(117, 138, size=(rows, k // 32)).astype(np.uint8)
+    return q, sf
+
+
 def gemm_oracle_bits(aq, asf, bq, bsf, kind: str, alpha: float = 1.0) -> np.ndarray:
-    dq = O.dequant_mx if kind == "mx" else O.dequant_nv
+    dq = {"mx": O.dequant_mx, "nv": O.dequant_nv, "f8": O.dequant_mxf8}[kind]
     return O.gemm_ref(dq(aq, asf), dq(bq, bsf), alpha)
 
 
@@ -76,15 +88,18 @@ def sf_torch(arr: np.ndarray, kind: str, device="cuda") -> torch.Tensor:
 
 
 def run_gemm(aq, asf, bq, bsf, kind: str, alpha: float = 1.0, cfg=(0, 0)) -> np.ndarray:
-    """Run the CUDA GEMM through the package's C-ABI path; returns bf16 bit patterns [M, N]."""
+    """Run the CUDA GEMM through the package's C-ABI path; returns bf16 bit patterns [M, N].
+    kind: 'mx' (MXFP4), 'nv' (NVFP4) or 'f8' (MXFP8: aq/bq are e4m3 bytes [rows, K])."""
     import qutlass_b200 as Q
     a = torch.from_numpy(aq).cuda()
     b = torch.from_numpy(bq).cuda()
-    a_sf = sf_torch(blocked_sf(asf), kind)
-    b_sf = sf_torch(blocked_sf(bsf), kind)
+    if kind == "f8":
+        a, b = a.view(torch.float8_e4m3fn), b.view(torch.float8_e4m3fn)
+    a_sf = sf_torch(blocked_sf(asf), "mx" if kind == "f8" else kind)
+    b_sf = sf_torch(blocked_sf(bsf), "mx" if kind == "f8" else kind)
     al = torch.tensor([alpha], dtype=torch.float32, device="cuda")
-    knd = Q.KIND_MXF4 if kind == "mx" else Q.KIND_NVF4
-    dt = torch.float8_e8m0fnu if kind == "mx" else torch.float8_e4m3fn
+    knd = {"mx": Q.KIND_MXF4, "nv": Q.KIND_NVF4, "f8": Q.KIND_MXF8}[kind]
+    dt = torch.float8_e4m3fn if kind == "nv" else torch.float8_e8m0fnu
     out = Q._matmul_fp4("test", a, b, a_sf, b_sf, al, knd, dt, 16, cfg=cfg)
     torch.cuda.synchronize()
     return bf16_bits_of(out)

@@ -200,6 +200,8 @@ def test_error_behaviour():
     with pytest.raises(ImportError):
         Q.matmul_mxf4_bf16_tn(a, a, sf, sf, al, backend="flashinfer")
     with pytest.raises(NotImplementedError):
+        Q.matmul_mxf8_bf16_nn(a, a, sf, sf, al)
+    with pytest.raises(RuntimeError, match="A must be float8_e4m3fn"):
         Q.matmul_mxf8_bf16_tn(a, a, sf, sf, al)
     # C-ABI error convention: negative code + message
     lib = _lib.load()
@@ -379,6 +381,49 @@ def test_linear_host_entry_point():
     want = Q.matmul_mxf4_bf16_tn(xq, wq, Q.to_blocked(xsf), wblk, al)
     torch.cuda.synchronize()
     assert torch.equal(d_host.cuda(), want)
+
+
+# ----------------------------------------------------------------------------- MXFP8 ("next" row of the scope table)
+@pytest.mark.parametrize("cfg", [(0, 0), (1, 128), (1, 256), (2, 128), (2, 192), (2, 256)])
+@pytest.mark.parametrize("shape", [(128, 128, 128), (256, 512, 1024), (504, 504, 2048), (16, 1000, 2176), (1, 504, 4096),
+                                   (130, 72, 96)])
+def test_mxfp8_gemm_vs_oracle(cfg, shape):
+    m, n, k = shape
+    aq, asf = H.random_f8_operand(m, k, seed=m + 11)
+    bq, bsf = H.random_f8_operand(n, k, seed=n + 12)
+    want = H.gemm_oracle_bits(aq, asf, bq, bsf, "f8", 1.0)
+    got = H.run_gemm(aq, asf, bq, bsf, "f8", 1.0, cfg=cfg)
+    a_dq, b_dq = O.dequant_mxf8(aq, asf), O.dequant_mxf8(bq, bsf)
+    scale = np.abs(a_dq) @ np.abs(b_dq).T
+    g = O.bf16_from_bits(got).astype(np.float64)
+    w = a_dq @ b_dq.T
+    assert (np.abs(g - w) <= REL_TOL * np.abs(w) + 2.0 ** -20 * scale).all()
+    assert (got != want).mean() <= 2e-2      # fp32 accumulation vs fp64: last-bit bf16 differences only
+
+
+def test_mxfp8_golden_and_reference_style(golden):
+    """golden vectors from the reference's _pseudoquant_mxfp8, then the reference's own test recipe
+    (tests/mxfp8_test.py:60-78: rand*25 -> pseudoquant -> to_blocked(.., True) -> matmul_mxf8_bf16_tn,
+    assert_close(atol=1e-1, rtol=1e-1)) at a Llama shape with batch 16."""
+    got = H.run_gemm(golden["f8_a_q"], golden["f8_a_s"], golden["f8_b_q"], golden["f8_b_s"], "f8", 1.0)
+    mism, rel = H.compare_bits(got, golden["f8_out64_bits"])
+    assert rel <= REL_TOL and mism <= 1e-2
+    m, n, k = 16, 4096, 4096
+    a = H.random_bf16((m, k), seed=81, dist="rand")
+    b = H.random_bf16((n, k), seed=82, dist="rand")
+    a_q, a_s = O.pseudoquant_mxfp8(a)
+    b_q, b_s = O.pseudoquant_mxfp8(b)
+    a_sf = torch.from_numpy(a_s).cuda().view(torch.float8_e8m0fnu)       # un-padded [M, K/32], like the reference test
+    b_sf = torch.from_numpy(b_s).cuda().view(torch.float8_e8m0fnu)
+    out = Q.matmul_mxf8_bf16_tn(torch.from_numpy(a_q).cuda().view(torch.float8_e4m3fn),
+                                torch.from_numpy(b_q).cuda().view(torch.float8_e4m3fn),
+                                Q.to_blocked(a_sf, True), Q.to_blocked(b_sf, True), torch.tensor([1.0], device="cuda"))
+    torch.cuda.synchronize()
+    ref = torch.from_numpy((O.dequant_mxf8(a_q, a_s) @ O.dequant_mxf8(b_q, b_s).T)).to(torch.bfloat16)
+    torch.testing.assert_close(out.cpu(), ref, atol=1e-1, rtol=1e-1)
+    assert (H.bf16_bits_of(out) != O.gemm_ref(O.dequant_mxf8(a_q, a_s), O.dequant_mxf8(b_q, b_s))).mean() <= 1e-2
+    with pytest.raises(NotImplementedError):
+        Q.matmul_mxf8_bf16_nn(out, out, out, out, out)
 
 
 # ----------------------------------------------------------------------------- full-size properties

@@ -28,7 +28,7 @@ def test_surface_matches_reference_names():
     assert inspect.signature(qutlass.matmul_mxf4_bf16_tn).parameters["backend"].default == "cutlass"
     assert inspect.signature(qutlass.utils.to_blocked).parameters["use_triton_kernel"].default is False
     for op in ("matmul_mxf4_bf16_tn", "matmul_nvf4_bf16_tn", "fusedQuantizeMxQuest", "fusedQuantizeMxAbsMax",
-               "fusedQuantizeNvQuest", "fusedQuantizeNvAbsMax", "fusedQuantizeMxQuestWithMask"):
+               "fusedQuantizeNvQuest", "fusedQuantizeNvAbsMax", "fusedQuantizeMxQuestWithMask", "matmul_mxf8_bf16_tn"):
         assert hasattr(torch.ops._qutlass_C, op)
 
 

@@ -144,3 +144,15 @@ def test_e8m0_decode():
     assert O.e8m0_decode(np.uint8(127)) == 1.0
     assert O.e8m0_decode(np.uint8(0)) == 2.0 ** -127
     assert np.isnan(O.e8m0_decode(np.uint8(255)))
+
+
+def test_mxfp8_pseudoquant_and_gemm_golden(golden):
+    """'next' row (matmul_mxf8_bf16_tn): the oracle's MXFP8 pseudo-quantiser and GEMM criterion against vectors from
+    the reference's _pseudoquant_mxfp8 (tests/mxfp8_test.py:27-78)."""
+    for t in ("a", "b"):
+        x = O.bf16_from_bits(golden[f"f8_{t}_bits"])
+        q, s = O.pseudoquant_mxfp8(x)
+        np.testing.assert_array_equal(q, golden[f"f8_{t}_q"])
+        np.testing.assert_array_equal(s, golden[f"f8_{t}_s"])
+    out = O.gemm_ref(O.dequant_mxf8(golden["f8_a_q"], golden["f8_a_s"]), O.dequant_mxf8(golden["f8_b_q"], golden["f8_b_s"]))
+    np.testing.assert_array_equal(out, golden["f8_out64_bits"])
