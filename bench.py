@@ -85,6 +85,21 @@ class ClockSampler:
                     power_w_max=max(pw))
 
 
+def _ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same command (profiles/r01_ncu_gemm_summary.txt); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_gemm_summary.txt")
+    try:
+        import re
+        line = open(p).readline()
+        rd = re.search(r"dram__bytes_read.sum=([0-9.]+) (\w+)", line)
+        wr = re.search(r"dram__bytes_write.sum=([0-9.]+) (\w+)", line)
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        return float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)]
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """CPU arm: the reference's test-oracle path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -266,7 +281,9 @@ def main():
         ach = flops / (ms_gemm * 1e-3) / 1e12
         line["roofline"] = {
             "bound": "tensor", "achieved": ach, "peak": fp4_peak, "unit": "TFLOP/s", "frac": ach / fp4_peak,
-            "traffic": None,
+            "traffic": _ncu_traffic_bytes() if (kind == "mx" and world == 1) else None,
+            "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/); algorithmic bytes "
+                            f"= {M * K // 2 + N * K // 2 + (M + N) * K // group + 2 * M * N}",
             "peak_basis": f"4 x {pk['source']} sustained cuBLAS bf16 ({pk['bf16_sustained']} TF/s): kind::mxf4 issues 4x the MACs "
                           "per tcgen05.mma slot of kind::f16; no FP4 figure in MEASURED_PEAKS.json",
             "frac_of_nominal_9PF": ach / NOMINAL_FP4_TFLOPS,

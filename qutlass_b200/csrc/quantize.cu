@@ -115,7 +115,7 @@ __device__ __forceinline__ void fwht_lane_stage(float* v, int lane_bit) {
 }
 
 template <int HAD, bool NV, int METHOD, bool MASK, bool TRUST>
-__global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantParams p) {
+__global__ void __launch_bounds__(kThreads, 3) quantize_kernel(const QuantParams p) {
   // per-warp staging: 2 KB of bf16 (swizzled 16-B units) -- reused as fp32 scratch by the generic path
   __shared__ __align__(16) uint4 s_stage[kWarpsPerCta][128];
 

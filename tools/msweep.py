@@ -63,6 +63,19 @@ if __name__ == "__main__":
     sweep("mx", 14336, 4096, Ms)
     sweep("nv", 14336, 4096, Ms)
     sweep("mx", 28672, 8192, [2048, 4096, 8192, 16384])     # Llama-3-70B FFN: per-GPU shards of M=16384 over 8/4/2/1 GPUs
+    # MXFP8 GEMM only ("next" row): e4m3 operands, ue8m0 scales per 32
+    for M in (16, 1024, 4096):
+        N, K = 14336, 4096
+        a = torch.randint(0, 120, (M, K), dtype=torch.uint8, device=dev); b = torch.randint(0, 120, (N, K), dtype=torch.uint8, device=dev)
+        sfa = torch.randint(126, 129, (((M + 127) // 128) * 128 * (K // 32),), dtype=torch.uint8, device=dev)
+        sfb = torch.randint(126, 129, (N * (K // 32),), dtype=torch.uint8, device=dev)
+        d = torch.empty(M, N, dtype=torch.bfloat16, device=dev); alpha = torch.ones(1, device=dev)
+        def gemm8(st):
+            rc = lib.b200q_gemm_fp4(a.data_ptr(), b.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), alpha.data_ptr(), d.data_ptr(), M, N, K, 2, st)
+            assert rc == 0, lib.b200q_last_error()
+        t = graph_time(gemm8, 20)
+        rec = dict(kind="mxf8", N=N, K=K, M=M, gemm_us=round(t, 2), quant_us=0, both_us=0, gemm_tflops=round(2.0 * M * N * K / t / 1e6, 1), actual_tflops=0)
+        rows_out.append(rec); print(json.dumps(rec), flush=True)
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", "r01_msweep.md"), "w") as f:
         f.write("# M sweep (one B200, CUDA-graph replay, best of 3; quantise = Hadamard-128 abs_max)\n\n")
