@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from .utils import (get_padded_shape_mx, get_padded_shape_nv, pad_to_block, to_blocked,  # noqa: F401
-                    _attach_blocked)
+                    _attach_blocked, _version_of)
 
 __all__ = [
     "matmul_mxf4_bf16_tn", "matmul_nvf4_bf16_tn", "fusedQuantizeMx", "fusedQuantizeNv",
@@ -155,7 +155,8 @@ def _rotation_hint(r: torch.Tensor) -> int:
     import weakref
     key = id(r)
     ent = _ROT_CACHE.get(key)
-    if ent is not None and ent[0]() is r and ent[1] == r._version:
+    ver = _version_of(r)
+    if ent is not None and ent[0]() is r and ent[1] == ver:
         return ROT_TRUSTED_HADAMARD if ent[2] else 0
     if r.is_cuda and torch.cuda.is_current_stream_capturing():
         return 0
@@ -174,7 +175,7 @@ def _rotation_hint(r: torch.Tensor) -> int:
     if len(_ROT_CACHE) > 64:
         for k in [k for k, v in _ROT_CACHE.items() if v[0]() is None]:
             _ROT_CACHE.pop(k, None)
-    _ROT_CACHE[key] = (weakref.ref(r), r._version, is_h)
+    _ROT_CACHE[key] = (weakref.ref(r), ver, is_h)
     return ROT_TRUSTED_HADAMARD if is_h else 0
 
 

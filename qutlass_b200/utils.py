@@ -26,8 +26,17 @@ def get_padded_shape_nv(a: torch.Tensor):
     return ceil_div(rows, 128) * 128, ceil_div(cols, 4) * 4
 
 
+def _version_of(t: torch.Tensor) -> int:
+    """Tensor version counter, or -1 for inference tensors (created under torch.inference_mode -- as the reference's
+    tests do -- they do not track versions; in-place edits of such a tensor are then not detectable)."""
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
 def _attach_blocked(sf_rowmajor: torch.Tensor, blocked: torch.Tensor) -> None:
-    setattr(sf_rowmajor, _BLOCKED_ATTR, (blocked, sf_rowmajor._version))
+    setattr(sf_rowmajor, _BLOCKED_ATTR, (blocked, _version_of(sf_rowmajor)))
 
 
 def to_blocked(input_matrix: torch.Tensor, use_triton_kernel: bool = False) -> torch.Tensor:
@@ -39,7 +48,7 @@ def to_blocked(input_matrix: torch.Tensor, use_triton_kernel: bool = False) -> t
     (there is no Triton here); like the reference's Triton path, inputs need not be pre-padded.
     """
     cached = getattr(input_matrix, _BLOCKED_ATTR, None)
-    if cached is not None and cached[1] == input_matrix._version:
+    if cached is not None and cached[1] == _version_of(input_matrix):
         return cached[0]
     assert input_matrix.dim() == 2, "to_blocked expects a 2-D scale matrix"
     assert input_matrix.element_size() == 1, "Expected element size to be 1 byte (8 bits)"

@@ -313,6 +313,23 @@ def test_llama_shapes_small_batch():
             np.testing.assert_array_equal(H.bf16_bits_of(out), O.gemm_ref(a_dq, b_dq, 1.0))
 
 
+@torch.inference_mode()
+def test_under_inference_mode_like_the_reference_tests():
+    """the reference's tests run under @torch.inference_mode (tests/mxfp4_test.py:209): tensors created there have
+    no version counter -- the cached rotation hint and the attached blocked scales must still work."""
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(64))
+    a = torch.randn(40, 512, dtype=torch.bfloat16, device="cuda") * 25
+    b = torch.randn(72, 512, dtype=torch.bfloat16, device="cuda") * 25
+    a_q, a_sf = Q.fusedQuantizeMx(a, R, method="abs_max")
+    b_q, b_sf = Q.fusedQuantizeMx(b, R, method="abs_max")
+    out = Q.matmul_mxf4_bf16_tn(a_q, b_q, Q.to_blocked(a_sf, use_triton_kernel=True), Q.to_blocked(b_sf, True),
+                                torch.tensor([1.0], device="cuda"))
+    torch.cuda.synchronize()
+    a_dq = O.dequant_mx(H.u8_of(a_q), H.u8_of(a_sf)[:40, :16])
+    b_dq = O.dequant_mx(H.u8_of(b_q), H.u8_of(b_sf)[:72, :16])
+    np.testing.assert_array_equal(H.bf16_bits_of(out), O.gemm_ref(a_dq, b_dq, 1.0))
+
+
 def test_torch_ops_schema_path():
     """external integrations call torch.ops._qutlass_C directly (bindings.cpp:498-507)."""
     R = H.bf16_tensor_from_f32(O.hadamard_matrix(32))
