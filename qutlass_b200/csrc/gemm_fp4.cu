@@ -164,32 +164,67 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // divergent `lane == 0` branch makes the compiler wrap every TMA / tcgen05 op in an R2UR waterfall loop.)
     {
       const bool elected = elect_one();
-      int stage = 0;
-      uint32_t phase = 0;
       // completion goes to the leader's barrier (own barrier when kCtaGroup == 1)
       const uint32_t full0 = (kCtaGroup == 2) ? mapa(bar_base, 0) : bar_base;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
-        const int m0 = (tm * kCtaGroup + (int)cta_rank) * BM;            // this CTA's A rows
-        const int n0 = tn * BN;
-        const int nb0 = n0 + (int)cta_rank * Cfg::B_ROWS;                // this CTA's B rows
-        for (int kt = 0; kt < p.k_tiles; ++kt) {
-          mbar_wait(bar_base + 8u * (STAGES + stage), phase ^ 1, 1);
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sb = sa + Cfg::A_BYTES;
-          const uint32_t ssfa = sb + Cfg::B_BYTES;
-          const uint32_t ssfb = ssfa + Cfg::SFA_BYTES;
-          const uint32_t fb = full0 + 8u * stage;
-          if (elected) {
-            if (is_leader) mbar_arrive_expect_tx(bar_base + 8u * stage, Cfg::TX_BYTES);
-            tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, kt * BK_BYTES, m0);
-            tma_load_2d<kCtaGroup>(sb, &tmap_b, fb, kt * BK_BYTES, nb0);
-            tma_load_3d<kCtaGroup>(ssfa, &tmap_sfa, fb, 0, kt * SFKB, m0 / 128);
-            tma_load_3d<kCtaGroup>(ssfb, &tmap_sfb, fb, 0, kt * SFKB, n0 / 128);
-          }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      int my_tiles = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) ++my_tiles;
+      const int total_kt = my_tiles * p.k_tiles;
+      // Programmatic dependent launch: the weights (B, SFB) do not depend on the previous kernel in the stream
+      // (normally our quantise kernel producing A / SFA), so the first ring of weight loads is issued BEFORE
+      // griddepcontrol.wait and overlaps the predecessor's tail; activations are loaded only after it.
+      const int pre = total_kt < STAGES ? total_kt : STAGES;
+      // (tile, kt) cursor advanced incrementally: no divisions on the per-k-tile path
+      struct Cursor { int tile, kt, m0, n0, nb0; };
+      auto set_tile = [&](Cursor& c) {
+        const int tm = c.tile % p.tiles_m, tn = c.tile / p.tiles_m;
+        c.m0 = (tm * kCtaGroup + (int)cta_rank) * BM;            // this CTA's A rows
+        c.n0 = tn * BN;
+        c.nb0 = c.n0 + (int)cta_rank * Cfg::B_ROWS;              // this CTA's B rows
+      };
+      auto advance = [&](Cursor& c) {
+        if (++c.kt == p.k_tiles) { c.kt = 0; c.tile += num_clusters; set_tile(c); }
+      };
+      auto load_weights = [&](int stage, int n0, int nb0, int kt) {
+        const uint32_t sb = smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+        const uint32_t ssfb = sb + Cfg::B_BYTES + Cfg::SFA_BYTES;
+        const uint32_t fb = full0 + 8u * stage;
+        if (is_leader) mbar_arrive_expect_tx(bar_base + 8u * stage, Cfg::TX_BYTES);
+        tma_load_2d<kCtaGroup>(sb, &tmap_b, fb, kt * BK_BYTES, nb0);
+        tma_load_3d<kCtaGroup>(ssfb, &tmap_sfb, fb, 0, kt * SFKB, n0 / 128);
+      };
+      auto load_acts = [&](int stage, int m0, int kt) {
+        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+        const uint32_t ssfa = sa + Cfg::A_BYTES + Cfg::B_BYTES;
+        const uint32_t fb = full0 + 8u * stage;
+        tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, kt * BK_BYTES, m0);
+        tma_load_3d<kCtaGroup>(ssfa, &tmap_sfa, fb, 0, kt * SFKB, m0 / 128);
+      };
+      Cursor cur{cluster_id, 0, 0, 0, 0};
+      set_tile(cur);
+      {
+        Cursor c = cur;
+        for (int g = 0; g < pre; ++g) {          // ring is empty: no wait needed for the first STAGES slots
+          if (elected) load_weights(g, c.n0, c.nb0, c.kt);
+          advance(c);
         }
+      }
+      pdl_wait();
+      for (int g = 0; g < pre; ++g) {
+        if (elected) load_acts(g, cur.m0, cur.kt);
+        advance(cur);
+      }
+      __syncwarp();
+      int stage = (pre == STAGES) ? 0 : pre;
+      uint32_t phase = (pre == STAGES) ? 1 : 0;
+      for (int g = pre; g < total_kt; ++g) {
+        mbar_wait(bar_base + 8u * (STAGES + stage), phase ^ 1, 1);
+        if (elected) {
+          load_weights(stage, cur.n0, cur.nb0, cur.kt);
+          load_acts(stage, cur.m0, cur.kt);
+        }
+        __syncwarp();
+        advance(cur);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -278,11 +313,12 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int half = ew >> 2;                        // which column half of the tile
     const int col0 = half * Cfg::EPI_COLS;
-    const float alpha = __ldg(p.alpha);
     const uint32_t stg = stg_base + ew * Cfg::STG_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty_leader = (kCtaGroup == 2) ? mapa(tempty_bar(0), 0) : tempty_bar(0);
+    pdl_wait();   // D must not be written before the predecessor kernel has finished (it may still read that memory)
+    const float alpha = __ldg(p.alpha);
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
       const int m0 = (tm * kCtaGroup + (int)cta_rank) * BM;
@@ -499,13 +535,20 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = kCtaGroup;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
+  // programmatic dependent launch: this grid may start while the previous kernel in the stream drains; everything that
+  // depends on that kernel sits behind griddepcontrol.wait inside (B200Q_NO_PDL=1 disables the attribute)
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  {
+    const char* e = getenv("B200Q_NO_PDL");
+    cfg.numAttrs = (e && e[0] == '1') ? 1 : 2;
+  }
   B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tsa, tsb, td, p));
   return 0;
 }

@@ -44,6 +44,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   return r;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// wait: block until the prerequisite grid (the previous kernel in the stream) has completed and its writes are
+// visible; launch_dependents: allow the next kernel in the stream (if launched with the PDL attribute) to start.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

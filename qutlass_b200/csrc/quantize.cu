@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include <cuda_fp8.h>
 #include <stdlib.h>
+#include "ptx.cuh"
 
 namespace b200q {
 
@@ -121,6 +122,9 @@ __global__ void __launch_bounds__(kThreads, 3) quantize_kernel(const QuantParams
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // let a dependent kernel launched with the PDL attribute (our GEMM) start its prologue and weight loads now;
+  // it waits (griddepcontrol.wait) for this whole grid before touching the activations written here
+  ptx::pdl_launch_dependents();
 
   // first tile's loads go out before anything else (they overlap the rotation check)
   uint4* stage = s_stage[warp];
@@ -448,6 +452,7 @@ __global__ void __launch_bounds__(kMmaThreads) quantize_mma_kernel(const QuantPa
   constexpr int NG = NT / 4;                             // 32-column groups per warp per row
 
   extern __shared__ __align__(128) uint8_t q_smem[];
+  ptx::pdl_launch_dependents();
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(q_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
