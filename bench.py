@@ -271,7 +271,7 @@ def main():
             "global_batch_rows": M * world, "parallelism": f"dp{world} (M-sharded, weights broadcast once at setup)",
             "l2_policy": f"rotating {NSETS} buffer sets (activations/outputs/weights), {NSETS * 190} MB footprint > 126 MB L2",
         },
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": (1 + (lib.b200q_gemm_fp4_launches(M, N, K, knd) if args.cta_group == 0 else 1)) * args.steps,
         "gemm_only_tflops_per_gpu": flops / (ms_gemm * 1e-3) / 1e12,
         "quantize_us": ms_quant * 1e3,
     }

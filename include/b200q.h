@@ -120,6 +120,10 @@ int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA, const void
                        const float* alpha_dev, void* D_bf16, int M, int N, int K, int kind,
                        int cta_group, int block_n, b200q_stream_t stream);
 
+/* Number of kernels b200q_gemm_fp4 launches for this problem (1, or 2 when the last 256-column block of N is peeled
+ * into a second launch of small tiles to fill the final, mostly empty wave of CTA pairs). */
+int b200q_gemm_fp4_launches(int M, int N, int K, int kind);
+
 /*
  * Host-buffer convenience for the whole path (what bench.py's e2e leg times):
  *   x_host [M,K] bf16 (pinned) -> H2D -> rotate+quantise (abs_max, MX or NV) ->

@@ -88,6 +88,7 @@ struct GemmParams {
   const float* alpha;
   __nv_bfloat16* d;
   int M, N, K;
+  int ldd;            // row pitch of D in elements (== N unless this launch covers a column slice of a wider D)
   int tiles_m;        // ceil(M / (BM * cta_group))   (cluster tiles along M)
   int tiles_n;        // ceil(N / BN)
   int k_tiles;        // ceil(K / 256)
@@ -127,6 +128,9 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int cluster_id = blockIdx.x / kCtaGroup;
   const int num_clusters = gridDim.x / kCtaGroup;
   const int total_tiles = p.tiles_m * p.tiles_n;
+
+  // a dependent grid (e.g. the tail GEMM of a split launch) may start its prologue / weight loads while this one runs
+  pdl_launch_dependents();
 
   // ------------------------------------------------------------------ setup
   if (warp == 0 && lane == 0) {
@@ -342,12 +346,13 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if constexpr (kCtaGroup == 2) mbar_arrive_cluster(tempty_leader + 8u * acc);
         else mbar_arrive(tempty_bar(acc));
       }
+      if (p.flags & 512) __nanosleep((uint32_t)ew * (((p.flags >> 12) & 0xff) * 50u));   // profiling: stagger the warps
       if (!(p.flags & 1)) {
         if (p.tma_store) {
 #pragma unroll
           for (int ch = 0; ch < Cfg::EPI_NCHUNK; ++ch) {
             // staging buffer must have been read by the previous TMA store
-            if (lane == 0) bulk_wait_group_read<0>();
+            if (lane == 0 && p.tma_store == 1) bulk_wait_group_read<0>();
             __syncwarp();
             constexpr int PIECES = Cfg::EPI_CHUNK / 8;   // 16-byte pieces per staged row (8 or 4)
 #pragma unroll
@@ -366,6 +371,26 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
                            : "memory");
             }
+            if (p.tma_store == 2) {
+              // variant: coalesced st.global from the staged tile (no TMA store): each instruction writes 4 full rows
+              // segments of EPI_CHUNK*2 bytes; reads undo the staging swizzle, so they are bank-conflict free
+              __syncwarp();
+              constexpr int LPR = Cfg::EPI_CHUNK / 8;              // lanes (16-B pieces) per row: 8 or 4
+              constexpr int RPI = 32 / LPR;                        // rows per instruction: 4 or 8
+#pragma unroll
+              for (int i = 0; i < 32 / RPI; ++i) {
+                const int rr = i * RPI + lane / LPR, jj = lane % LPR;
+                const int phys = (Cfg::EPI_CHUNK == 64) ? (jj ^ (rr & 7)) : (jj ^ ((rr >> 1) & 3));
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                             : "r"(stg + rr * (Cfg::EPI_CHUNK * 2) + phys * 16));
+                const int grow = m0 + q * 32 + rr, gcol = n0 + col0 + ch * Cfg::EPI_CHUNK + jj * 8;
+                if (grow < p.M && gcol < p.N)
+                  *reinterpret_cast<uint4*>(p.d + (int64_t)grow * p.ldd + gcol) = make_uint4(w0, w1, w2, w3);
+              }
+              __syncwarp();
+              continue;
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && !(p.flags & 16)) {
@@ -375,12 +400,13 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               tma_store_2d(&tmap_d, stg, cx, cy);
               bulk_commit_group();
             }
+            if (p.flags & 256) __nanosleep(((p.flags >> 12) & 0xff) * 50u);   // profiling: pace the stores
           }
-        } else if (p.tma_store == 0 && (p.N % 16) == 0) {
+        } else if (p.tma_store == 0 && (p.ldd % 16) == 0) {
           // direct 256-bit stores: thread = row, one full 32-byte sector per instruction
           const int row = m0 + q * 32 + lane;
           if (row < p.M) {
-            __nv_bfloat16* drow = p.d + (int64_t)row * p.N + n0 + col0;
+            __nv_bfloat16* drow = p.d + (int64_t)row * p.ldd + n0 + col0;
 #pragma unroll
             for (int v = 0; v < Cfg::EPI_COLS / 16; ++v) {
               if (n0 + col0 + v * 16 < p.N) {
@@ -401,7 +427,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           // scalar stores (row pitch not a multiple of 16 bytes, i.e. N % 8 != 0): thread = row
           const int row = m0 + q * 32 + lane;
           if (row < p.M) {
-            uint16_t* drow = reinterpret_cast<uint16_t*>(p.d) + (int64_t)row * p.N + n0 + col0;
+            uint16_t* drow = reinterpret_cast<uint16_t*>(p.d) + (int64_t)row * p.ldd + n0 + col0;
 #pragma unroll
             for (int i = 0; i < Cfg::EPI_COLS; ++i) {
               if (n0 + col0 + i < p.N) {
@@ -482,9 +508,9 @@ static int make_sf_tmap(CUtensorMap* tm, const void* ptr, int64_t row_blocks, in
 }
 
 // D [M, N] bf16 row-major, box = [32 rows, chunk cols], swizzle matching the staging layout
-static int make_d_tmap(CUtensorMap* tm, const void* ptr, int64_t M, int64_t N, int chunk) {
+static int make_d_tmap(CUtensorMap* tm, const void* ptr, int64_t M, int64_t N, int64_t ldd, int chunk) {
   cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
-  cuuint64_t strides[1] = {(cuuint64_t)N * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ldd * 2};
   cuuint32_t box[2] = {(cuuint32_t)chunk, 32};
   return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box,
                 chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "D");
@@ -492,7 +518,7 @@ static int make_d_tmap(CUtensorMap* tm, const void* ptr, int64_t M, int64_t N, i
 
 template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false>
 static int launch_gemm(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D,
-                       int M, int N, int K, cudaStream_t stream) {
+                       int M, int N, int K, int ldd, cudaStream_t stream) {
   using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8>;
   auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV, A_ROWS, kF8>;
   static bool attr_set = false;  // per instantiation
@@ -513,17 +539,19 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   p.alpha = alpha;
   p.d = (__nv_bfloat16*)D;
   p.M = M; p.N = N; p.K = K;
+  p.ldd = ldd;
   p.tiles_m = (int)ceil_div(M, BM * kCtaGroup);
   p.tiles_n = (int)ceil_div(N, BN);
   p.k_tiles = (int)ceil_div(K, Cfg::BK_ELEMS);
-  p.tma_store = (N % 8 == 0) ? 1 : 0;
+  p.tma_store = (ldd % 8 == 0) ? 1 : 0;
   {
     const char* f = getenv("B200Q_GEMM_DEBUG_FLAGS");
     p.flags = f ? atoi(f) : 0;
     if (p.flags & 4) p.tma_store = 0;
+    if ((p.flags & 128) && p.tma_store) p.tma_store = 2;   // coalesced st.global from the staged tile
   }
   if (p.tma_store) {
-    if ((rc = make_d_tmap(&td, D, M, N, Cfg::EPI_CHUNK))) return rc;
+    if ((rc = make_d_tmap(&td, D, M, N, ldd, Cfg::EPI_CHUNK))) return rc;
   } else {
     td = ta;  // unused
   }
@@ -555,13 +583,13 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
 
 template <bool kNV, bool kF8>
 static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B, const void* SFA, const void* SFB,
-                        const float* alpha, void* D, int M, int N, int K, cudaStream_t s) {
+                        const float* alpha, void* D, int M, int N, int K, int ldd, cudaStream_t s) {
   // small M: same 128-wide single-CTA tile, fewer A rows staged (more weight k-tiles in flight)
-  if (cta_group == 1 && block_n == 128 && M <= 16) return launch_gemm<1, 128, kNV, 16, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, s);
-  if (cta_group == 1 && block_n == 128 && M <= 32) return launch_gemm<1, 128, kNV, 32, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, s);
-  if (cta_group == 1 && block_n == 128 && M <= 64) return launch_gemm<1, 128, kNV, 64, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, s);
+  if (cta_group == 1 && block_n == 128 && M <= 16) return launch_gemm<1, 128, kNV, 16, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+  if (cta_group == 1 && block_n == 128 && M <= 32) return launch_gemm<1, 128, kNV, 32, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+  if (cta_group == 1 && block_n == 128 && M <= 64) return launch_gemm<1, 128, kNV, 64, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
 #define B200Q_CASE(CG, BNV) \
-  if (cta_group == CG && block_n == BNV) return launch_gemm<CG, BNV, kNV, 128, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, s);
+  if (cta_group == CG && block_n == BNV) return launch_gemm<CG, BNV, kNV, 128, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
   B200Q_CASE(1, 128)
   B200Q_CASE(1, 256)
   B200Q_CASE(2, 128)
@@ -578,21 +606,13 @@ static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B
 
 }  // namespace b200q
 
-using namespace b200q;
-
-extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA, const void* SFB,
-                                  const float* alpha_dev, void* D_bf16, int M, int N, int K, int kind, int cta_group,
-                                  int block_n, b200q_stream_t stream) {
-  int rc = check_device_sm100();
-  if (rc) return rc;
-  B200Q_REQUIRE(A && B && SFA && SFB && alpha_dev && D_bf16, "null pointer argument");
-  B200Q_REQUIRE(kind == B200Q_KIND_MXF4 || kind == B200Q_KIND_NVF4 || kind == B200Q_KIND_MXF8, "invalid kind %d", kind);
-  B200Q_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive (got %d, %d, %d)", M, N, K);
-  B200Q_REQUIRE(K % 32 == 0, "K (%d) must be a multiple of 32", K);
-  B200Q_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)SFA | (uintptr_t)SFB) & 15) == 0,
-                "A, B, SFA, SFB must be 16-byte aligned");
-  B200Q_REQUIRE(((uintptr_t)D_bf16 & 15) == 0 || (N % 8) != 0, "D must be 16-byte aligned");
-  if (cta_group == 0 || block_n == 0) {
+namespace b200q {
+struct GemmPlan { int cta_group, block_n, n_main; };   // n_main > 0: peel columns [n_main, N) into a second launch
+static GemmPlan plan_auto(int M, int N, int K, int kind) {
+  GemmPlan pl{1, 128, 0};
+  int cta_group = 0, block_n = 0;
+  (void)K;
+  {
     // heuristic (measured on B200, profiles/): small M streams weights with single-CTA tiles; otherwise CTA pairs
     // (256-row tiles halve the B traffic per flop) with the tile width that minimises rounds x width.
     if (M <= 128) { cta_group = 1; block_n = 128; }
@@ -611,13 +631,75 @@ extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA,
       }
     }
   }
+  pl.cta_group = cta_group;
+  pl.block_n = block_n;
+  // Measured (profiles/r01_notes.md): the peeled launch costs more than the saved part of a round (92.5 vs 89.4 us at
+  // config 1 with (2,128) tail tiles, 97.1 us with (1,64)), because a tile's sequential k-loop, not the tile count, sets
+  // the length of the last round.  Kept as an opt-in experiment: B200Q_TAIL_SPLIT=1.
+  const char* split_env = getenv("B200Q_TAIL_SPLIT");
+  if (split_env && split_env[0] == '1' && cta_group == 2 && block_n == 256 && N % 8 == 0 && kind != B200Q_KIND_MXF8) {
+    // Wave quantisation: with T tiles over C CTA pairs the last round is only (T mod C)/C full.  When that round is
+    // less than half full and peeling the LAST 256-column block of N saves a whole round, that block runs as a second
+    // launch of narrower (2,128) tiles that fits in one wave (it starts as the main grid drains: PDL, disjoint D
+    // columns, identical arithmetic -- every configuration is bit-identical).
+    const int64_t clusters = num_sms() / 2;
+    const int64_t tm = ceil_div(M, 256), tn = ceil_div(N, 256);
+    const int64_t rounds = ceil_div(tm * tn, clusters);
+    const int64_t waste = rounds * clusters - tm * tn;
+    const int64_t rounds_main = tn > 1 ? ceil_div(tm * (tn - 1), clusters) : rounds;
+    const int n_main = (int)(tn - 1) * 256;
+    const int64_t tail_tiles = tm * ceil_div(N - n_main, 128);          // (2,128) tiles: half the k-loop latency of (2,256)
+    if (tn > 1 && waste * 2 >= clusters && rounds_main < rounds && tail_tiles <= clusters) pl.n_main = n_main;
+  }
+  return pl;
+}
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA, const void* SFB,
+                                  const float* alpha_dev, void* D_bf16, int M, int N, int K, int kind, int cta_group,
+                                  int block_n, b200q_stream_t stream) {
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  B200Q_REQUIRE(A && B && SFA && SFB && alpha_dev && D_bf16, "null pointer argument");
+  B200Q_REQUIRE(kind == B200Q_KIND_MXF4 || kind == B200Q_KIND_NVF4 || kind == B200Q_KIND_MXF8, "invalid kind %d", kind);
+  B200Q_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive (got %d, %d, %d)", M, N, K);
+  B200Q_REQUIRE(K % 32 == 0, "K (%d) must be a multiple of 32", K);
+  B200Q_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)SFA | (uintptr_t)SFB) & 15) == 0,
+                "A, B, SFA, SFB must be 16-byte aligned");
+  B200Q_REQUIRE(((uintptr_t)D_bf16 & 15) == 0 || (N % 8) != 0, "D must be 16-byte aligned");
+  const bool auto_cfg = (cta_group == 0 || block_n == 0);
+  GemmPlan pl{cta_group, block_n, 0};
+  if (auto_cfg) {
+    pl = plan_auto(M, N, K, kind);
+    cta_group = pl.cta_group;
+    block_n = pl.block_n;
+  }
   cudaStream_t s = (cudaStream_t)stream;
-  if (kind == B200Q_KIND_NVF4) return dispatch_cfg<true, false>(cta_group, block_n, A, B, SFA, SFB, alpha_dev, D_bf16, M, N, K, s);
-  if (kind == B200Q_KIND_MXF8) return dispatch_cfg<false, true>(cta_group, block_n, A, B, SFA, SFB, alpha_dev, D_bf16, M, N, K, s);
-  return dispatch_cfg<false, false>(cta_group, block_n, A, B, SFA, SFB, alpha_dev, D_bf16, M, N, K, s);
+  auto run = [&](int cg, int bn, const void* Bp, const void* SFBp, void* Dp, int n_sub) -> int {
+    if (kind == B200Q_KIND_NVF4) return dispatch_cfg<true, false>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
+    if (kind == B200Q_KIND_MXF8) return dispatch_cfg<false, true>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
+    return dispatch_cfg<false, false>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
+  };
+  if (pl.n_main > 0) {
+    const int group = kind == B200Q_KIND_NVF4 ? 16 : 32;
+    const int64_t sf_col_blocks = ceil_div(ceil_div(K, group), 4);
+    rc = run(2, 256, B, SFB, D_bf16, pl.n_main);
+    if (rc) return rc;
+    const uint8_t* Bt = (const uint8_t*)B + (int64_t)pl.n_main * (K / 2);
+    const uint8_t* SFBt = (const uint8_t*)SFB + (int64_t)(pl.n_main / 128) * sf_col_blocks * 512;
+    return run(2, 128, Bt, SFBt, (uint8_t*)D_bf16 + (int64_t)pl.n_main * 2, N - pl.n_main);
+  }
+  return run(cta_group, block_n, B, SFB, D_bf16, N);
 }
 
 extern "C" int b200q_gemm_fp4(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha_dev,
                               void* D_bf16, int M, int N, int K, int kind, b200q_stream_t stream) {
   return b200q_gemm_fp4_cfg(A, B, SFA, SFB, alpha_dev, D_bf16, M, N, K, kind, 0, 0, stream);
+}
+
+extern "C" int b200q_gemm_fp4_launches(int M, int N, int K, int kind) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return plan_auto(M, N, K, kind).n_main > 0 ? 2 : 1;
 }

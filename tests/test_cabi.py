@@ -30,7 +30,7 @@ def test_header_declares_the_hot_path_entry_points():
     d = _declared()
     for name in ("b200q_quantize_mx", "b200q_quantize_nv", "b200q_swizzle_sf", "b200q_gemm_fp4",
                  "b200q_gemm_fp4_cfg", "b200q_last_error", "b200q_abi_version", "b200q_linear_fp4_host",
-                 "b200q_linear_workspace_bytes"):
+                 "b200q_linear_workspace_bytes", "b200q_gemm_fp4_launches"):
         assert name in d, name
 
 

@@ -78,8 +78,9 @@ if __name__ == "__main__":
     if "quant" in which:
         quant_sweep()
     if "gemmst" in which:
-        gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 256), (2, 192)], [(0, 2), (64, 2), (1, 2), (65, 2), (33, 2)])
-        gemm_sweep("nv", [(4096, 14336, 4096)], [(2, 256)], [(0, 2), (64, 2), (33, 2)])
+        F = lambda base, n: base | (n << 12)
+        gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 256)], [(0, 2), (F(256, 4), 2), (F(256, 10), 2), (F(512, 6), 2), (F(512, 14), 2), (F(768, 6), 2)])
+        gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 192)], [(0, 2), (F(512, 6), 2), (F(768, 6), 2)])
     if "gemmq" in which:
         gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (1, 2), (4, 2)])
         gemm_sweep("nv", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (4, 2)])
