@@ -107,6 +107,13 @@ def run_reference(args):
         return 0
     import torch
     from oracle import cpu_baseline as C
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would otherwise pin the
+    # reference arm to one core when it is launched for N > 1)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except Exception:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncpu))
     kind = args.kind
     # bounded sample: the full config costs a few seconds per step on a many-core host; cap steps
     steps = max(1, min(args.steps, 3))
