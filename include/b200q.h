@@ -41,6 +41,9 @@ typedef struct CUstream_st* b200q_stream_t;
  * device-side structure check.  Without the flag the kernel verifies R itself (exact, on the device, graph-safe)
  * and falls back to a generic x @ R for any other matrix. */
 #define B200Q_ROT_TRUSTED_HADAMARD 0x100
+/* OR into `method`: the caller knows rot is NOT of that form (e.g. identity, a learned rotation): the rotation then
+ * runs on the tensor-core (mma.sync) kernel for had >= 32 instead of the butterfly kernel's scalar fallback. */
+#define B200Q_ROT_GENERIC 0x200
 
 #define B200Q_KIND_MXF4 0      /* e2m1 x e2m1, ue8m0 scales, group 32          */
 #define B200Q_KIND_NVF4 1      /* e2m1 x e2m1, ue4m3 scales, group 16          */

@@ -29,6 +29,7 @@ __all__ = [
 
 METHOD_QUEST, METHOD_ABSMAX = 0, 1
 ROT_TRUSTED_HADAMARD = 0x100   # include/b200q.h: B200Q_ROT_TRUSTED_HADAMARD
+ROT_GENERIC = 0x200            # include/b200q.h: B200Q_ROT_GENERIC (known non-Hadamard -> tensor-core rotation)
 KIND_MXF4, KIND_NVF4, KIND_MXF8 = 0, 1, 2
 
 
@@ -157,7 +158,7 @@ def _rotation_hint(r: torch.Tensor) -> int:
     ent = _ROT_CACHE.get(key)
     ver = _version_of(r)
     if ent is not None and ent[0]() is r and ent[1] == ver:
-        return ROT_TRUSTED_HADAMARD if ent[2] else 0
+        return ROT_TRUSTED_HADAMARD if ent[2] else ROT_GENERIC
     if r.is_cuda and torch.cuda.is_current_stream_capturing():
         return 0
     h = r.size(0)
@@ -176,7 +177,7 @@ def _rotation_hint(r: torch.Tensor) -> int:
         for k in [k for k, v in _ROT_CACHE.items() if v[0]() is None]:
             _ROT_CACHE.pop(k, None)
     _ROT_CACHE[key] = (weakref.ref(r), ver, is_h)
-    return ROT_TRUSTED_HADAMARD if is_h else 0
+    return ROT_TRUSTED_HADAMARD if is_h else ROT_GENERIC
 
 
 def _quant_checks(name: str, a, r, outs, extra=()):

@@ -721,9 +721,12 @@ static int launch(const QuantParams& p, cudaStream_t stream) {
   return 0;
 }
 
+static thread_local bool g_rot_generic = false;   // set per call from B200Q_ROT_GENERIC
 static bool use_butterfly() {
   // Default: the CUDA-core butterfly kernel (measured faster on B200 for Hadamard rotations, profiles/).
-  // B200Q_QUANT_MMA=1 selects the tensor-core (mma.sync) kernel, which handles ANY rotation at full speed.
+  // The tensor-core (mma.sync) kernel handles ANY rotation at full speed: it is used when the caller says the rotation
+  // is not a Hadamard matrix (B200Q_ROT_GENERIC) or when B200Q_QUANT_MMA=1 forces it.
+  if (g_rot_generic) return false;
   const char* e = getenv("B200Q_QUANT_MMA");
   return !(e && e[0] == '1');
 }
@@ -784,7 +787,8 @@ extern "C" int b200q_quantize_mx(const void* x_bf16, const void* rot_bf16, void*
   B200Q_REQUIRE(sf_rowmajor || sf_blocked, "at least one scale output is required");
   p.mask = (uint32_t*)clip_mask;
   p.trust_hadamard = (method & B200Q_ROT_TRUSTED_HADAMARD) ? 1 : 0;
-  method &= ~B200Q_ROT_TRUSTED_HADAMARD;
+  g_rot_generic = (method & B200Q_ROT_GENERIC) != 0 && !p.trust_hadamard;
+  method &= ~(B200Q_ROT_TRUSTED_HADAMARD | B200Q_ROT_GENERIC);
   cudaStream_t s = (cudaStream_t)stream;
   if (method == B200Q_METHOD_QUEST) {
     if (clip_mask) return dispatch_had<false, B200Q_METHOD_QUEST, true>(had, p, s);
@@ -809,7 +813,8 @@ extern "C" int b200q_quantize_nv(const void* x_bf16, const void* rot_bf16, void*
   B200Q_REQUIRE(global_scale_dev, "global_scale must be a device pointer to one float");
   p.gs = global_scale_dev;
   p.trust_hadamard = (method & B200Q_ROT_TRUSTED_HADAMARD) ? 1 : 0;
-  method &= ~B200Q_ROT_TRUSTED_HADAMARD;
+  g_rot_generic = (method & B200Q_ROT_GENERIC) != 0 && !p.trust_hadamard;
+  method &= ~(B200Q_ROT_TRUSTED_HADAMARD | B200Q_ROT_GENERIC);
   cudaStream_t s = (cudaStream_t)stream;
   if (method == B200Q_METHOD_QUEST) return dispatch_had<true, B200Q_METHOD_QUEST, false>(had, p, s);
   if (method == B200Q_METHOD_ABSMAX) return dispatch_had<true, B200Q_METHOD_ABSMAX, false>(had, p, s);

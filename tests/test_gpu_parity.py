@@ -170,7 +170,30 @@ def test_quantize_device_check_equals_trusted_hint(kind, had):
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
     assert Q._rotation_hint(R) == Q.ROT_TRUSTED_HADAMARD
-    assert Q._rotation_hint(torch.eye(had, dtype=torch.bfloat16, device="cuda")) == 0
+    assert Q._rotation_hint(torch.eye(had, dtype=torch.bfloat16, device="cuda")) == Q.ROT_GENERIC
+
+
+@pytest.mark.parametrize("kind", ["mx", "nv"])
+@pytest.mark.parametrize("had", [32, 64, 128])
+def test_quantize_arbitrary_rotation_on_tensor_cores(kind, had):
+    """a non-Hadamard runtime rotation (the API allows any matrix) takes the mma.sync kernel via the Python hint and the
+    butterfly kernel's scalar fallback without it; both must agree with the oracle."""
+    rows, k = 96, 1024
+    x = H.random_bf16((rows, k), seed=had)
+    R = O.bf16_round(np.random.default_rng(had).standard_normal((had, had)).astype(np.float32) * had ** -0.5)
+    xt, Rt = H.bf16_tensor_from_f32(x), H.bf16_tensor_from_f32(R)
+    if kind == "mx":
+        ref = O.quantize_mx(x, R, "abs_max")
+        q, sf = Q.fusedQuantizeMx(xt, Rt, method="abs_max")
+        dq = O.dequant_mx(H.u8_of(q), _flat_sf(sf, rows, k // 32))
+        dq_ref = O.dequant_mx(ref["q"].reshape(rows, -1), ref["sf"].reshape(rows, -1))
+    else:
+        ref = O.quantize_nv(x, R, 1.0, "abs_max")
+        q, sf = Q.fusedQuantizeNv(xt, Rt, torch.tensor([1.0], device="cuda"))
+        dq = O.dequant_nv(H.u8_of(q), _flat_sf(sf, rows, k // 16))
+        dq_ref = O.dequant_nv(ref["q"].reshape(rows, -1), ref["sf"].reshape(rows, -1))
+    torch.cuda.synchronize()
+    assert (dq != dq_ref).mean() <= (1e-3 if kind == "mx" else 1e-2)
 
 
 def test_error_behaviour():
