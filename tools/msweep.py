@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """M sweep on Llama-3-8B / 70B FFN shapes (BASELINE.json configs 1-4), CUDA-graph replayed like the reference's
 benchmarks (triton do_bench_cudagraph): GEMM only ("ideal") and quantise(H=128, abs_max)+GEMM ("actual").
-Writes profiles/r01_msweep.md (markdown table) and prints JSON lines."""
+Writes gpurun_out/msweep.md (markdown table) and prints JSON lines."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -76,8 +76,8 @@ if __name__ == "__main__":
         t = graph_time(gemm8, 20)
         rec = dict(kind="mxf8", N=N, K=K, M=M, gemm_us=round(t, 2), quant_us=0, both_us=0, gemm_tflops=round(2.0 * M * N * K / t / 1e6, 1), actual_tflops=0)
         rows_out.append(rec); print(json.dumps(rec), flush=True)
-    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    with open(os.path.join(ROOT, "profiles", "r01_msweep.md"), "w") as f:
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)     # gpurun merges this directory back; copy to profiles/ after review
+    with open(os.path.join(ROOT, "gpurun_out", "msweep.md"), "w") as f:
         f.write("# M sweep (one B200, CUDA-graph replay, best of 3; quantise = Hadamard-128 abs_max)\n\n")
         f.write("| kind | N | K | M | GEMM us | GEMM TFLOP/s | quantise us | quant+GEMM us | quant+GEMM TFLOP/s |\n|---|---|---|---|---|---|---|---|---|\n")
         for r in rows_out:
