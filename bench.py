@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="step = two launches (quantise kernel, then GEMM) instead of the fused kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -230,9 +231,24 @@ def main():
                                           alpha.data_ptr(), outs[s].data_ptr(), M, N, K, knd, args.cta_group,
                                           args.block_n, stream))
 
-    def step(i):
+    def step_two_launches(i):
         quant(i)
         gemm(i)
+
+    # the whole step through ONE C-ABI call: one persistent kernel (quantiser warps inside the GEMM) when eligible
+    fuse_ws = torch.zeros(max(int(lib.b200q_linear_fp4_workspace_bytes(M)), 256), dtype=torch.uint8, device=dev)
+    fused = (not args.no_fuse) and args.cta_group == 0
+    launches_per_step = lib.b200q_linear_fp4_launches(M, N, K, args.had, method, knd) if fused else \
+        1 + (lib.b200q_gemm_fp4_launches(M, N, K, knd) if args.cta_group == 0 else 1)
+
+    def step_fused(i):
+        s = i % NSETS
+        _lib.check(lib.b200q_linear_fp4(acts[s].data_ptr(), H.data_ptr(), aqs[s].data_ptr(), None, asfs[s].data_ptr(),
+                                        wqs[s].data_ptr(), wsfs[s].data_ptr(), alpha.data_ptr(),
+                                        gs.data_ptr() if kind == "nv" else None, outs[s].data_ptr(), fuse_ws.data_ptr(),
+                                        M, N, K, args.had, method, knd, stream))
+
+    step = step_fused if fused else step_two_launches
 
     def barrier():
         if world > 1:
@@ -265,6 +281,7 @@ def main():
     # dominant kernel alone (CUDA events on the launching stream), and the quantise kernel alone
     ms_gemm = timed(gemm, args.steps, 3)
     ms_quant = timed(quant, args.steps, 3)
+    ms_two = timed(step_two_launches, args.steps, 3) if fused else ms_step
 
     value = flops * world / (ms_step * 1e-3) / 1e12
     line = {
@@ -274,11 +291,12 @@ def main():
         "config": {
             "workload": f"Llama-3-8B FFN M={M} (per GPU) N={N} K={K} {'MXFP4' if kind == 'mx' else 'NVFP4'} W4A4 abs_max, "
                         f"step = fused Hadamard-{args.had} rotate+quantise of activations + block-scaled FP4 GEMM "
-                        "(weights pre-quantised)",
+                        "(weights pre-quantised)" + (", one persistent kernel (b200q_linear_fp4)" if launches_per_step == 1 else ""),
             "global_batch_rows": M * world, "parallelism": f"dp{world} (M-sharded, weights broadcast once at setup)",
             "l2_policy": f"rotating {NSETS} buffer sets (activations/outputs/weights), {NSETS * 190} MB footprint > 126 MB L2",
         },
-        "gpu_launches": (1 + (lib.b200q_gemm_fp4_launches(M, N, K, knd) if args.cta_group == 0 else 1)) * args.steps,
+        "gpu_launches": launches_per_step * args.steps,
+        "two_launch_step_us": ms_two * 1e3,
         "gemm_only_tflops_per_gpu": flops / (ms_gemm * 1e-3) / 1e12,
         "quantize_us": ms_quant * 1e3,
     }

@@ -128,6 +128,28 @@ int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA, const void
 int b200q_gemm_fp4_launches(int M, int N, int K, int kind);
 
 /*
+ * The whole device-side path in ONE call: rotate + quantise x (as b200q_quantize_mx / _nv, clip mask excluded), then
+ * D = bf16(alpha * xq @ Wq^T) (as b200q_gemm_fp4).  Same outputs, bit for bit, as the two calls in sequence: xq_e2m1,
+ * x_sf_rowmajor (nullable) and x_sf_blocked (required) are written like the quantiser writes them.
+ * Replaces the reference's per-layer sequence fusedQuantizeMx -> to_blocked -> matmul_mxf4_bf16_tn
+ * (qutlass/__init__.py:149-180, utils.py:160-193, __init__.py:34-43; benchmarks/bench_mxfp4_sm100.py:93-104).
+ *
+ * When `method` carries B200Q_ROT_TRUSTED_HADAMARD, K % 1024 == 0, N % 8 == 0 and the problem is large enough for the
+ * CTA-pair GEMM (M > 256), this is ONE persistent kernel: 4 extra warps per CTA quantise the activations under the
+ * tensor pipe's shadow and publish 256-row blocks through progress counters in `ws`; the GEMM's TMA producer acquires
+ * a block's counter before loading it.  Otherwise it is the two launches.  B200Q_NO_FUSE=1 forces the two launches.
+ *   ws: NULL (never fuse) or b200q_linear_fp4_workspace_bytes(M) bytes of device memory that the caller zeroes ONCE
+ *       (cudaMemset) after allocating; every call leaves it zeroed.  One workspace per stream.
+ *   had / method / global_scale_dev as for b200q_quantize_*; kind B200Q_KIND_MXF4 or B200Q_KIND_NVF4.
+ */
+int64_t b200q_linear_fp4_workspace_bytes(int M);
+int b200q_linear_fp4(const void* x_bf16, const void* rot_bf16, void* xq_e2m1, void* x_sf_rowmajor, void* x_sf_blocked,
+                     const void* Wq, const void* Wsf_blocked, const float* alpha_dev, const float* global_scale_dev,
+                     void* D_bf16, void* ws, int M, int N, int K, int had, int method, int kind, b200q_stream_t stream);
+/* Kernels b200q_linear_fp4 launches for this problem (1 when fused, else quantiser + b200q_gemm_fp4_launches). */
+int b200q_linear_fp4_launches(int M, int N, int K, int had, int method, int kind);
+
+/*
  * Host-buffer convenience for the whole path (what bench.py's e2e leg times):
  *   x_host [M,K] bf16 (pinned) -> H2D -> rotate+quantise (abs_max, MX or NV) ->
  *   GEMM against pre-quantised weights (device) -> D2H into d_host [M,N] bf16.

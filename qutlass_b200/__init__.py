@@ -24,7 +24,7 @@ from .utils import (get_padded_shape_mx, get_padded_shape_nv, pad_to_block, to_b
 __all__ = [
     "matmul_mxf4_bf16_tn", "matmul_nvf4_bf16_tn", "fusedQuantizeMx", "fusedQuantizeNv",
     "matmul_ada_mxf4_bf16_tn", "matmul_mxf8_bf16_tn", "matmul_mxf8_bf16_nn", "backward_t_bf16",
-    "backward_qt_bf16", "backward_bf16_square_double_mxfp8", "mxfp4_transpose_mxfp8",
+    "backward_qt_bf16", "backward_bf16_square_double_mxfp8", "mxfp4_transpose_mxfp8", "fused_linear_fp4",
 ]
 
 METHOD_QUEST, METHOD_ABSMAX = 0, 1
@@ -260,6 +260,77 @@ def fusedQuantizeNv(a: torch.Tensor, b: torch.Tensor, global_scale: torch.Tensor
 
 
 # --------------------------------------------------------------------------------------- out of scope
+_FUSE_WS = {}   # (device index, stream handle) -> zeroed progress-counter workspace of the fused kernel
+
+
+def _fuse_workspace(device: torch.device, stream: int, m: int) -> torch.Tensor:
+    need = _lib.load().b200q_linear_fp4_workspace_bytes(m)
+    key = (device.index, stream)
+    ws = _FUSE_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 4096), dtype=torch.uint8, device=device)   # zeroed once; every call leaves it zeroed
+        _FUSE_WS[key] = ws
+    return ws
+
+
+def fused_linear_fp4(x: torch.Tensor, rot: torch.Tensor, w_q: torch.Tensor, w_sf: torch.Tensor, alpha: torch.Tensor, *,
+                     global_scale: torch.Tensor | None = None, method: Literal["quest", "abs_max"] = "abs_max",
+                     fmt: Literal["mx", "nv"] = "mx"):
+    """The per-layer forward sequence of the reference in one call (benchmarks/bench_mxfp4_sm100.py:93-104):
+
+        xq, x_sf = fusedQuantizeMx(x, rot, method=method)          # or fusedQuantizeNv(x, rot, global_scale)
+        out = matmul_mxf4_bf16_tn(xq, w_q, to_blocked(x_sf), w_sf, alpha)
+
+    Returns (out [M, N] bf16, xq, x_sf) -- bit-identical to the two calls.  For a Hadamard rotation, K % 1024 == 0,
+    N % 8 == 0 and M > 256 it runs as ONE persistent kernel (quantiser warps inside the GEMM, include/b200q.h:
+    b200q_linear_fp4); otherwise as the two launches.  ``w_sf`` is the blocked (to_blocked) weight scale buffer.
+    """
+    if method not in ("quest", "abs_max"):
+        raise ValueError(f"invalid method {method!r}, must be 'quest' or 'abs_max'")
+    if fmt not in ("mx", "nv"):
+        raise ValueError(f"invalid fmt {fmt!r}, must be 'mx' or 'nv'")
+    nv = fmt == "nv"
+    name = "fused_linear_fp4"
+    extra = [("W", w_q), ("W_sf", w_sf), ("alpha", alpha)] + ([("global_scale", global_scale)] if nv else [])
+    had = _quant_checks(name, x, rot, [], extra=extra)
+    _check_contig(name, [("W", w_q), ("W_sf", w_sf)])
+    _check(x.dim() == 2 and w_q.dim() == 2, "x and W must be 2D")
+    _check(w_q.dtype == torch.uint8, "W must be uint8")
+    sf_dtype = torch.float8_e4m3fn if nv else torch.float8_e8m0fnu
+    _check(w_sf.dtype == sf_dtype, f"W_sf must be {'float8_e4m3fn' if nv else 'float8_e8m0fnu'}")
+    _check(alpha.dtype == torch.float32 and alpha.numel() >= 1, "alpha must be a float32 tensor with one element")
+    if nv:
+        _check(global_scale is not None and global_scale.dtype == torch.float32 and global_scale.numel() == 1,
+               "global_scale must be a float32 tensor with one element")
+        _check(had in (16, 32, 64, 128), f"Unsupported rotation size {had}; expected 16, 32, 64, or 128.")
+    else:
+        _check(had in (32, 64, 128), f"Unsupported rotation size {had}; expected 32, 64, or 128.")
+    m, k = x.shape
+    n = w_q.size(0)
+    _check(k % 32 == 0, f"K ({k}) must be a multiple of 32")
+    _check(w_q.size(1) * 2 == k, "Inner dimensions must match for A @ B.T")
+    group = 16 if nv else 32
+    need_w = ((n + 127) // 128) * 128 * (((k // group) + 3) // 4) * 4
+    _check(w_sf.numel() >= need_w, f"W_sf has {w_sf.numel()} scales, the blocked layout needs {need_w}")
+    padded_rows, padded_cols = (get_padded_shape_nv if nv else get_padded_shape_mx)(x)
+    xq = torch.empty(m, k // 2, dtype=torch.uint8, device=x.device)
+    x_sf = torch.empty(padded_rows, padded_cols, dtype=sf_dtype, device=x.device)
+    blocked = torch.empty(padded_rows * padded_cols, dtype=sf_dtype, device=x.device)
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=x.device)
+    meth = (METHOD_QUEST if method == "quest" else METHOD_ABSMAX) | _rotation_hint(rot)
+    with _DeviceGuard(x.device):
+        stream = _stream(x)
+        capturing = torch.cuda.is_current_stream_capturing()
+        # the counter workspace is keyed by stream; under graph capture the capture stream's handle is stable too
+        ws = _fuse_workspace(x.device, stream, m) if not capturing or (x.device.index, stream) in _FUSE_WS else None
+        _lib.check(_lib.load().b200q_linear_fp4(
+            x.data_ptr(), rot.data_ptr(), xq.data_ptr(), x_sf.data_ptr(), blocked.data_ptr(), w_q.data_ptr(),
+            w_sf.data_ptr(), alpha.data_ptr(), global_scale.data_ptr() if nv else None, out.data_ptr(),
+            ws.data_ptr() if ws is not None else None, m, n, k, had, meth, KIND_NVF4 if nv else KIND_MXF4, stream))
+    _attach_blocked(x_sf, blocked)
+    return out, xq, x_sf
+
+
 def _out_of_scope(name: str):
     def fn(*args, **kwargs):
         raise NotImplementedError(

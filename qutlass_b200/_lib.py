@@ -22,6 +22,9 @@ SIGNATURES = {
     "b200q_gemm_fp4": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "b200q_gemm_fp4_cfg": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200q_gemm_fp4_launches": (_i32, [_i32, _i32, _i32, _i32]),
+    "b200q_linear_fp4_workspace_bytes": (_i64, [_i32]),
+    "b200q_linear_fp4": (_i32, [_vp] * 11 + [_i32] * 6 + [_vp]),
+    "b200q_linear_fp4_launches": (_i32, [_i32] * 6),
     "b200q_linear_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "b200q_linear_fp4_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
 }

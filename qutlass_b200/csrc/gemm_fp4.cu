@@ -27,6 +27,7 @@
 // per output over all of K (no split-K), alpha applied once in fp32, one RNE to bf16.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "quantize_tile.cuh"
 
 #include <cuda.h>
 #include <mutex>
@@ -39,9 +40,11 @@ constexpr int BM = 128;          // rows of A per CTA
 constexpr int BK_BYTES = 128;    // one k-tile = 256 e2m1 = 128 bytes per row (one 128B-swizzle row)
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 320
+constexpr int kQuantWarps = 4;                       // fused kernel only: warps 10-13 rotate + quantise the activations
+constexpr int kFusedThreads = kGemmThreads + 32 * kQuantWarps;   // 448 -> 144 registers / thread
 constexpr int kSmemBudget = 227 * 1024;
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false, bool kFuse = false>
 struct GemmCfg {
   // A_ROWS < 128 (small M): only A_ROWS rows of the A tile are loaded and kept per stage; the MMA still reads a
   // 128-row operand (the bytes that follow) -- those accumulator rows are garbage and never stored.  Smaller
@@ -74,9 +77,10 @@ struct GemmCfg {
   static constexpr int STG_BYTES = 32 * EPI_CHUNK * 2;           // one staging buffer per epilogue warp
   static constexpr int STG_TOTAL = kEpiWarps * STG_BYTES;
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int STAGES_RAW = (kSmemBudget - BAR_BYTES - 1024 - STG_TOTAL) / STAGE_BYTES;
+  static constexpr int QSTG_BYTES = kFuse ? kQuantWarps * 2048 : 0;   // quantiser warps' swizzled staging (2 KB each)
+  static constexpr int STAGES_RAW = (kSmemBudget - BAR_BYTES - 1024 - STG_TOTAL - QSTG_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_TOTAL + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_TOTAL + BAR_BYTES + QSTG_BYTES + 1024;  // +1024 alignment slack
   static constexpr uint32_t TX_BYTES = (uint32_t)LOAD_BYTES * kCtaGroup;   // what the (leader's) full barrier expects
   static_assert(TMEM_USED <= 512, "TMEM overflow");
   static_assert(STAGES >= 2, "not enough shared memory for 2 stages");
@@ -96,12 +100,90 @@ struct GemmParams {
   int flags;          // profiling: bit0 skip stores, bit1 skip TMEM loads
 };
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS, bool kF8>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// Fused quantise + GEMM (kFuse): the activations are rotated + quantised by 4 extra warps of the SAME persistent kernel
+// while its tensor pipe works, instead of by a separate kernel in front of it.
+//   * quantiser warps take warp-tiles (1024 consecutive elements of x) from a global ticket counter in ascending
+//     order (dynamic, so progress never depends on a CTA that is not resident yet), write e2m1 codes + scales to
+//     global memory exactly like the standalone kernel, and bump ready[tile's 256-row block] with a release add;
+//   * output tiles are walked N-fastest, so the first wave needs only the first one or two row blocks of A; the TMA
+//     producer acquires ready[tm] == (rows in block) * K/1024 before the first A / SFA load of a tile of row block tm;
+//   * the last CTA to finish zeroes the counters again (the workspace is zero on entry AND on exit).
+struct FuseParams {
+  QuantParams q;
+  uint32_t* ctr;                 // [0] ticket, [1] finished CTAs, [2 + tm] warp-tiles of row block tm written
+  uint32_t tiles_per_row;        // K / 1024
+  int had, method;
+};
+
+template <int HAD, bool NV, int METHOD>
+__device__ __forceinline__ void quantiser_loop(const FuseParams& fp, uint4* stage, int lane) {
+  const QuantParams& p = fp.q;
+  const float c_scale = __bfloat162float(p.rot[0]);
+  float gs = 1.f, gs_rcp = 1.f;
+  if constexpr (NV) {
+    gs = *p.gs;
+    gs_rcp = rcp_approx_ftz(gs);
+  }
+  const uint32_t n_tiles = (uint32_t)p.n_tiles;
+  const uint32_t tiles_per_block = 256u * fp.tiles_per_row;     // one cluster tile = 256 rows of A
+  uint32_t* ready = fp.ctr + 2;
+  auto grab = [&]() -> uint32_t {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(fp.ctr, 1u);
+    return __shfl_sync(0xffffffffu, t, 0);
+  };
+  auto load = [&](uint32_t tile, uint4 (&dst)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      dst[i] = (tile < n_tiles) ? __ldg(p.x + ((int64_t)tile * 128 + i * 32 + lane)) : make_uint4(0, 0, 0, 0);
+  };
+  uint32_t tile = grab();
+  uint4 nxt[4];
+  load(tile, nxt);
+  while (tile < n_tiles) {
+    const uint32_t ntile = grab();           // ticket + loads of the next tile are in flight under this tile's math
+    uint4 ld[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld[i] = nxt[i];
+    load(ntile, nxt);
+    float v[32];
+    tile_stage_unpack(ld, stage, lane, v);
+    tile_rotate_hadamard<HAD>(v, c_scale);
+    tile_quantise_store<NV, METHOD, false>(p, v, (int64_t)tile, lane, gs, gs_rcp);
+    __syncwarp();                            // every lane's stores precede lane 0's release
+    if (lane == 0) red_release_gpu_add(ready + tile / tiles_per_block, 1u);
+    tile = ntile;
+  }
+}
+
+template <bool NV>
+__device__ __forceinline__ void quantiser_role(const FuseParams& fp, uint4* stage, int lane) {
+#define B200Q_QCASE(H)                                                                        \
+  case H:                                                                                     \
+    if (fp.method == B200Q_METHOD_QUEST) quantiser_loop<H, NV, B200Q_METHOD_QUEST>(fp, stage, lane); \
+    else quantiser_loop<H, NV, B200Q_METHOD_ABSMAX>(fp, stage, lane);                         \
+    break;
+  switch (fp.had) {
+    B200Q_QCASE(128)
+    B200Q_QCASE(64)
+    B200Q_QCASE(32)
+    case 16:
+      if constexpr (NV) {
+        if (fp.method == B200Q_METHOD_QUEST) quantiser_loop<16, NV, B200Q_METHOD_QUEST>(fp, stage, lane);
+        else quantiser_loop<16, NV, B200Q_METHOD_ABSMAX>(fp, stage, lane);
+      }
+      break;
+  }
+#undef B200Q_QCASE
+}
+
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS, bool kF8, bool kFuse>
+__global__ void __launch_bounds__(kFuse ? kFusedThreads : kGemmThreads, 1)
 gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb,
-                const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
-  using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8>;
+                const __grid_constant__ CUtensorMap tmap_d, const GemmParams p, const FuseParams fp) {
+  static_assert(!kFuse || (kCtaGroup == 2 && A_ROWS == 128 && !kF8), "fused quantise+GEMM: CTA pairs, FP4 only");
+  using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ACC = Cfg::ACC_STAGES;
   constexpr int SFKB = Cfg::SFKB;
@@ -178,9 +260,12 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // griddepcontrol.wait and overlaps the predecessor's tail; activations are loaded only after it.
       const int pre = total_kt < STAGES ? total_kt : STAGES;
       // (tile, kt) cursor advanced incrementally: no divisions on the per-k-tile path
-      struct Cursor { int tile, kt, m0, n0, nb0; };
+      struct Cursor { int tile, kt, m0, n0, nb0, tm; };
       auto set_tile = [&](Cursor& c) {
-        const int tm = c.tile % p.tiles_m, tn = c.tile / p.tiles_m;
+        // fused: N-fastest (the first wave touches only the first row blocks of A); otherwise M-fastest
+        const int tm = kFuse ? c.tile / p.tiles_n : c.tile % p.tiles_m;
+        const int tn = kFuse ? c.tile - tm * p.tiles_n : c.tile / p.tiles_m;
+        c.tm = tm;
         c.m0 = (tm * kCtaGroup + (int)cta_rank) * BM;            // this CTA's A rows
         c.n0 = tn * BN;
         c.nb0 = c.n0 + (int)cta_rank * Cfg::B_ROWS;              // this CTA's B rows
@@ -203,8 +288,20 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, kt * BK_BYTES, m0);
         tma_load_3d<kCtaGroup>(ssfa, &tmap_sfa, fb, 0, kt * SFKB, m0 / 128);
       };
-      Cursor cur{cluster_id, 0, 0, 0, 0};
+      Cursor cur{cluster_id, 0, 0, 0, 0, 0};
       set_tile(cur);
+      // fused: A / SFA of row block tm exist once the quantiser warps (of ALL CTAs) have written its warp-tiles
+      int ready_tm = -1;
+      auto wait_acts = [&](int tm) {
+        if constexpr (kFuse) {
+          if (tm != ready_tm) {
+            const int rows = (p.M - tm * 256) < 256 ? (p.M - tm * 256) : 256;
+            wait_counter_ge(fp.ctr + 2 + tm, (uint32_t)rows * fp.tiles_per_row, 7);
+            fence_proxy_async_global();     // generic-proxy writes (other SMs) -> this SM's TMA (async proxy) reads
+            ready_tm = tm;
+          }
+        }
+      };
       {
         Cursor c = cur;
         for (int g = 0; g < pre; ++g) {          // ring is empty: no wait needed for the first STAGES slots
@@ -214,6 +311,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       pdl_wait();
       for (int g = 0; g < pre; ++g) {
+        wait_acts(cur.tm);
         if (elected) load_acts(g, cur.m0, cur.kt);
         advance(cur);
       }
@@ -222,10 +320,9 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       uint32_t phase = (pre == STAGES) ? 1 : 0;
       for (int g = pre; g < total_kt; ++g) {
         mbar_wait(bar_base + 8u * (STAGES + stage), phase ^ 1, 1);
-        if (elected) {
-          load_weights(stage, cur.n0, cur.nb0, cur.kt);
-          load_acts(stage, cur.m0, cur.kt);
-        }
+        if (elected) load_weights(stage, cur.n0, cur.nb0, cur.kt);
+        wait_acts(cur.tm);
+        if (elected) load_acts(stage, cur.m0, cur.kt);
         __syncwarp();
         advance(cur);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -257,7 +354,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int tn = tile / p.tiles_m;
+        const int tn = kFuse ? tile % p.tiles_n : tile / p.tiles_m;
         const int n0 = tn * BN;
         const uint32_t sfb_shift = (uint32_t)((n0 % 128) / 32);     // 0 or 2 columns into the first SFB block
         mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2);
@@ -311,6 +408,16 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (kFuse && warp >= 2 + kEpiWarps) {
+    // ===================== quantiser (warps 10..13, fused kernel only) =====================
+    if constexpr (kFuse) {
+      pdl_wait();   // x comes from the previous kernel in the stream; the outputs may still be read by it
+      zero_fill_sf_padding(fp.q, (int64_t)blockIdx.x * (32 * kQuantWarps) + (threadIdx.x - kGemmThreads),
+                           (int64_t)gridDim.x * (32 * kQuantWarps));
+      uint4* qstage = reinterpret_cast<uint4*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STG_TOTAL + Cfg::BAR_BYTES) +
+                      (warp - 2 - kEpiWarps) * 128;
+      quantiser_role<kNV>(fp, qstage, lane);
+    }
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int ew = warp - 2;
@@ -324,12 +431,57 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     pdl_wait();   // D must not be written before the predecessor kernel has finished (it may still read that memory)
     const float alpha = __ldg(p.alpha);
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+      const int tm = kFuse ? tile / p.tiles_n : tile % p.tiles_m;
+      const int tn = kFuse ? tile - tm * p.tiles_n : tile / p.tiles_m;
       const int m0 = (tm * kCtaGroup + (int)cta_rank) * BM;
       const int n0 = tn * BN;
       mbar_wait(tfull_bar(acc), acc_phase, 6);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + col0 + ((uint32_t)(q * 32) << 16);
+      if constexpr (kFuse) {
+        // 448 threads -> 144 registers: drain chunk by chunk, keeping only packed bf16 pairs (EPI_COLS / 2 registers)
+        uint32_t pk[Cfg::EPI_COLS / 2];
+#pragma unroll
+        for (int ch = 0; ch < Cfg::EPI_NCHUNK; ++ch) {
+          uint32_t r[Cfg::EPI_CHUNK];
+#pragma unroll
+          for (int j = 0; j < Cfg::EPI_CHUNK / 32; ++j) tmem_ld_32x32b_x32(taddr + ch * Cfg::EPI_CHUNK + j * 32, r + j * 32);
+          tmem_ld_wait();
+          if (ch == Cfg::EPI_NCHUNK - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader + 8u * acc);
+          }
+#pragma unroll
+          for (int i = 0; i < Cfg::EPI_CHUNK / 2; ++i) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[2 * i]) * alpha, __uint_as_float(r[2 * i + 1]) * alpha);
+            pk[ch * (Cfg::EPI_CHUNK / 2) + i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < Cfg::EPI_NCHUNK; ++ch) {
+          if (lane == 0) bulk_wait_group_read<0>();     // staging buffer free again
+          __syncwarp();
+          constexpr int PIECES = Cfg::EPI_CHUNK / 8;
+#pragma unroll
+          for (int jj = 0; jj < PIECES; ++jj) {
+            const int phys = (Cfg::EPI_CHUNK == 64) ? (jj ^ (lane & 7)) : (jj ^ ((lane >> 1) & 3));
+            const uint32_t addr = stg + lane * (Cfg::EPI_CHUNK * 2) + phys * 16;
+            const int b = ch * (Cfg::EPI_CHUNK / 2) + jj * 4;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[b]), "r"(pk[b + 1]), "r"(pk[b + 2]),
+                         "r"(pk[b + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_d, stg, n0 + col0 + ch * Cfg::EPI_CHUNK, m0 + q * 32);
+            bulk_commit_group();
+          }
+        }
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       // drain this warp's 32 x EPI_COLS slice of the accumulator into registers, then release TMEM at once
       uint32_t r[Cfg::EPI_COLS];
       if (!(p.flags & 2)) {
@@ -450,6 +602,18 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     __syncwarp();   // .sync.aligned: the issuing lane must have reconverged with its warp
     tmem_dealloc<kCtaGroup>(tmem_base, Cfg::TMEM_COLS);
   }
+  if constexpr (kFuse) {
+    // every poll / release of this CTA is behind the barrier above; the last CTA to get here re-zeroes the workspace
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(fp.ctr + 1, 1u) == gridDim.x - 1) {
+        for (int i = 0; i < p.tiles_m; ++i) fp.ctr[2 + i] = 0u;
+        fp.ctr[0] = 0u;
+        fp.ctr[1] = 0u;
+        __threadfence();
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -516,11 +680,11 @@ static int make_d_tmap(CUtensorMap* tm, const void* ptr, int64_t M, int64_t N, i
                 chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "D");
 }
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false, bool kFuse = false>
 static int launch_gemm(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D,
-                       int M, int N, int K, int ldd, cudaStream_t stream) {
-  using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8>;
-  auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV, A_ROWS, kF8>;
+                       int M, int N, int K, int ldd, cudaStream_t stream, const FuseParams* fuse = nullptr) {
+  using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
+  auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -560,7 +724,7 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   if (clusters > total) clusters = total;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * kCtaGroup));
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(kFuse ? kFusedThreads : kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
@@ -577,7 +741,9 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
     const char* e = getenv("B200Q_NO_PDL");
     cfg.numAttrs = (e && e[0] == '1') ? 1 : 2;
   }
-  B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tsa, tsb, td, p));
+  FuseParams fpv = {};
+  if (fuse) fpv = *fuse;
+  B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tsa, tsb, td, p, fpv));
   return 0;
 }
 
@@ -697,6 +863,87 @@ extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA,
 extern "C" int b200q_gemm_fp4(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha_dev,
                               void* D_bf16, int M, int N, int K, int kind, b200q_stream_t stream) {
   return b200q_gemm_fp4_cfg(A, B, SFA, SFB, alpha_dev, D_bf16, M, N, K, kind, 0, 0, stream);
+}
+
+// ------------------------------------------------------------------ fused quantise + GEMM
+namespace b200q {
+static bool fusion_enabled() {
+  const char* e = getenv("B200Q_NO_FUSE");
+  return !(e && e[0] == '1');
+}
+// the fused kernel needs: trusted Hadamard rotation, whole warp-tiles per row (K % 1024 == 0), TMA-store epilogue
+// (N % 8 == 0), the CTA-pair plan (M > 256 or wide N) and FP4 operands
+static bool fusable(int M, int N, int K, int had, int method, int kind) {
+  if (!fusion_enabled()) return false;
+  if (kind != B200Q_KIND_MXF4 && kind != B200Q_KIND_NVF4) return false;
+  if (!(method & B200Q_ROT_TRUSTED_HADAMARD)) return false;
+  if (K % 1024 != 0 || N % 8 != 0) return false;
+  if ((int64_t)M * K / 1024 >= ((int64_t)1 << 31)) return false;
+  (void)had;
+  return plan_auto(M, N, K, kind).cta_group == 2;
+}
+}  // namespace b200q
+
+extern "C" int64_t b200q_linear_fp4_workspace_bytes(int M) {
+  if (M <= 0) return 0;
+  return round_up((int64_t)(ceil_div(M, 256) + 2) * 4, 256);
+}
+
+extern "C" int b200q_linear_fp4_launches(int M, int N, int K, int had, int method, int kind) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (fusable(M, N, K, had, method, kind)) return 1;
+  return 1 + b200q_gemm_fp4_launches(M, N, K, kind);
+}
+
+extern "C" int b200q_linear_fp4(const void* x_bf16, const void* rot_bf16, void* xq_e2m1, void* x_sf_rowmajor,
+                                void* x_sf_blocked, const void* Wq, const void* Wsf_blocked, const float* alpha_dev,
+                                const float* global_scale_dev, void* D_bf16, void* ws, int M, int N, int K, int had,
+                                int method, int kind, b200q_stream_t stream) {
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  B200Q_REQUIRE(kind == B200Q_KIND_MXF4 || kind == B200Q_KIND_NVF4, "invalid kind %d (MXF4 or NVF4)", kind);
+  B200Q_REQUIRE(x_sf_blocked, "x_sf_blocked is required (the GEMM reads the blocked scales)");
+  B200Q_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive (got %d, %d, %d)", M, N, K);
+  const bool nv = kind == B200Q_KIND_NVF4;
+  if (!ws || !fusable(M, N, K, had, method, kind)) {
+    // two launches: the standalone quantiser, then the GEMM (programmatic dependent launch overlaps its prologue)
+    rc = nv ? b200q_quantize_nv(x_bf16, rot_bf16, xq_e2m1, x_sf_rowmajor, x_sf_blocked, global_scale_dev, (int64_t)M * K, K,
+                                had, method, stream)
+            : b200q_quantize_mx(x_bf16, rot_bf16, xq_e2m1, x_sf_rowmajor, x_sf_blocked, nullptr, (int64_t)M * K, K, had,
+                                method, stream);
+    if (rc) return rc;
+    return b200q_gemm_fp4(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, kind, stream);
+  }
+  B200Q_REQUIRE(Wq && Wsf_blocked && alpha_dev && D_bf16, "null pointer argument");
+  B200Q_REQUIRE((((uintptr_t)xq_e2m1 | (uintptr_t)Wq | (uintptr_t)x_sf_blocked | (uintptr_t)Wsf_blocked | (uintptr_t)D_bf16) & 15) == 0,
+                "xq, Wq, scale buffers and D must be 16-byte aligned");
+  B200Q_REQUIRE(((uintptr_t)ws & 3) == 0, "workspace must be 4-byte aligned");
+  const int m = method & ~(B200Q_ROT_TRUSTED_HADAMARD | B200Q_ROT_GENERIC);
+  B200Q_REQUIRE(m == B200Q_METHOD_QUEST || m == B200Q_METHOD_ABSMAX, "invalid method %d, must be quest (0) or abs_max (1)", m);
+  B200Q_REQUIRE(had == 32 || had == 64 || had == 128 || (nv && had == 16),
+                nv ? "Unsupported rotation size %d; expected 16, 32, 64, or 128." : "Unsupported rotation size %d; expected 32, 64, or 128.", had);
+  B200Q_REQUIRE(!nv || global_scale_dev, "global_scale must be a device pointer to one float");
+  FuseParams fp = {};
+  rc = fill_params(fp.q, x_bf16, rot_bf16, xq_e2m1, x_sf_rowmajor, x_sf_blocked, (int64_t)M * K, K, had, nv ? 16 : 32);
+  if (rc) return rc;
+  fp.q.gs = global_scale_dev;
+  fp.q.trust_hadamard = 1;
+  fp.ctr = (uint32_t*)ws;
+  fp.tiles_per_row = (uint32_t)(K / 1024);
+  fp.had = had;
+  fp.method = m;
+  const GemmPlan pl = plan_auto(M, N, K, kind);
+  cudaStream_t s = (cudaStream_t)stream;
+#define B200Q_FCASE(BNV)                                                                                                      \
+  if (pl.block_n == BNV)                                                                                                      \
+    return nv ? launch_gemm<2, BNV, true, 128, false, true>(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, N, s, &fp) \
+              : launch_gemm<2, BNV, false, 128, false, true>(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, N, s, &fp);
+  B200Q_FCASE(256)
+  B200Q_FCASE(192)
+  B200Q_FCASE(128)
+#undef B200Q_FCASE
+  set_error("no fused configuration for block_n=%d", pl.block_n);
+  return B200Q_EINVAL;
 }
 
 extern "C" int b200q_gemm_fp4_launches(int M, int N, int K, int kind) {

@@ -114,6 +114,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   }
 }
 
+// ------------------------------------------------------------------ cross-CTA progress counters in global memory
+// producer side: all writes of the warp, __syncwarp, then ONE lane publishes with a gpu-scope release add;
+// consumer side: acquire load, then a generic->async proxy fence so that a following TMA load sees the data.
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* addr, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void wait_counter_ge(const uint32_t* addr, uint32_t want, int tag = 0) {
+  if (ld_acquire_gpu(addr) >= want) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(addr) < want) {
+    __nanosleep(100);
+    if (clock64() - t0 > B200Q_SPIN_LIMIT_CYCLES) {
+      printf("b200q: progress-counter wait timed out (tag %d, block %d, thread %d, want %u)\n", tag, (int)blockIdx.x,
+             (int)threadIdx.x, want);
+      __trap();
+    }
+  }
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");

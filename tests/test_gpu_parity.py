@@ -423,6 +423,85 @@ def test_linear_host_entry_point():
     assert torch.equal(d_host.cuda(), want)
 
 
+# ----------------------------------------------------------------------------- fused quantise + GEMM (one persistent kernel)
+def _fused_case(m, n, k, had, method, fmt, seed):
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(had))
+    x = H.bf16_tensor_from_f32(H.random_bf16((m, k), seed=seed))
+    w = H.bf16_tensor_from_f32(H.random_bf16((n, k), seed=seed + 1))
+    al = torch.tensor([1.0 / 9.0], device="cuda")
+    gs = torch.tensor([3.0], device="cuda")
+    if fmt == "mx":
+        wq, wsf = Q.fusedQuantizeMx(w, R, method="abs_max")
+        xq, xsf = Q.fusedQuantizeMx(x, R, method=method)
+        want = Q.matmul_mxf4_bf16_tn(xq, wq, Q.to_blocked(xsf), Q.to_blocked(wsf), al)
+    else:
+        wq, wsf = Q.fusedQuantizeNv(w, R, gs, method="abs_max")
+        xq, xsf = Q.fusedQuantizeNv(x, R, gs, method=method)
+        want = Q.matmul_nvf4_bf16_tn(xq, wq, Q.to_blocked(xsf), Q.to_blocked(wsf), al)
+    torch.cuda.synchronize()
+    return R, x, wq, Q.to_blocked(wsf), al, gs, xq, xsf, want
+
+
+@pytest.mark.parametrize("fmt,had,method", [("mx", 128, "abs_max"), ("mx", 64, "quest"), ("mx", 32, "abs_max"),
+                                            ("nv", 16, "abs_max"), ("nv", 128, "quest"), ("nv", 64, "abs_max")])
+@pytest.mark.parametrize("shape", [(512, 512, 1024), (1000, 1544, 2048), (300, 4096, 1024), (2048, 2304, 4096)])
+def test_fused_linear_equals_two_calls(fmt, had, method, shape):
+    """b200q_linear_fp4 (quantiser warps inside the persistent GEMM) must reproduce fusedQuantize* followed by matmul_*
+    bit for bit: codes, both scale layouts and the bf16 output."""
+    m, n, k = shape
+    R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, had, method, fmt, seed=m + n)
+    lib = _lib.load()
+    meth = (0 if method == "quest" else 1) | Q.ROT_TRUSTED_HADAMARD
+    assert lib.b200q_linear_fp4_launches(m, n, k, had, meth, 0 if fmt == "mx" else 1) == 1      # really the fused kernel
+    for _ in range(3):    # repeated calls reuse the self-cleaning counter workspace
+        out, xq2, xsf2 = Q.fused_linear_fp4(x, R, wq, wblk, al, global_scale=gs if fmt == "nv" else None, method=method, fmt=fmt)
+        torch.cuda.synchronize()
+        assert torch.equal(xq2, xq)
+        rows, cols = m, k // (32 if fmt == "mx" else 16)
+        assert torch.equal(xsf2.view(torch.uint8)[:rows, :cols], xsf.view(torch.uint8)[:rows, :cols])
+        assert torch.equal(Q.to_blocked(xsf2).view(torch.uint8), Q.to_blocked(xsf).view(torch.uint8))
+        assert torch.equal(out, want)
+    for ws in Q._FUSE_WS.values():
+        assert int(ws.view(torch.int32).abs().sum()) == 0           # left zeroed
+
+
+def test_fused_linear_fallback_and_graph():
+    """shapes the fused kernel does not take (K % 1024 != 0, small M) run as two launches with the same results; the
+    fused kernel is CUDA-graph capturable once its workspace exists."""
+    lib = _lib.load()
+    for (m, n, k) in ((512, 512, 1536), (128, 1024, 1024)):
+        R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, 64, "abs_max", "mx", seed=7)
+        assert lib.b200q_linear_fp4_launches(m, n, k, 64, 1 | Q.ROT_TRUSTED_HADAMARD, 0) == 2
+        out, xq2, _ = Q.fused_linear_fp4(x, R, wq, wblk, al)
+        torch.cuda.synchronize()
+        assert torch.equal(out, want) and torch.equal(xq2, xq)
+    m, n, k = 768, 1024, 2048
+    R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, 128, "abs_max", "mx", seed=9)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        Q.fused_linear_fp4(x, R, wq, wblk, al)       # warm-up on the capture stream: creates its workspace
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        out, _, _ = Q.fused_linear_fp4(x, R, wq, wblk, al)
+    for _ in range(3):
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want)
+
+
+def test_fused_linear_full_size():
+    """config 1 (4096 x 14336 x 4096) through the fused kernel, 20 back-to-back calls: identical to the two-kernel path."""
+    m, n, k = 4096, 14336, 4096
+    R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, 128, "abs_max", "mx", seed=3)
+    for i in range(20):
+        out, xq2, _ = Q.fused_linear_fp4(x, R, wq, wblk, al)
+    torch.cuda.synchronize()
+    assert torch.equal(xq2, xq) and torch.equal(out, want)
+
+
 # ----------------------------------------------------------------------------- MXFP8 ("next" row of the scope table)
 @pytest.mark.parametrize("cfg", [(0, 0), (1, 128), (1, 256), (2, 128), (2, 192), (2, 256)])
 @pytest.mark.parametrize("shape", [(128, 128, 128), (256, 512, 1024), (504, 504, 2048), (16, 1000, 2176), (1, 504, 4096),
