@@ -40,11 +40,11 @@ constexpr int BM = 128;          // rows of A per CTA
 constexpr int BK_BYTES = 128;    // one k-tile = 256 e2m1 = 128 bytes per row (one 128B-swizzle row)
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 320
-constexpr int kQuantWarps = 4;                       // fused kernel only: warps 10-13 rotate + quantise the activations
-constexpr int kFusedThreads = kGemmThreads + 32 * kQuantWarps;   // 448 -> 144 registers / thread
+// fused kernel: kFuse (2 or 4) extra warps rotate + quantise the activations.  4 warps -> 448 threads -> 4 warps on one
+// scheduler -> 128 registers / thread (chunked epilogue drain); 2 warps -> 384 threads -> 168 registers (plain epilogue).
 constexpr int kSmemBudget = 227 * 1024;
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false, bool kFuse = false>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false, int kFuse = 0>
 struct GemmCfg {
   // A_ROWS < 128 (small M): only A_ROWS rows of the A tile are loaded and kept per stage; the MMA still reads a
   // 128-row operand (the bytes that follow) -- those accumulator rows are garbage and never stored.  Smaller
@@ -77,7 +77,8 @@ struct GemmCfg {
   static constexpr int STG_BYTES = 32 * EPI_CHUNK * 2;           // one staging buffer per epilogue warp
   static constexpr int STG_TOTAL = kEpiWarps * STG_BYTES;
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int QSTG_BYTES = kFuse ? kQuantWarps * 2048 : 0;   // quantiser warps' swizzled staging (2 KB each)
+  static constexpr int QSTG_BYTES = kFuse * 2048;                // quantiser warps' swizzled staging (2 KB each)
+  static constexpr int THREADS = kGemmThreads + 32 * kFuse;
   static constexpr int STAGES_RAW = (kSmemBudget - BAR_BYTES - 1024 - STG_TOTAL - QSTG_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_TOTAL + BAR_BYTES + QSTG_BYTES + 1024;  // +1024 alignment slack
@@ -177,12 +178,13 @@ __device__ __forceinline__ void quantiser_role(const FuseParams& fp, uint4* stag
 #undef B200Q_QCASE
 }
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS, bool kF8, bool kFuse>
-__global__ void __launch_bounds__(kFuse ? kFusedThreads : kGemmThreads, 1)
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS, bool kF8, int kFuse>
+__global__ void __launch_bounds__(kGemmThreads + 32 * kFuse, 1)
 gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb,
                 const __grid_constant__ CUtensorMap tmap_d, const GemmParams p, const FuseParams fp) {
-  static_assert(!kFuse || (kCtaGroup == 2 && A_ROWS == 128 && !kF8), "fused quantise+GEMM: CTA pairs, FP4 only");
+  static_assert(kFuse == 0 || ((kFuse == 2 || kFuse == 4) && kCtaGroup == 2 && A_ROWS == 128 && !kF8),
+                "fused quantise+GEMM: CTA pairs, FP4 only, 2 or 4 quantiser warps");
   using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ACC = Cfg::ACC_STAGES;
@@ -210,6 +212,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int cluster_id = blockIdx.x / kCtaGroup;
   const int num_clusters = gridDim.x / kCtaGroup;
   const int total_tiles = p.tiles_m * p.tiles_n;
+  const bool nfast = kFuse != 0 || (p.flags & 2048) != 0;   // tile walk: N-fastest (fused; profiling flag 2048) or M-fastest
 
   // a dependent grid (e.g. the tail GEMM of a split launch) may start its prologue / weight loads while this one runs
   pdl_launch_dependents();
@@ -263,8 +266,8 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       struct Cursor { int tile, kt, m0, n0, nb0, tm; };
       auto set_tile = [&](Cursor& c) {
         // fused: N-fastest (the first wave touches only the first row blocks of A); otherwise M-fastest
-        const int tm = kFuse ? c.tile / p.tiles_n : c.tile % p.tiles_m;
-        const int tn = kFuse ? c.tile - tm * p.tiles_n : c.tile / p.tiles_m;
+        const int tm = nfast ? c.tile / p.tiles_n : c.tile % p.tiles_m;
+        const int tn = nfast ? c.tile - tm * p.tiles_n : c.tile / p.tiles_m;
         c.tm = tm;
         c.m0 = (tm * kCtaGroup + (int)cta_rank) * BM;            // this CTA's A rows
         c.n0 = tn * BN;
@@ -294,7 +297,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int ready_tm = -1;
       auto wait_acts = [&](int tm) {
         if constexpr (kFuse) {
-          if (tm != ready_tm) {
+          if (tm != ready_tm && !(p.flags & 1024)) {     // profiling flag 1024: no quantisers, no waits
             const int rows = (p.M - tm * 256) < 256 ? (p.M - tm * 256) : 256;
             wait_counter_ge(fp.ctr + 2 + tm, (uint32_t)rows * fp.tiles_per_row, 7);
             fence_proxy_async_global();     // generic-proxy writes (other SMs) -> this SM's TMA (async proxy) reads
@@ -354,7 +357,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int tn = kFuse ? tile % p.tiles_n : tile / p.tiles_m;
+        const int tn = nfast ? tile % p.tiles_n : tile / p.tiles_m;
         const int n0 = tn * BN;
         const uint32_t sfb_shift = (uint32_t)((n0 % 128) / 32);     // 0 or 2 columns into the first SFB block
         mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2);
@@ -409,14 +412,14 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
     }
   } else if (kFuse && warp >= 2 + kEpiWarps) {
-    // ===================== quantiser (warps 10..13, fused kernel only) =====================
-    if constexpr (kFuse) {
+    // ===================== quantiser (warps 10.., fused kernel only) =====================
+    if constexpr (kFuse != 0) {
       pdl_wait();   // x comes from the previous kernel in the stream; the outputs may still be read by it
-      zero_fill_sf_padding(fp.q, (int64_t)blockIdx.x * (32 * kQuantWarps) + (threadIdx.x - kGemmThreads),
-                           (int64_t)gridDim.x * (32 * kQuantWarps));
+      if (!(p.flags & 1024)) zero_fill_sf_padding(fp.q, (int64_t)blockIdx.x * (32 * kFuse) + (threadIdx.x - kGemmThreads),
+                           (int64_t)gridDim.x * (32 * kFuse));
       uint4* qstage = reinterpret_cast<uint4*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STG_TOTAL + Cfg::BAR_BYTES) +
                       (warp - 2 - kEpiWarps) * 128;
-      quantiser_role<kNV>(fp, qstage, lane);
+      if (!(p.flags & 1024)) quantiser_role<kNV>(fp, qstage, lane);   // profiling flag 1024: GEMM part only
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -431,15 +434,15 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     pdl_wait();   // D must not be written before the predecessor kernel has finished (it may still read that memory)
     const float alpha = __ldg(p.alpha);
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const int tm = kFuse ? tile / p.tiles_n : tile % p.tiles_m;
-      const int tn = kFuse ? tile - tm * p.tiles_n : tile / p.tiles_m;
+      const int tm = nfast ? tile / p.tiles_n : tile % p.tiles_m;
+      const int tn = nfast ? tile - tm * p.tiles_n : tile / p.tiles_m;
       const int m0 = (tm * kCtaGroup + (int)cta_rank) * BM;
       const int n0 = tn * BN;
       mbar_wait(tfull_bar(acc), acc_phase, 6);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + col0 + ((uint32_t)(q * 32) << 16);
-      if constexpr (kFuse) {
-        // 448 threads -> 144 registers: drain chunk by chunk, keeping only packed bf16 pairs (EPI_COLS / 2 registers)
+      if constexpr (kFuse > 2) {
+        // 448 threads -> 128 registers: drain chunk by chunk, keeping only packed bf16 pairs (EPI_COLS / 2 registers)
         uint32_t pk[Cfg::EPI_COLS / 2];
 #pragma unroll
         for (int ch = 0; ch < Cfg::EPI_NCHUNK; ++ch) {
@@ -602,7 +605,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     __syncwarp();   // .sync.aligned: the issuing lane must have reconverged with its warp
     tmem_dealloc<kCtaGroup>(tmem_base, Cfg::TMEM_COLS);
   }
-  if constexpr (kFuse) {
+  if constexpr (kFuse != 0) {
     // every poll / release of this CTA is behind the barrier above; the last CTA to get here re-zeroes the workspace
     if (threadIdx.x == 0) {
       __threadfence();
@@ -680,7 +683,7 @@ static int make_d_tmap(CUtensorMap* tm, const void* ptr, int64_t M, int64_t N, i
                 chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "D");
 }
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false, bool kFuse = false>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false, int kFuse = 0>
 static int launch_gemm(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D,
                        int M, int N, int K, int ldd, cudaStream_t stream, const FuseParams* fuse = nullptr) {
   using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
@@ -724,7 +727,7 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   if (clusters > total) clusters = total;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * kCtaGroup));
-  cfg.blockDim = dim3(kFuse ? kFusedThreads : kGemmThreads);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
@@ -934,13 +937,21 @@ extern "C" int b200q_linear_fp4(const void* x_bf16, const void* rot_bf16, void* 
   fp.method = m;
   const GemmPlan pl = plan_auto(M, N, K, kind);
   cudaStream_t s = (cudaStream_t)stream;
-#define B200Q_FCASE(BNV)                                                                                                      \
-  if (pl.block_n == BNV)                                                                                                      \
-    return nv ? launch_gemm<2, BNV, true, 128, false, true>(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, N, s, &fp) \
-              : launch_gemm<2, BNV, false, 128, false, true>(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, N, s, &fp);
-  B200Q_FCASE(256)
-  B200Q_FCASE(192)
-  B200Q_FCASE(128)
+  int qwarps = 4;
+  {
+    const char* e = getenv("B200Q_FUSE_WARPS");
+    if (e && e[0] == '2') qwarps = 2;
+  }
+#define B200Q_FCASE(BNV, QW)                                                                                                  \
+  if (pl.block_n == BNV && qwarps == QW)                                                                                      \
+    return nv ? launch_gemm<2, BNV, true, 128, false, QW>(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, N, s, &fp) \
+              : launch_gemm<2, BNV, false, 128, false, QW>(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, N, s, &fp);
+  B200Q_FCASE(256, 4)
+  B200Q_FCASE(192, 4)
+  B200Q_FCASE(128, 4)
+  B200Q_FCASE(256, 2)
+  B200Q_FCASE(192, 2)
+  B200Q_FCASE(128, 2)
 #undef B200Q_FCASE
   set_error("no fused configuration for block_n=%d", pl.block_n);
   return B200Q_EINVAL;
