@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-fuse", action="store_true", help="step = two launches (quantise kernel, then GEMM) instead of the fused kernel")
+    ap.add_argument("--fuse", action="store_true", help="step = the single fused quantise+GEMM kernel (B200Q_FUSE=1; measured slower)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -237,7 +237,9 @@ def main():
 
     # the whole step through ONE C-ABI call: one persistent kernel (quantiser warps inside the GEMM) when eligible
     fuse_ws = torch.zeros(max(int(lib.b200q_linear_fp4_workspace_bytes(M)), 256), dtype=torch.uint8, device=dev)
-    fused = (not args.no_fuse) and args.cta_group == 0
+    fused = args.fuse and args.cta_group == 0
+    if fused:
+        os.environ["B200Q_FUSE"] = "1"
     launches_per_step = lib.b200q_linear_fp4_launches(M, N, K, args.had, method, knd) if fused else \
         1 + (lib.b200q_gemm_fp4_launches(M, N, K, knd) if args.cta_group == 0 else 1)
 

@@ -134,10 +134,13 @@ int b200q_gemm_fp4_launches(int M, int N, int K, int kind);
  * Replaces the reference's per-layer sequence fusedQuantizeMx -> to_blocked -> matmul_mxf4_bf16_tn
  * (qutlass/__init__.py:149-180, utils.py:160-193, __init__.py:34-43; benchmarks/bench_mxfp4_sm100.py:93-104).
  *
- * When `method` carries B200Q_ROT_TRUSTED_HADAMARD, K % 1024 == 0, N % 8 == 0 and the problem is large enough for the
- * CTA-pair GEMM (M > 256), this is ONE persistent kernel: 4 extra warps per CTA quantise the activations under the
- * tensor pipe's shadow and publish 256-row blocks through progress counters in `ws`; the GEMM's TMA producer acquires
- * a block's counter before loading it.  Otherwise it is the two launches.  B200Q_NO_FUSE=1 forces the two launches.
+ * Default: the two launches (the GEMM's prologue and weight loads overlap the quantiser's tail through programmatic
+ * dependent launch).  With B200Q_FUSE=1 in the environment, `method` carrying B200Q_ROT_TRUSTED_HADAMARD, K % 1024 == 0,
+ * N % 8 == 0 and a problem large enough for the CTA-pair GEMM (M > 256) it is ONE persistent kernel: 4 extra warps per
+ * CTA (plus the epilogue warps until their first accumulator is ready) quantise the activations and publish 256-row
+ * blocks through progress counters in `ws`; the GEMM's TMA producer acquires a block's counter before loading it.
+ * Measured on B200 the single kernel is bit-identical but not faster (the part is power-limited under FP4 MMA load:
+ * profiles/r01_notes.md), hence opt-in.
  *   ws: NULL (never fuse) or b200q_linear_fp4_workspace_bytes(M) bytes of device memory that the caller zeroes ONCE
  *       (cudaMemset) after allocating; every call leaves it zeroed.  One workspace per stream.
  *   had / method / global_scale_dev as for b200q_quantize_*; kind B200Q_KIND_MXF4 or B200Q_KIND_NVF4.

@@ -281,9 +281,10 @@ def fused_linear_fp4(x: torch.Tensor, rot: torch.Tensor, w_q: torch.Tensor, w_sf
         xq, x_sf = fusedQuantizeMx(x, rot, method=method)          # or fusedQuantizeNv(x, rot, global_scale)
         out = matmul_mxf4_bf16_tn(xq, w_q, to_blocked(x_sf), w_sf, alpha)
 
-    Returns (out [M, N] bf16, xq, x_sf) -- bit-identical to the two calls.  For a Hadamard rotation, K % 1024 == 0,
-    N % 8 == 0 and M > 256 it runs as ONE persistent kernel (quantiser warps inside the GEMM, include/b200q.h:
-    b200q_linear_fp4); otherwise as the two launches.  ``w_sf`` is the blocked (to_blocked) weight scale buffer.
+    Returns (out [M, N] bf16, xq, x_sf) -- bit-identical to the two calls.  By default it IS the two launches behind one
+    C-ABI call (include/b200q.h: b200q_linear_fp4); with B200Q_FUSE=1, a Hadamard rotation, K % 1024 == 0, N % 8 == 0 and
+    M > 256 it runs as one persistent kernel with quantiser warps inside the GEMM (measured: not faster on a power-limited
+    B200, profiles/r01_notes.md).  ``w_sf`` is the blocked (to_blocked) weight scale buffer.
     """
     if method not in ("quest", "abs_max"):
         raise ValueError(f"invalid method {method!r}, must be 'quest' or 'abs_max'")

@@ -116,8 +116,14 @@ struct FuseParams {
   int had, method;
 };
 
-template <int HAD, bool NV, int METHOD>
-__device__ __forceinline__ void quantiser_loop(const FuseParams& fp, uint4* stage, int lane) {
+// One warp's share of the activation quantisation.  Work is claimed in batches of BATCH consecutive warp-tiles from the
+// ticket counter.  HELPER = false (dedicated quantiser warps): the next batch's ticket and the next tile's loads are
+// always in flight under the current tile's math.  HELPER = true (epilogue warps before their first accumulator): no
+// look-ahead -- a claimed batch must be finished, so the warp re-checks `stop_bar` (its CTA's first tmem-full
+// barrier, phase 0) before every claim and leaves at most one batch late.
+template <int HAD, bool NV, int METHOD, bool HELPER>
+__device__ __forceinline__ void quantiser_loop(const FuseParams& fp, uint4* stage, int lane, uint32_t stop_bar) {
+  constexpr uint32_t BATCH = HELPER ? 2u : 4u;
   const QuantParams& p = fp.q;
   const float c_scale = __bfloat162float(p.rot[0]);
   float gs = 1.f, gs_rcp = 1.f;
@@ -128,41 +134,69 @@ __device__ __forceinline__ void quantiser_loop(const FuseParams& fp, uint4* stag
   const uint32_t n_tiles = (uint32_t)p.n_tiles;
   const uint32_t tiles_per_block = 256u * fp.tiles_per_row;     // one cluster tile = 256 rows of A
   uint32_t* ready = fp.ctr + 2;
-  auto grab = [&]() -> uint32_t {
+  auto claim = [&]() -> uint32_t {          // lane 0's register only; broadcast (and wait for it) with bcast()
     uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(fp.ctr, 1u);
-    return __shfl_sync(0xffffffffu, t, 0);
+    if (lane == 0) t = atomicAdd(fp.ctr, BATCH);
+    return t;
   };
+  auto bcast = [&](uint32_t t) -> uint32_t { return __shfl_sync(0xffffffffu, t, 0); };
   auto load = [&](uint32_t tile, uint4 (&dst)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       dst[i] = (tile < n_tiles) ? __ldg(p.x + ((int64_t)tile * 128 + i * 32 + lane)) : make_uint4(0, 0, 0, 0);
   };
-  uint32_t tile = grab();
+  auto publish = [&](uint32_t t0, uint32_t t1) {   // warp-tiles [t0, t1) are written: bump their row blocks' counters
+    __syncwarp();                                  // every lane's stores precede lane 0's release
+    if (lane == 0) {
+      const uint32_t b0 = t0 / tiles_per_block, b1 = (t1 - 1u) / tiles_per_block;
+      if (b0 == b1) {
+        red_release_gpu_add(ready + b0, t1 - t0);
+      } else {                                     // a batch can straddle one block boundary
+        const uint32_t cut = b1 * tiles_per_block;
+        __threadfence();
+        atomicAdd(ready + b0, cut - t0);
+        atomicAdd(ready + b1, t1 - cut);
+      }
+    }
+  };
+  uint32_t base = bcast(claim());
+  uint32_t next_ticket = 0;
   uint4 nxt[4];
-  load(tile, nxt);
-  while (tile < n_tiles) {
-    const uint32_t ntile = grab();           // ticket + loads of the next tile are in flight under this tile's math
-    uint4 ld[4];
+  load(base, nxt);
+  while (base < n_tiles) {
+    if constexpr (!HELPER) next_ticket = claim();            // result is not needed before this batch's last tile
+    const uint32_t end = (base + BATCH < n_tiles) ? base + BATCH : n_tiles;
+    uint32_t nbase = n_tiles;
+    for (uint32_t tile = base; tile < end; ++tile) {
+      uint4 ld[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ld[i] = nxt[i];
-    load(ntile, nxt);
-    float v[32];
-    tile_stage_unpack(ld, stage, lane, v);
-    tile_rotate_hadamard<HAD>(v, c_scale);
-    tile_quantise_store<NV, METHOD, false>(p, v, (int64_t)tile, lane, gs, gs_rcp);
-    __syncwarp();                            // every lane's stores precede lane 0's release
-    if (lane == 0) red_release_gpu_add(ready + tile / tiles_per_block, 1u);
-    tile = ntile;
+      for (int i = 0; i < 4; ++i) ld[i] = nxt[i];
+      uint32_t ntile = tile + 1u;
+      if (ntile == end) {
+        if constexpr (!HELPER) { nbase = bcast(next_ticket); ntile = nbase; } else { ntile = n_tiles; }
+      }
+      load(ntile, nxt);
+      float v[32];
+      tile_stage_unpack(ld, stage, lane, v);
+      tile_rotate_hadamard<HAD>(v, c_scale);
+      tile_quantise_store<NV, METHOD, false>(p, v, (int64_t)tile, lane, gs, gs_rcp);
+    }
+    publish(base, end);
+    if constexpr (HELPER) {
+      if (bcast(lane == 0 ? (uint32_t)mbar_try_wait(stop_bar, 0) : 0u)) break;   // first accumulator ready: back to epilogue duty
+      nbase = bcast(claim());
+      load(nbase, nxt);
+    }
+    base = nbase;
   }
 }
 
-template <bool NV>
-__device__ __forceinline__ void quantiser_role(const FuseParams& fp, uint4* stage, int lane) {
-#define B200Q_QCASE(H)                                                                        \
-  case H:                                                                                     \
-    if (fp.method == B200Q_METHOD_QUEST) quantiser_loop<H, NV, B200Q_METHOD_QUEST>(fp, stage, lane); \
-    else quantiser_loop<H, NV, B200Q_METHOD_ABSMAX>(fp, stage, lane);                         \
+template <bool NV, bool HELPER>
+__device__ __forceinline__ void quantiser_role(const FuseParams& fp, uint4* stage, int lane, uint32_t stop_bar) {
+#define B200Q_QCASE(H)                                                                                          \
+  case H:                                                                                                       \
+    if (fp.method == B200Q_METHOD_QUEST) quantiser_loop<H, NV, B200Q_METHOD_QUEST, HELPER>(fp, stage, lane, stop_bar); \
+    else quantiser_loop<H, NV, B200Q_METHOD_ABSMAX, HELPER>(fp, stage, lane, stop_bar);                          \
     break;
   switch (fp.had) {
     B200Q_QCASE(128)
@@ -170,8 +204,8 @@ __device__ __forceinline__ void quantiser_role(const FuseParams& fp, uint4* stag
     B200Q_QCASE(32)
     case 16:
       if constexpr (NV) {
-        if (fp.method == B200Q_METHOD_QUEST) quantiser_loop<16, NV, B200Q_METHOD_QUEST>(fp, stage, lane);
-        else quantiser_loop<16, NV, B200Q_METHOD_ABSMAX>(fp, stage, lane);
+        if (fp.method == B200Q_METHOD_QUEST) quantiser_loop<16, NV, B200Q_METHOD_QUEST, HELPER>(fp, stage, lane, stop_bar);
+        else quantiser_loop<16, NV, B200Q_METHOD_ABSMAX, HELPER>(fp, stage, lane, stop_bar);
       }
       break;
   }
@@ -212,7 +246,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int cluster_id = blockIdx.x / kCtaGroup;
   const int num_clusters = gridDim.x / kCtaGroup;
   const int total_tiles = p.tiles_m * p.tiles_n;
-  const bool nfast = kFuse != 0 || (p.flags & 2048) != 0;   // tile walk: N-fastest (fused; profiling flag 2048) or M-fastest
+  const bool nfast = (p.flags & 2048) != 0;   // tile walk: M-fastest (B tiles shared by concurrent clusters); profiling flag 2048: N-fastest
 
   // a dependent grid (e.g. the tail GEMM of a split launch) may start its prologue / weight loads while this one runs
   pdl_launch_dependents();
@@ -297,7 +331,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int ready_tm = -1;
       auto wait_acts = [&](int tm) {
         if constexpr (kFuse) {
-          if (tm != ready_tm && !(p.flags & 1024)) {     // profiling flag 1024: no quantisers, no waits
+          if (tm != ready_tm && !(p.flags & (1024 | 8192))) {     // profiling flags: 1024 no quantisers + no waits, 8192 no waits
             const int rows = (p.M - tm * 256) < 256 ? (p.M - tm * 256) : 256;
             wait_counter_ge(fp.ctr + 2 + tm, (uint32_t)rows * fp.tiles_per_row, 7);
             fence_proxy_async_global();     // generic-proxy writes (other SMs) -> this SM's TMA (async proxy) reads
@@ -419,7 +453,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                            (int64_t)gridDim.x * (32 * kFuse));
       uint4* qstage = reinterpret_cast<uint4*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STG_TOTAL + Cfg::BAR_BYTES) +
                       (warp - 2 - kEpiWarps) * 128;
-      if (!(p.flags & 1024)) quantiser_role<kNV>(fp, qstage, lane);   // profiling flag 1024: GEMM part only
+      if (!(p.flags & 1024)) quantiser_role<kNV, false>(fp, qstage, lane, 0u);   // profiling flag 1024: GEMM part only
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -433,6 +467,14 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const uint32_t tempty_leader = (kCtaGroup == 2) ? mapa(tempty_bar(0), 0) : tempty_bar(0);
     pdl_wait();   // D must not be written before the predecessor kernel has finished (it may still read that memory)
     const float alpha = __ldg(p.alpha);
+    if constexpr (kFuse != 0) {
+      // Until this CTA's first accumulator is complete the 8 epilogue warps have nothing to do: they help quantise
+      // (their TMA-store staging buffer doubles as the quantiser staging).  All of A is then written about as fast as
+      // by the standalone kernel, and the M-fastest tile walk of the first round can start row block by row block.
+      if (!(p.flags & (1024 | 4096)))
+        quantiser_role<kNV, true>(fp, reinterpret_cast<uint4*>(smem_gen + STAGES * Cfg::STAGE_BYTES + ew * Cfg::STG_BYTES), lane,
+                                  tfull_bar(0));
+    }
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int tm = nfast ? tile / p.tiles_n : tile % p.tiles_m;
       const int tn = nfast ? tile - tm * p.tiles_n : tile / p.tiles_m;
@@ -870,9 +912,13 @@ extern "C" int b200q_gemm_fp4(const void* A, const void* B, const void* SFA, con
 
 // ------------------------------------------------------------------ fused quantise + GEMM
 namespace b200q {
+// Measured on B200 (profiles/r01_notes.md, tools/fuse_probe.py): the fused kernel is bit-identical but NOT faster -- the
+// part is power-limited under FP4 MMA load, the quantiser warps' work costs the tensor pipe about as much time as the
+// standalone quantise kernel takes (104.8 us fused with the producer never waiting vs 103.7 us for the two launches,
+// 93.8 us with the quantisers idle).  So the default is the two launches; B200Q_FUSE=1 opts into the single kernel.
 static bool fusion_enabled() {
-  const char* e = getenv("B200Q_NO_FUSE");
-  return !(e && e[0] == '1');
+  const char* e = getenv("B200Q_FUSE");
+  return e && e[0] == '1';
 }
 // the fused kernel needs: trusted Hadamard rotation, whole warp-tiles per row (K % 1024 == 0), TMA-store epilogue
 // (N % 8 == 0), the CTA-pair plan (M > 256 or wide N) and FP4 operands
@@ -950,8 +996,6 @@ extern "C" int b200q_linear_fp4(const void* x_bf16, const void* rot_bf16, void* 
   B200Q_FCASE(192, 4)
   B200Q_FCASE(128, 4)
   B200Q_FCASE(256, 2)
-  B200Q_FCASE(192, 2)
-  B200Q_FCASE(128, 2)
 #undef B200Q_FCASE
   set_error("no fused configuration for block_n=%d", pl.block_n);
   return B200Q_EINVAL;

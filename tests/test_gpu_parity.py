@@ -445,10 +445,12 @@ def _fused_case(m, n, k, had, method, fmt, seed):
 @pytest.mark.parametrize("fmt,had,method", [("mx", 128, "abs_max"), ("mx", 64, "quest"), ("mx", 32, "abs_max"),
                                             ("nv", 16, "abs_max"), ("nv", 128, "quest"), ("nv", 64, "abs_max")])
 @pytest.mark.parametrize("shape", [(512, 512, 1024), (1000, 1544, 2048), (300, 4096, 1024), (2048, 2304, 4096)])
-def test_fused_linear_equals_two_calls(fmt, had, method, shape):
+def test_fused_linear_equals_two_calls(fmt, had, method, shape, monkeypatch):
     """b200q_linear_fp4 (quantiser warps inside the persistent GEMM) must reproduce fusedQuantize* followed by matmul_*
     bit for bit: codes, both scale layouts and the bf16 output."""
     m, n, k = shape
+    assert _lib.load().b200q_linear_fp4_launches(m, n, k, had, 1 | Q.ROT_TRUSTED_HADAMARD, 0) >= 2   # default: two launches
+    monkeypatch.setenv("B200Q_FUSE", "1")
     R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, had, method, fmt, seed=m + n)
     lib = _lib.load()
     meth = (0 if method == "quest" else 1) | Q.ROT_TRUSTED_HADAMARD
@@ -465,10 +467,11 @@ def test_fused_linear_equals_two_calls(fmt, had, method, shape):
         assert int(ws.view(torch.int32).abs().sum()) == 0           # left zeroed
 
 
-def test_fused_linear_fallback_and_graph():
+def test_fused_linear_fallback_and_graph(monkeypatch):
     """shapes the fused kernel does not take (K % 1024 != 0, small M) run as two launches with the same results; the
     fused kernel is CUDA-graph capturable once its workspace exists."""
     lib = _lib.load()
+    monkeypatch.setenv("B200Q_FUSE", "1")
     for (m, n, k) in ((512, 512, 1536), (128, 1024, 1024)):
         R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, 64, "abs_max", "mx", seed=7)
         assert lib.b200q_linear_fp4_launches(m, n, k, 64, 1 | Q.ROT_TRUSTED_HADAMARD, 0) == 2
@@ -492,12 +495,17 @@ def test_fused_linear_fallback_and_graph():
         assert torch.equal(out, want)
 
 
-def test_fused_linear_full_size():
+def test_fused_linear_full_size(monkeypatch):
     """config 1 (4096 x 14336 x 4096) through the fused kernel, 20 back-to-back calls: identical to the two-kernel path."""
     m, n, k = 4096, 14336, 4096
+    monkeypatch.setenv("B200Q_FUSE", "1")
     R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, 128, "abs_max", "mx", seed=3)
     for i in range(20):
         out, xq2, _ = Q.fused_linear_fp4(x, R, wq, wblk, al)
+    torch.cuda.synchronize()
+    assert torch.equal(xq2, xq) and torch.equal(out, want)
+    monkeypatch.delenv("B200Q_FUSE")
+    out, xq2, _ = Q.fused_linear_fp4(x, R, wq, wblk, al)          # default path: two launches behind the same call
     torch.cuda.synchronize()
     assert torch.equal(xq2, xq) and torch.equal(out, want)
 

@@ -5,6 +5,7 @@ with 2 / 4 quantiser warps.  Prints one JSON line per variant."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ["B200Q_FUSE"] = "1"
 import torch
 import qutlass_b200 as Q
 from qutlass_b200 import _lib
@@ -55,19 +56,29 @@ def timed(fn, n=100, warm=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 
-def run(name, fn, flags=0, warps=None):
-    os.environ["B200Q_GEMM_DEBUG_FLAGS"] = str(flags)
-    if warps: os.environ["B200Q_FUSE_WARPS"] = str(warps)
-    best = min(timed(fn) for _ in range(3))
-    ws.zero_(); torch.cuda.synchronize()     # variants that skip the quantisers leave nothing behind, but stay safe
-    print(json.dumps({"variant": name, "us": round(best, 2), "flags": flags, "warps": warps}), flush=True)
-
+VARIANTS = [
+    ("two launches (quantise, GEMM)", two, 0, None),
+    ("GEMM alone, M-fastest tiles", gemm, 0, None),
+    ("GEMM alone, N-fastest tiles", gemm, 2048, None),
+    ("fused, quantisers off, 4 warps (chunked drain, 448 thr)", fused, 1024, 4),
+    ("fused, quantisers off, 2 warps (plain epilogue, 384 thr)", fused, 1024, 2),
+    ("fused, 4 quantiser warps + epilogue helpers", fused, 0, 4),
+    ("fused, 4 quantiser warps + helpers, producer does not wait (timing only)", fused, 8192, 4),
+    ("fused, 4 quantiser warps, no helpers", fused, 4096, 4),
+    ("fused, 4 quantiser warps, no helpers, no waits (timing only)", fused, 4096 | 8192, 4),
+    ("fused, 4 quantiser warps, no helpers, N-fastest", fused, 4096 | 2048, 4),
+    ("fused, 4 quantiser warps, no helpers, N-fastest, no waits (timing only)", fused, 4096 | 2048 | 8192, 4),
+    ("fused, 2 quantiser warps, no helpers, N-fastest", fused, 4096 | 2048, 2),
+    ("fused, 4 quantiser warps + helpers, N-fastest", fused, 2048, 4),
+]
 for i in range(NS): quant(i)
-run("two launches (quantise, GEMM)", two)
-run("GEMM alone, M-fastest tiles", gemm)
-run("GEMM alone, N-fastest tiles", gemm, flags=2048)
-run("fused kernel, quantisers off, 4 warps (chunked drain, 448 thr)", fused, flags=1024, warps=4)
-run("fused kernel, quantisers off, 2 warps (plain epilogue, 384 thr)", fused, flags=1024, warps=2)
-run("fused kernel, 4 quantiser warps", fused, warps=4)
-run("fused kernel, 2 quantiser warps", fused, warps=2)
-run("two launches again", two)
+res = {v[0]: [] for v in VARIANTS}
+for rnd in range(int(os.environ.get("PROBE_ROUNDS", 6))):       # interleaved: clock / thermal drift hits every variant alike
+    for name, fn, flags, warps in VARIANTS:
+        os.environ["B200Q_GEMM_DEBUG_FLAGS"] = str(flags)
+        if warps: os.environ["B200Q_FUSE_WARPS"] = str(warps)
+        res[name].append(timed(fn, n=60, warm=5))
+        ws.zero_(); torch.cuda.synchronize()
+for name, ts in res.items():
+    ts = sorted(ts)
+    print(json.dumps({"variant": name, "min_us": round(ts[0], 2), "median_us": round(ts[len(ts) // 2], 2), "max_us": round(ts[-1], 2)}), flush=True)
