@@ -50,6 +50,9 @@ typedef struct CUstream_st* b200q_stream_t;
 #define B200Q_KIND_MXF8 2      /* e4m3 x e4m3 (one byte / element), ue8m0 scales, group 32 -- the "next"
                                   row of the scope table: replaces matmul_host_mxf8_bf16_tn (gemm.cu:328-380);
                                   A [M, K], B [N, K] bytes, same blocked scale layout                         */
+#define B200Q_KIND_MXF8_NN 3   /* as MXF8 but A is stored [K, M] (M contiguous; M % 16 == 0): replaces
+                                  matmul_host_mxf8_bf16_nn (gemm.cu:388-434).  D[m,n] = sum_k A[k,m] B[n,k]; the scales
+                                  of A stay in the blocked layout of the LOGICAL [M, K/32] matrix                */
 
 /* ABI version of this header (bumped on incompatible change). */
 int b200q_abi_version(void);

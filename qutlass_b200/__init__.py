@@ -30,7 +30,7 @@ __all__ = [
 METHOD_QUEST, METHOD_ABSMAX = 0, 1
 ROT_TRUSTED_HADAMARD = 0x100   # include/b200q.h: B200Q_ROT_TRUSTED_HADAMARD
 ROT_GENERIC = 0x200            # include/b200q.h: B200Q_ROT_GENERIC (known non-Hadamard -> tensor-core rotation)
-KIND_MXF4, KIND_NVF4, KIND_MXF8 = 0, 1, 2
+KIND_MXF4, KIND_NVF4, KIND_MXF8, KIND_MXF8_NN = 0, 1, 2, 3
 
 
 def _check(cond: bool, msg: str) -> None:
@@ -83,18 +83,25 @@ def _matmul_fp4(name: str, a, b, a_sf, b_sf, alpha, kind: int, sf_dtype, min_k_b
     """reference checks: qutlass/csrc/bindings.cpp:32-102"""
     _check_contig(name, [("A", a), ("B", b), ("A_sf", a_sf), ("B_sf", b_sf)])
     _check_cuda_same(name, [("A", a), ("B", b), ("A_sf", a_sf), ("B_sf", b_sf), ("alpha", alpha)])
-    op_dtype, op_name = (torch.float8_e4m3fn, "float8_e4m3fn") if kind == KIND_MXF8 else (torch.uint8, "uint8")
+    f8 = kind in (KIND_MXF8, KIND_MXF8_NN)
+    nn = kind == KIND_MXF8_NN            # A is stored [K, M] (reference: bindings.cpp:179-216)
+    op_dtype, op_name = (torch.float8_e4m3fn, "float8_e4m3fn") if f8 else (torch.uint8, "uint8")
     _check(a.dtype == op_dtype, f"A must be {op_name}")
     _check(b.dtype == op_dtype, f"B must be {op_name}")
     sf_name = "float8_e4m3fn" if kind == KIND_NVF4 else "float8_e8m0fnu"
     _check(a_sf.dtype == sf_dtype, f"A_sf must be {sf_name}")
     _check(b_sf.dtype == sf_dtype, f"B_sf must be {sf_name}")
     _check(a.dim() == 2 and b.dim() == 2, "A and B must be 2D")
-    _check(a.size(1) == b.size(1), "Inner dimensions must match for A @ B.T")
-    _check(a.size(1) >= min_k_bytes, f"A K-dim must be >= {min_k_bytes}")
+    if nn:
+        _check(a.size(0) == b.size(1), "Inner dimensions must match for A.T @ B.T")
+        _check(a.size(0) >= min_k_bytes, f"A K-dim must be >= {min_k_bytes}")
+        _check(a.size(1) % 16 == 0, f"M ({a.size(1)}) must be a multiple of 16")
+    else:
+        _check(a.size(1) == b.size(1), "Inner dimensions must match for A @ B.T")
+        _check(a.size(1) >= min_k_bytes, f"A K-dim must be >= {min_k_bytes}")
     _check(b.size(1) >= min_k_bytes, f"B K-dim must be >= {min_k_bytes}")
     _check(alpha.dtype == torch.float32 and alpha.numel() >= 1, "alpha must be a float32 tensor with one element")
-    m, n, k = a.size(0), b.size(0), a.size(1) * (1 if kind == KIND_MXF8 else 2)
+    m, n, k = (a.size(1) if nn else a.size(0)), b.size(0), b.size(1) * (1 if f8 else 2)
     group = 16 if kind == KIND_NVF4 else 32
     _check(k % 32 == 0, f"K ({k}) must be a multiple of 32")
     need_a = ((m + 127) // 128) * 128 * (((k // group) + 3) // 4) * 4
@@ -138,6 +145,16 @@ def matmul_mxf8_bf16_tn(a: torch.Tensor, b: torch.Tensor, block_scale_a: torch.T
     (reference: qutlass/__init__.py:134-139, bindings.cpp:140-176, gemm.cu:328-380) -- the first "next" row after
     the FP4 path, same tcgen05 kernel with kind::mxf8f6f4."""
     return _matmul_fp4("matmul_mxf8_bf16_tn", a, b, block_scale_a, block_scale_b, alpha, KIND_MXF8,
+                       torch.float8_e8m0fnu, 32)
+
+
+def matmul_mxf8_bf16_nn(a: torch.Tensor, b: torch.Tensor, block_scale_a: torch.Tensor, block_scale_b: torch.Tensor,
+                        alpha: torch.Tensor) -> torch.Tensor:
+    """As matmul_mxf8_bf16_tn with A stored TRANSPOSED, a = [K, M] e4m3 (M contiguous): D[m, n] = sum_k a[k, m] b[n, k]
+    (reference: qutlass/__init__.py:141-146, bindings.cpp:179-216, gemm.cu:388-434; tests/mxfp8_test.py:77-96).
+    ``block_scale_a`` is still the blocked scale buffer of the logical [M, K/32] matrix.  The tile of A is loaded by
+    TMA as 128 K-rows x 128 M-bytes and consumed as an MN-major tcgen05 operand -- no transpose pass."""
+    return _matmul_fp4("matmul_mxf8_bf16_nn", a, b, block_scale_a, block_scale_b, alpha, KIND_MXF8_NN,
                        torch.float8_e8m0fnu, 32)
 
 
@@ -342,7 +359,6 @@ def _out_of_scope(name: str):
 
 
 matmul_ada_mxf4_bf16_tn = _out_of_scope("matmul_ada_mxf4_bf16_tn")      # sm_120-only prototype (gemm_ada.cu)
-matmul_mxf8_bf16_nn = _out_of_scope("matmul_mxf8_bf16_nn")              # MN-major A operand (QAT backward)
 backward_t_bf16 = _out_of_scope("backward_t_bf16")
 backward_qt_bf16 = _out_of_scope("backward_qt_bf16")
 backward_bf16_square_double_mxfp8 = _out_of_scope("backward_bf16_square_double_mxfp8")
@@ -361,6 +377,7 @@ def _register_ops() -> None:
         "matmul_mxf4_bf16_tn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
         "matmul_nvf4_bf16_tn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
         "matmul_mxf8_bf16_tn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
+        "matmul_mxf8_bf16_nn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
         "fusedQuantizeMxQuest": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf) -> (Tensor, Tensor)",
         "fusedQuantizeMxAbsMax": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf) -> (Tensor, Tensor)",
         "fusedQuantizeNvQuest": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf, Tensor global_scale) -> (Tensor, Tensor)",
@@ -371,6 +388,7 @@ def _register_ops() -> None:
         "matmul_mxf4_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_mxf4_bf16_tn(A, B, A_sf, B_sf, alpha),
         "matmul_nvf4_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_nvf4_bf16_tn(A, B, A_sf, B_sf, alpha),
         "matmul_mxf8_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_mxf8_bf16_tn(A, B, A_sf, B_sf, alpha),
+        "matmul_mxf8_bf16_nn": lambda A, B, A_sf, B_sf, alpha: matmul_mxf8_bf16_nn(A, B, A_sf, B_sf, alpha),
         "fusedQuantizeMxQuest": lambda A, R, OUT, OUT_sf: (_quantize_mx_into(A, R, OUT, OUT_sf, None, None, METHOD_QUEST), (OUT, OUT_sf))[1],
         "fusedQuantizeMxAbsMax": lambda A, R, OUT, OUT_sf: (_quantize_mx_into(A, R, OUT, OUT_sf, None, None, METHOD_ABSMAX), (OUT, OUT_sf))[1],
         "fusedQuantizeNvQuest": lambda A, R, OUT, OUT_sf, gs: (_quantize_nv_into(A, R, OUT, OUT_sf, None, gs, METHOD_QUEST), (OUT, OUT_sf))[1],

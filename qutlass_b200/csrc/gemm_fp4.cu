@@ -44,12 +44,15 @@ constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 320
 // scheduler -> 128 registers / thread (chunked epilogue drain); 2 warps -> 384 threads -> 168 registers (plain epilogue).
 constexpr int kSmemBudget = 227 * 1024;
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false, int kFuse = 0>
+// kF8: 0 = FP4 operands; 1 = MXFP8 "tn" (A [M, K] bytes); 2 = MXFP8 "nn" (A stored [K, M], M contiguous: an MN-major
+// tcgen05 operand -- same 128B-swizzled 16 KB stage, rows are K instead of M)
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, int kF8 = 0, int kFuse = 0>
 struct GemmCfg {
   // A_ROWS < 128 (small M): only A_ROWS rows of the A tile are loaded and kept per stage; the MMA still reads a
   // 128-row operand (the bytes that follow) -- those accumulator rows are garbage and never stored.  Smaller
   // stages = more k-tiles of B in flight, which is what bounds the weight-streaming (decode) regime.
   static_assert(A_ROWS % 8 == 0 && A_ROWS >= 8 && A_ROWS <= 128 && (A_ROWS == 128 || kCtaGroup == 1), "A_ROWS");
+  static_assert(kF8 != 2 || A_ROWS == 128, "the MN-major A tile is always 128 K-rows x 128 M-bytes");
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 64 in [64, 256]");
   // kF8: 8-bit e4m3 operands (MXFP8, ue8m0 scales per 32): a 128-byte k-tile is 128 elements = 4 scales = one block
   static constexpr int SFKB = kNV ? 4 : (kF8 ? 1 : 2);           // 512-B scale blocks per 128 rows per k-tile
@@ -212,7 +215,7 @@ __device__ __forceinline__ void quantiser_role(const FuseParams& fp, uint4* stag
 #undef B200Q_QCASE
 }
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS, bool kF8, int kFuse>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS, int kF8, int kFuse>
 __global__ void __launch_bounds__(kGemmThreads + 32 * kFuse, 1)
 gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb,
@@ -322,7 +325,8 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
         const uint32_t ssfa = sa + Cfg::A_BYTES + Cfg::B_BYTES;
         const uint32_t fb = full0 + 8u * stage;
-        tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, kt * BK_BYTES, m0);
+        if constexpr (kF8 == 2) tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, m0, kt * Cfg::BK_ELEMS);   // A [K, M]: box = 128 K-rows x 128 M-bytes
+        else tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, kt * BK_BYTES, m0);
         tma_load_3d<kCtaGroup>(ssfa, &tmap_sfa, fb, 0, kt * SFKB, m0 / 128);
       };
       Cursor cur{cluster_id, 0, 0, 0, 0, 0};
@@ -374,8 +378,12 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // (Measured: issuing the scale copies of k-tile g+1 ahead of the MMAs of k-tile g is SLOWER -- the
       // tensor pipe runs cp/mma in order -- so the order is cp(g), mma(g).)
       // instruction descriptor: e2m1 operands (format 1) for the mxf4 kinds, e4m3 (format 0) for mxf8f6f4
-      constexpr uint32_t idesc_base = kF8 ? (make_idesc_fp4(BM * kCtaGroup, BN, true) & ~((1u << 7) | (1u << 10)))
+      constexpr uint32_t idesc_base = kF8 ? ((make_idesc_fp4(BM * kCtaGroup, BN, true) & ~((1u << 7) | (1u << 10))) |
+                                             (kF8 == 2 ? (1u << 15) : 0u))                 // a_major = MN
                                           : make_idesc_fp4(BM * kCtaGroup, BN, !kNV);
+      // K advance of the A descriptor per MMA: 32 bytes along the swizzled row (K-major), or 32 K-rows of 128 bytes
+      // = four 1024-byte swizzle atoms (MN-major: canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, SBO = 1024 B)
+      constexpr uint32_t kAStep16 = (kF8 == 2) ? (32u * 128u) >> 4 : 2u;
       constexpr uint32_t kDescHiAB = (1024u >> 4) | (1u << 14) | (kLayoutSw128 << 29);   // SBO 1024 B, version 1, 128B swizzle
       constexpr uint32_t kDescHiSF = (128u >> 4) | (1u << 14);                            // SBO 128 B, version 1, no swizzle
       constexpr uint32_t kStage16 = Cfg::STAGE_BYTES >> 4;
@@ -431,7 +439,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (!upfront && !skip_cp && (kNV || (kF8 ? kb == 0 : (kb & 1) == 0))) copy_chunk((int)chunk);
             if (k_left > kb * Cfg::MMA_K) {
               const uint32_t sf_id = kNV ? 0u : (kF8 ? (uint32_t)kb : (uint32_t)((kb & 1) * 2));
-              mma_fp4_block_scaled<kCtaGroup, kNV, kF8>(tmem_acc, mk(a_lo + kb * 2, kDescHiAB), mk(b_lo + kb * 2, kDescHiAB),
+              mma_fp4_block_scaled<kCtaGroup, kNV, (kF8 != 0)>(tmem_acc, mk(a_lo + kb * kAStep16, kDescHiAB), mk(b_lo + kb * 2, kDescHiAB),
                                                    idesc_base | (sf_id << 4) | (sf_id << 29), tmem_sfa + chunk * 4,
                                                    tsfb + chunk * (4 * NB), (kt > 0 || kb > 0) ? 1u : 0u);
             }
@@ -725,7 +733,7 @@ static int make_d_tmap(CUtensorMap* tm, const void* ptr, int64_t M, int64_t N, i
                 chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "D");
 }
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, bool kF8 = false, int kFuse = 0>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, int kF8 = 0, int kFuse = 0>
 static int launch_gemm(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D,
                        int M, int N, int K, int ldd, cudaStream_t stream, const FuseParams* fuse = nullptr) {
   using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
@@ -740,7 +748,11 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   CUtensorMap ta, tb, tsa, tsb, td;
   int rc;
   const int64_t row_bytes = kF8 ? K : K / 2;
-  if ((rc = make_operand_tmap(&ta, A, M, row_bytes, A_ROWS, "A"))) return rc;
+  if constexpr (kF8 == 2) {
+    if ((rc = make_operand_tmap(&ta, A, K, M, 128, "A[K,M]"))) return rc;      // rows = K, row pitch = M bytes, box 128 x 128
+  } else {
+    if ((rc = make_operand_tmap(&ta, A, M, row_bytes, A_ROWS, "A"))) return rc;
+  }
   if ((rc = make_operand_tmap(&tb, B, N, row_bytes, Cfg::B_ROWS, "B"))) return rc;
   if ((rc = make_sf_tmap(&tsa, SFA, ceil_div(M, 128), sf_col_blocks, Cfg::SFKB, 1, "SFA"))) return rc;
   if ((rc = make_sf_tmap(&tsb, SFB, ceil_div(N, 128), sf_col_blocks, Cfg::SFKB, Cfg::NB, "SFB"))) return rc;
@@ -792,13 +804,15 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   return 0;
 }
 
-template <bool kNV, bool kF8>
+template <bool kNV, int kF8>
 static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B, const void* SFA, const void* SFB,
                         const float* alpha, void* D, int M, int N, int K, int ldd, cudaStream_t s) {
   // small M: same 128-wide single-CTA tile, fewer A rows staged (more weight k-tiles in flight)
-  if (cta_group == 1 && block_n == 128 && M <= 16) return launch_gemm<1, 128, kNV, 16, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
-  if (cta_group == 1 && block_n == 128 && M <= 32) return launch_gemm<1, 128, kNV, 32, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
-  if (cta_group == 1 && block_n == 128 && M <= 64) return launch_gemm<1, 128, kNV, 64, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+  if constexpr (kF8 != 2) {
+    if (cta_group == 1 && block_n == 128 && M <= 16) return launch_gemm<1, 128, kNV, 16, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+    if (cta_group == 1 && block_n == 128 && M <= 32) return launch_gemm<1, 128, kNV, 32, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+    if (cta_group == 1 && block_n == 128 && M <= 64) return launch_gemm<1, 128, kNV, 64, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+  }
 #define B200Q_CASE(CG, BNV) \
   if (cta_group == CG && block_n == BNV) return launch_gemm<CG, BNV, kNV, 128, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
   B200Q_CASE(1, 128)
@@ -806,7 +820,7 @@ static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B
   B200Q_CASE(2, 128)
   B200Q_CASE(2, 192)
   B200Q_CASE(2, 256)
-  if constexpr (!kF8) {
+  if constexpr (kF8 == 0) {
     B200Q_CASE(1, 64)
     B200Q_CASE(1, 192)
   }
@@ -848,7 +862,7 @@ static GemmPlan plan_auto(int M, int N, int K, int kind) {
   // config 1 with (2,128) tail tiles, 97.1 us with (1,64)), because a tile's sequential k-loop, not the tile count, sets
   // the length of the last round.  Kept as an opt-in experiment: B200Q_TAIL_SPLIT=1.
   const char* split_env = getenv("B200Q_TAIL_SPLIT");
-  if (split_env && split_env[0] == '1' && cta_group == 2 && block_n == 256 && N % 8 == 0 && kind != B200Q_KIND_MXF8) {
+  if (split_env && split_env[0] == '1' && cta_group == 2 && block_n == 256 && N % 8 == 0 && kind != B200Q_KIND_MXF8 && kind != B200Q_KIND_MXF8_NN) {
     // Wave quantisation: with T tiles over C CTA pairs the last round is only (T mod C)/C full.  When that round is
     // less than half full and peeling the LAST 256-column block of N saves a whole round, that block runs as a second
     // launch of narrower (2,128) tiles that fits in one wave (it starts as the main grid drains: PDL, disjoint D
@@ -874,7 +888,9 @@ extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA,
   int rc = check_device_sm100();
   if (rc) return rc;
   B200Q_REQUIRE(A && B && SFA && SFB && alpha_dev && D_bf16, "null pointer argument");
-  B200Q_REQUIRE(kind == B200Q_KIND_MXF4 || kind == B200Q_KIND_NVF4 || kind == B200Q_KIND_MXF8, "invalid kind %d", kind);
+  B200Q_REQUIRE(kind == B200Q_KIND_MXF4 || kind == B200Q_KIND_NVF4 || kind == B200Q_KIND_MXF8 || kind == B200Q_KIND_MXF8_NN,
+                "invalid kind %d", kind);
+  B200Q_REQUIRE(kind != B200Q_KIND_MXF8_NN || M % 16 == 0, "nn: M (%d) must be a multiple of 16 (row pitch of A [K, M])", M);
   B200Q_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive (got %d, %d, %d)", M, N, K);
   B200Q_REQUIRE(K % 32 == 0, "K (%d) must be a multiple of 32", K);
   B200Q_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)SFA | (uintptr_t)SFB) & 15) == 0,
@@ -889,9 +905,10 @@ extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA,
   }
   cudaStream_t s = (cudaStream_t)stream;
   auto run = [&](int cg, int bn, const void* Bp, const void* SFBp, void* Dp, int n_sub) -> int {
-    if (kind == B200Q_KIND_NVF4) return dispatch_cfg<true, false>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
-    if (kind == B200Q_KIND_MXF8) return dispatch_cfg<false, true>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
-    return dispatch_cfg<false, false>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
+    if (kind == B200Q_KIND_NVF4) return dispatch_cfg<true, 0>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
+    if (kind == B200Q_KIND_MXF8) return dispatch_cfg<false, 1>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
+    if (kind == B200Q_KIND_MXF8_NN) return dispatch_cfg<false, 2>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
+    return dispatch_cfg<false, 0>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
   };
   if (pl.n_main > 0) {
     const int group = kind == B200Q_KIND_NVF4 ? 16 : 32;

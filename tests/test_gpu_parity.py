@@ -223,6 +223,8 @@ def test_error_behaviour():
     with pytest.raises(ImportError):
         Q.matmul_mxf4_bf16_tn(a, a, sf, sf, al, backend="flashinfer")
     with pytest.raises(NotImplementedError):
+        Q.backward_t_bf16(a, a)
+    with pytest.raises(RuntimeError, match="A must be float8_e4m3fn"):
         Q.matmul_mxf8_bf16_nn(a, a, sf, sf, al)
     with pytest.raises(RuntimeError, match="A must be float8_e4m3fn"):
         Q.matmul_mxf8_bf16_tn(a, a, sf, sf, al)
@@ -549,8 +551,51 @@ def test_mxfp8_golden_and_reference_style(golden):
     ref = torch.from_numpy((O.dequant_mxf8(a_q, a_s) @ O.dequant_mxf8(b_q, b_s).T)).to(torch.bfloat16)
     torch.testing.assert_close(out.cpu(), ref, atol=1e-1, rtol=1e-1)
     assert (H.bf16_bits_of(out) != O.gemm_ref(O.dequant_mxf8(a_q, a_s), O.dequant_mxf8(b_q, b_s))).mean() <= 1e-2
-    with pytest.raises(NotImplementedError):
-        Q.matmul_mxf8_bf16_nn(out, out, out, out, out)
+
+
+@pytest.mark.parametrize("cfg", [(0, 0), (1, 128), (1, 256), (2, 128), (2, 192), (2, 256)])
+@pytest.mark.parametrize("shape", [(128, 128, 128), (256, 512, 1024), (496, 504, 2048), (16, 1000, 2176), (144, 72, 96),
+                                   (1024, 1536, 512)])
+def test_mxfp8_nn_gemm(cfg, shape):
+    """matmul_mxf8_bf16_nn: A stored [K, M] (reference tests/mxfp8_test.py:77-96 builds it as a_e4m3.T.contiguous()).
+    Same arithmetic as the tn kernel on the same logical operands -> bit-identical to it, and within fp32-accumulation
+    distance of the oracle."""
+    m, n, k = shape
+    aq, asf = H.random_f8_operand(m, k, seed=m + 21)
+    bq, bsf = H.random_f8_operand(n, k, seed=n + 22)
+    tn = H.run_gemm(aq, asf, bq, bsf, "f8", 1.0, cfg=cfg)
+    a_t = torch.from_numpy(np.ascontiguousarray(aq.T)).cuda().view(torch.float8_e4m3fn)          # [K, M]
+    b = torch.from_numpy(bq).cuda().view(torch.float8_e4m3fn)
+    al = torch.ones(1, device="cuda")
+    out = Q._matmul_fp4("matmul_mxf8_bf16_nn", a_t, b, H.sf_torch(H.blocked_sf(asf), "mx"), H.sf_torch(H.blocked_sf(bsf), "mx"),
+                        al, Q.KIND_MXF8_NN, torch.float8_e8m0fnu, 32, cfg=cfg)
+    torch.cuda.synchronize()
+    got = H.bf16_bits_of(out)
+    assert np.array_equal(got, tn)
+    want = H.gemm_oracle_bits(aq, asf, bq, bsf, "f8", 1.0)
+    assert (got != want).mean() <= 2e-2
+
+
+def test_mxfp8_nn_reference_style():
+    """the reference's own nn recipe (tests/mxfp8_test.py:77-96): randn*25 -> pseudoquant -> to_blocked(.., True) ->
+    a_e4m3.T.contiguous().view(k, m) -> matmul_mxf8_bf16_nn, assert_close(atol=1e-1, rtol=1e-1); Llama-7B shape, batch 16."""
+    m, n, k = 16, 4096, 4096
+    a = H.random_bf16((m, k), seed=91)
+    b = H.random_bf16((n, k), seed=92)
+    a_q, a_s = O.pseudoquant_mxfp8(a)
+    b_q, b_s = O.pseudoquant_mxfp8(b)
+    a_sf = torch.from_numpy(a_s).cuda().view(torch.float8_e8m0fnu)
+    b_sf = torch.from_numpy(b_s).cuda().view(torch.float8_e8m0fnu)
+    a_e4m3 = torch.from_numpy(a_q).cuda().view(torch.float8_e4m3fn)
+    a_e4m3 = a_e4m3.T.contiguous().view((k, m))
+    out = Q.matmul_mxf8_bf16_nn(a_e4m3, torch.from_numpy(b_q).cuda().view(torch.float8_e4m3fn),
+                                Q.to_blocked(a_sf, True), Q.to_blocked(b_sf, True), torch.tensor([1.0], device="cuda"))
+    torch.cuda.synchronize()
+    ref = torch.from_numpy((O.dequant_mxf8(a_q, a_s) @ O.dequant_mxf8(b_q, b_s).T)).to(torch.bfloat16)
+    torch.testing.assert_close(out.cpu(), ref, atol=1e-1, rtol=1e-1)
+    out2 = torch.ops._qutlass_C.matmul_mxf8_bf16_nn(a_e4m3, torch.from_numpy(b_q).cuda().view(torch.float8_e4m3fn),
+                                                    Q.to_blocked(a_sf, True), Q.to_blocked(b_sf, True), torch.tensor([1.0], device="cuda"))
+    assert torch.equal(out, out2)
 
 
 # ----------------------------------------------------------------------------- full-size properties
