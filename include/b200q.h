@@ -168,6 +168,54 @@ int b200q_linear_fp4_host(const void* x_host, const void* rot_bf16, const void* 
                           void* d_host, void* ws, int M, int N, int K, int had, int kind,
                           b200q_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Transposing re-quantisers of the QAT backward pass.  Same argument order as the
+ * reference's own raw-pointer entry points in qutlass/csrc/include/backward_host.h:4-46, plus `flags`
+ * (0 or B200Q_ROT_TRUSTED_HADAMARD: rot == c * Sylvester-Hadamard(32), in-register butterflies; without it the
+ * rotation is a generic fp32 x @ rot) where a rotation matrix is involved.  All tensors contiguous.
+ */
+
+/*
+ * MXFP4 abs-max quantisation of rotate(x^T).  Replaces backward_t_bf16_cuda (backward_host.h:17-26,
+ * quartet_bwd_sm120.cu:237-318,414-440; Python qutlass/__init__.py:206-244).
+ *   x_bf16 [size_b, size_n, size_m] bf16; rot_bf16 [32, 32]
+ *   xh_e2m1 [size_b, size_m, size_n/2], xh_e8m0 [size_b, size_m, size_n/32]: for every (b, m) and 32-group of n,
+ *   xh = x[b, n-group, m] @ rot; s = 2^floor(log2(amax)); codes e2m1(xh * 3 / s); scale byte of s.
+ *   size_n % 32 == 0, size_m % 8 == 0.
+ */
+int b200q_backward_t_bf16(const void* x_bf16, const void* rot_bf16, void* xh_e2m1, void* xh_e8m0, int size_m,
+                          int size_n, int size_b, int flags, b200q_stream_t stream);
+
+/*
+ * Same on an MXFP4 input: dequantise (code * 2^(e-127)), transpose, rotate, s = 2^floor(log2(amax / alpha)),
+ * codes e2m1(xh * 3 / (s * alpha)).  Replaces backward_qt_bf16_cuda (backward_host.h:4-15,
+ * quartet_bwd_sm120.cu:320-412,443-470; Python qutlass/__init__.py:247-283).
+ *   x_e2m1 [size_b, size_n, size_m/2], x_e8m0 [size_b, size_n, size_m/32], alpha_dev: one fp32 on the device
+ *   outputs as above; size_n % 32 == 0, size_m % 32 == 0.
+ */
+int b200q_backward_qt_bf16(const void* x_e2m1, const void* x_e8m0, const void* rot_bf16, const float* alpha_dev,
+                           void* xh_e2m1, void* xh_e8m0, int size_m, int size_n, int size_b, int flags,
+                           b200q_stream_t stream);
+
+/*
+ * bf16 [m, n] -> e4m3 with one ue8m0 scale per 32 x 32 tile (biased exponent of the tile's abs-max minus 7; 127 for an
+ * all-zero tile), the scale written twice: row_scales [m_pad, n/32] and column_scales [n, m_pad/32], m_pad = m rounded
+ * up to 128 (rows >= m are treated as zero -- the reference pads on the host, qutlass/__init__.py:285-288).
+ * Replaces backward_bf16_square_double_mxfp8_cuda (backward_host.h:28-36, quartet_bwd_sm120.cu:497-623).
+ *   x_fp8 [m_pad, n] bytes; n % 32 == 0.
+ */
+int b200q_backward_bf16_square_double_mxfp8(const void* x_bf16, int m, int n, void* x_fp8, void* row_scales,
+                                            void* column_scales, b200q_stream_t stream);
+
+/*
+ * MXFP4 [m, n/2] + ue8m0 scales [>= m, n/32] -> MXFP8 of the TRANSPOSE: x_fp8 [n, m_pad] e4m3 and shared_exps
+ * [n, m_pad/32] (32-groups along m, exponent as above), m_pad = m rounded up to 256; rows >= m read as zero (the
+ * reference pads on the host, qutlass/__init__.py:296-304).  Replaces mxfp4_transpose_mxfp8_cuda
+ * (backward_host.h:38-46, quartet_bwd_sm120.cu:625-734).   n % 32 == 0.
+ */
+int b200q_mxfp4_transpose_mxfp8(const void* x_fp4, const void* scales_e8m0, int m, int n, void* x_fp8,
+                                void* shared_exps, b200q_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,3 +14,4 @@ helpers (``/root/reference/tests/mxfp4_test.py`` and ``nvfp4_test.py``:
 and ``tests/test_oracle_golden.py`` (the check).
 """
 from .fp4_oracle import *  # noqa: F401,F403
+from . import bwd_oracle  # noqa: F401  (backward re-quantisers: oracle.bwd_oracle.*)

@@ -5,6 +5,10 @@ Drop-in for the hot-path subset of the reference's ``qutlass`` package
 
     fusedQuantizeMx, fusedQuantizeNv, matmul_mxf4_bf16_tn, matmul_nvf4_bf16_tn, utils.to_blocked
 
+plus, from the "next" rows of the scope table, the MXFP8 GEMMs (matmul_mxf8_bf16_tn / _nn) and the transposing
+re-quantisers of the QAT backward pass (backward_t_bf16, backward_qt_bf16, backward_bf16_square_double_mxfp8,
+mxfp4_transpose_mxfp8; reference qutlass/__init__.py:206-309)
+
 and the same op names/schemas under ``torch.ops._qutlass_C`` (bindings.cpp:498-507).  Host side =
 this module (argument checks, output allocation, stream selection) calling hand-written sm_100a
 CUDA in ``lib/libb200q.so`` through the thin C-ABI of ``include/b200q.h``.  No CUTLASS, FlashInfer,
@@ -359,10 +363,150 @@ def _out_of_scope(name: str):
 
 
 matmul_ada_mxf4_bf16_tn = _out_of_scope("matmul_ada_mxf4_bf16_tn")      # sm_120-only prototype (gemm_ada.cu)
-backward_t_bf16 = _out_of_scope("backward_t_bf16")
-backward_qt_bf16 = _out_of_scope("backward_qt_bf16")
-backward_bf16_square_double_mxfp8 = _out_of_scope("backward_bf16_square_double_mxfp8")
-mxfp4_transpose_mxfp8 = _out_of_scope("mxfp4_transpose_mxfp8")
+
+
+# --------------------------------------------------------------------------------------- backward re-quantisers
+def _bwd_rot_checks(name: str, h: torch.Tensor) -> int:
+    _check(h.dtype == torch.bfloat16, f"{name}: h must be bf16")
+    _check(h.dim() == 2 and h.size(0) == 32 and h.size(1) == 32, f"{name}: h must be a 32 x 32 rotation matrix")
+    return ROT_TRUSTED_HADAMARD if _rotation_hint(h) == ROT_TRUSTED_HADAMARD else 0
+
+
+def _backward_t_bf16_into(x, h, xh_e2m1, xh_e8m0) -> None:
+    name = "backward_t_bf16"
+    _check_cuda_same(name, [("x", x), ("h", h), ("xh_e2m1", xh_e2m1), ("xh_e8m0", xh_e8m0)])
+    _check_contig(name, [("x", x), ("h", h), ("xh_e2m1", xh_e2m1), ("xh_e8m0", xh_e8m0)])
+    _check(x.dtype == torch.bfloat16, f"{name}: x must be bf16")
+    _check(x.dim() >= 2, f"{name}: x must have at least 2 dimensions")
+    size_m, size_n = x.size(-1), x.size(-2)
+    size_b = x.numel() // max(size_m * size_n, 1)
+    _check(size_n % 32 == 0, f"{name}: x.size(-2) ({size_n}) must be a multiple of 32")
+    _check(size_m % 8 == 0, f"{name}: x.size(-1) ({size_m}) must be a multiple of 8")
+    _check(xh_e2m1.numel() * xh_e2m1.element_size() == size_b * size_m * size_n // 2, f"{name}: xh_e2m1 has the wrong size")
+    _check(xh_e8m0.numel() == size_b * size_m * size_n // 32, f"{name}: xh_e8m0 has the wrong size")
+    flags = _bwd_rot_checks(name, h)
+    with _DeviceGuard(x.device):
+        _lib.check(_lib.load().b200q_backward_t_bf16(x.data_ptr(), h.data_ptr(), xh_e2m1.data_ptr(), xh_e8m0.data_ptr(),
+                                                     size_m, size_n, size_b, flags, _stream(x)))
+
+
+def backward_t_bf16(x: torch.Tensor, h: torch.Tensor, xh_e2m1: torch.Tensor = None, xh_e8m0: torch.Tensor = None):
+    """MXFP4 abs-max quantisation of rotate(x.transpose(-2, -1)) without materialising the transpose
+    (reference: qutlass/__init__.py:206-244, quartet_bwd_sm120.cu:237-318; pinned by tests/quartet_test.py:220-226).
+    x [..., N, M] bf16 -> (e2m1 [..., M, N/2], e8m0 [..., M, N/32])."""
+    if xh_e2m1 is None:
+        xh_e2m1 = torch.empty(*x.shape[:-2], x.size(-1), x.size(-2) // 2, dtype=torch.float4_e2m1fn_x2, device=h.device)
+    if xh_e8m0 is None:
+        xh_e8m0 = torch.empty(*x.shape[:-2], x.size(-1), x.size(-2) // 32, dtype=torch.float8_e8m0fnu, device=h.device)
+    assert (x.dtype == h.dtype == torch.bfloat16 and xh_e2m1.dtype == torch.float4_e2m1fn_x2
+            and xh_e8m0.dtype == torch.float8_e8m0fnu)
+    assert x.is_contiguous() and h.is_contiguous() and xh_e2m1.is_contiguous() and xh_e8m0.is_contiguous()
+    _backward_t_bf16_into(x, h, xh_e2m1, xh_e8m0)
+    return xh_e2m1, xh_e8m0
+
+
+def _backward_qt_bf16_into(x_e2m1, x_e8m0, h, alpha, xh_e2m1, xh_e8m0) -> None:
+    name = "backward_qt_bf16"
+    ts = [("x_e2m1", x_e2m1), ("x_e8m0", x_e8m0), ("h", h), ("xh_e2m1", xh_e2m1), ("xh_e8m0", xh_e8m0)]
+    _check_cuda_same(name, ts + [("alpha", alpha)])
+    _check_contig(name, ts)
+    _check(x_e2m1.element_size() == 1 and x_e8m0.element_size() == 1, f"{name}: x_e2m1 / x_e8m0 must be 1-byte dtypes")
+    _check(alpha.dtype == torch.float32 and alpha.numel() >= 1, f"{name}: alpha must be a float32 tensor with one element")
+    _check(x_e2m1.dim() >= 2, f"{name}: x_e2m1 must have at least 2 dimensions")
+    size_m, size_n = x_e2m1.size(-1) * 2, x_e2m1.size(-2)
+    size_b = x_e2m1.numel() // max(x_e2m1.size(-1) * size_n, 1)
+    _check(size_n % 32 == 0, f"{name}: x_e2m1.size(-2) ({size_n}) must be a multiple of 32")
+    _check(size_m % 32 == 0, f"{name}: 2 * x_e2m1.size(-1) ({size_m}) must be a multiple of 32")
+    _check(x_e8m0.numel() == size_b * size_n * size_m // 32, f"{name}: x_e8m0 has the wrong size")
+    _check(xh_e2m1.numel() * xh_e2m1.element_size() == size_b * size_m * size_n // 2, f"{name}: xh_e2m1 has the wrong size")
+    _check(xh_e8m0.numel() == size_b * size_m * size_n // 32, f"{name}: xh_e8m0 has the wrong size")
+    flags = _bwd_rot_checks(name, h)
+    with _DeviceGuard(h.device):
+        _lib.check(_lib.load().b200q_backward_qt_bf16(
+            x_e2m1.data_ptr(), x_e8m0.data_ptr(), h.data_ptr(), alpha.data_ptr(), xh_e2m1.data_ptr(), xh_e8m0.data_ptr(),
+            size_m, size_n, size_b, flags, _stream(h)))
+
+
+def backward_qt_bf16(x_e2m1: torch.Tensor, x_e8m0: torch.Tensor, h: torch.Tensor, alpha: torch.Tensor,
+                     xh_e2m1: torch.Tensor = None, xh_e8m0: torch.Tensor = None):
+    """Dequantise an MXFP4 tensor, transpose, rotate and re-quantise (abs-max, scale / alpha) in one pass
+    (reference: qutlass/__init__.py:247-283, quartet_bwd_sm120.cu:320-412; pinned by tests/quartet_test.py:228-239).
+    x_e2m1 [..., N, M/2], x_e8m0 [..., N, M/32] -> (e2m1 [..., M, N/2], e8m0 [..., M, N/32])."""
+    if xh_e2m1 is None:
+        xh_e2m1 = torch.empty(*x_e2m1.shape[:-2], x_e2m1.size(-1) * 2, x_e2m1.size(-2) // 2,
+                              dtype=torch.float4_e2m1fn_x2, device=h.device)
+    if xh_e8m0 is None:
+        xh_e8m0 = torch.empty(*x_e8m0.shape[:-2], x_e8m0.size(-1) * 32, x_e8m0.size(-2) // 32,
+                              dtype=torch.float8_e8m0fnu, device=h.device)
+    assert (x_e2m1.is_contiguous() and x_e8m0.is_contiguous() and h.is_contiguous() and xh_e2m1.is_contiguous()
+            and xh_e8m0.is_contiguous())
+    _backward_qt_bf16_into(x_e2m1, x_e8m0, h, alpha, xh_e2m1, xh_e8m0)
+    return xh_e2m1, xh_e8m0
+
+
+def _square_double_into(x_bf16, x_fp8, row_scales, column_scales) -> None:
+    name = "backward_bf16_square_double_mxfp8"
+    ts = [("x_bf16", x_bf16), ("x_fp8", x_fp8), ("row_scales", row_scales), ("column_scales", column_scales)]
+    _check_cuda_same(name, ts)
+    _check_contig(name, ts)
+    _check(x_bf16.dtype == torch.bfloat16 and x_bf16.dim() == 2, f"{name}: x_bf16 must be a 2-D bf16 tensor")
+    m, n = x_bf16.shape
+    m_pad = (m + 127) // 128 * 128
+    _check(n % 32 == 0, f"{name}: x_bf16.size(1) ({n}) must be a multiple of 32")
+    _check(x_fp8.numel() == m_pad * n and x_fp8.element_size() == 1, f"{name}: x_fp8 must hold {m_pad} x {n} bytes")
+    _check(row_scales.numel() == m_pad * n // 32, f"{name}: row_scales must hold {m_pad} x {n // 32} bytes")
+    _check(column_scales.numel() == n * m_pad // 32, f"{name}: column_scales must hold {n} x {m_pad // 32} bytes")
+    with _DeviceGuard(x_bf16.device):
+        _lib.check(_lib.load().b200q_backward_bf16_square_double_mxfp8(
+            x_bf16.data_ptr(), m, n, x_fp8.data_ptr(), row_scales.data_ptr(), column_scales.data_ptr(), _stream(x_bf16)))
+
+
+def backward_bf16_square_double_mxfp8(x_bf16: torch.Tensor):
+    """bf16 [m, n] -> (e4m3 [m_pad, n], row scales [m_pad, n/32], column scales [n, m_pad/32]) with one e8m0 scale per
+    32 x 32 tile, usable both as a K-major and as an MN-major MXFP8 GEMM operand (reference: qutlass/__init__.py:285-294,
+    quartet_bwd_sm120.cu:497-623; pinned by tests/quartet_test.py:264-291,369-378).  The reference pads x to a multiple
+    of 128 rows with a host-side copy; here the kernel reads the missing rows as zero."""
+    _check(x_bf16.dim() == 2, "backward_bf16_square_double_mxfp8: x_bf16 must be 2-D")
+    m, n = x_bf16.shape
+    m_pad = (m + 127) // 128 * 128
+    x_fp8 = torch.empty(m_pad, n, dtype=torch.float8_e4m3fn, device=x_bf16.device)
+    row_scales = torch.empty(m_pad, n // 32, dtype=torch.float8_e8m0fnu, device=x_bf16.device)
+    column_scales = torch.empty(n, m_pad // 32, dtype=torch.float8_e8m0fnu, device=x_bf16.device)
+    _square_double_into(x_bf16.contiguous(), x_fp8, row_scales, column_scales)
+    return x_fp8, row_scales, column_scales
+
+
+def _mxfp4_transpose_mxfp8_into(x_fp4, scales, x_fp8, shared_exps, m: int) -> None:
+    name = "mxfp4_transpose_mxfp8"
+    ts = [("x_fp4", x_fp4), ("scales", scales), ("x_fp8", x_fp8), ("shared_exps", shared_exps)]
+    _check_cuda_same(name, ts)
+    _check_contig(name, ts)
+    _check(x_fp4.dim() == 2 and x_fp4.element_size() == 1, f"{name}: x_fp4 must be a 2-D 1-byte tensor")
+    _check(scales.element_size() == 1, f"{name}: scales must be a 1-byte dtype")
+    n = x_fp4.size(1) * 2
+    m_pad = (m + 255) // 256 * 256
+    _check(m <= x_fp4.size(0), f"{name}: m ({m}) exceeds x_fp4.size(0)")
+    _check(n % 32 == 0, f"{name}: 2 * x_fp4.size(1) ({n}) must be a multiple of 32")
+    _check(scales.numel() >= m * (n // 32), f"{name}: scales must hold at least {m} x {n // 32} bytes")
+    _check(x_fp8.numel() == n * m_pad and x_fp8.element_size() == 1, f"{name}: x_fp8 must hold {n} x {m_pad} bytes")
+    _check(shared_exps.numel() == n * m_pad // 32, f"{name}: shared_exps must hold {n} x {m_pad // 32} bytes")
+    with _DeviceGuard(x_fp4.device):
+        _lib.check(_lib.load().b200q_mxfp4_transpose_mxfp8(
+            x_fp4.data_ptr(), scales.data_ptr(), m, n, x_fp8.data_ptr(), shared_exps.data_ptr(), _stream(x_fp4)))
+
+
+def mxfp4_transpose_mxfp8(x_fp4: torch.Tensor, scales: torch.Tensor):
+    """MXFP4 [m, n/2] + e8m0 scales [>= m, n/32] -> MXFP8 of the transpose: (e4m3 [n, m_pad], e8m0 [n, m_pad/32]),
+    m_pad = m rounded up to 256 (reference: qutlass/__init__.py:296-309, quartet_bwd_sm120.cu:625-734; pinned by
+    tests/quartet_test.py:294-345,380-385).  The reference pads x_fp4 with a host-side copy and overwrites the pad rows
+    of ``scales`` with 1.0; here the kernel reads rows >= m as zero and leaves ``scales`` untouched."""
+    _check(x_fp4.dim() == 2, "mxfp4_transpose_mxfp8: x_fp4 must be 2-D")
+    m, n = x_fp4.size(0), x_fp4.size(1) * 2
+    m_pad = (m + 255) // 256 * 256
+    x_fp8 = torch.empty(n, m_pad, dtype=torch.float8_e4m3fn, device=x_fp4.device)
+    shared_exps = torch.empty(n, m_pad // 32, dtype=torch.float8_e8m0fnu, device=x_fp4.device)
+    _mxfp4_transpose_mxfp8_into(x_fp4, scales, x_fp8, shared_exps, m)
+    return x_fp8, shared_exps
 
 
 # --------------------------------------------------------------------------------------- torch.ops._qutlass_C
@@ -383,6 +527,10 @@ def _register_ops() -> None:
         "fusedQuantizeNvQuest": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf, Tensor global_scale) -> (Tensor, Tensor)",
         "fusedQuantizeNvAbsMax": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf, Tensor global_scale) -> (Tensor, Tensor)",
         "fusedQuantizeMxQuestWithMask": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf, Tensor OUT_mask) -> (Tensor, Tensor, Tensor)",
+        "backward_t_bf16": "(Tensor x, Tensor h, Tensor xh_e2m1, Tensor xh_e8m0) -> ()",
+        "backward_qt_bf16": "(Tensor x_e2m1, Tensor x_e8m0, Tensor h, Tensor alpha, Tensor xh_e2m1, Tensor xh_e8m0) -> ()",
+        "backward_bf16_square_double_mxfp8": "(Tensor x_bf16, Tensor x_fp8, Tensor row_scales, Tensor column_scales) -> ()",
+        "mxfp4_transpose_mxfp8": "(Tensor x_fp4, Tensor scales, Tensor x_fp8, Tensor shared_exps) -> ()",
     }
     impls = {
         "matmul_mxf4_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_mxf4_bf16_tn(A, B, A_sf, B_sf, alpha),
@@ -394,6 +542,11 @@ def _register_ops() -> None:
         "fusedQuantizeNvQuest": lambda A, R, OUT, OUT_sf, gs: (_quantize_nv_into(A, R, OUT, OUT_sf, None, gs, METHOD_QUEST), (OUT, OUT_sf))[1],
         "fusedQuantizeNvAbsMax": lambda A, R, OUT, OUT_sf, gs: (_quantize_nv_into(A, R, OUT, OUT_sf, None, gs, METHOD_ABSMAX), (OUT, OUT_sf))[1],
         "fusedQuantizeMxQuestWithMask": lambda A, R, OUT, OUT_sf, OUT_mask: (_quantize_mx_into(A, R, OUT, OUT_sf, None, OUT_mask, METHOD_QUEST), (OUT, OUT_sf, OUT_mask))[1],
+        "backward_t_bf16": lambda x, h, xh_e2m1, xh_e8m0: _backward_t_bf16_into(x, h, xh_e2m1, xh_e8m0),
+        "backward_qt_bf16": lambda x_e2m1, x_e8m0, h, alpha, xh_e2m1, xh_e8m0: _backward_qt_bf16_into(x_e2m1, x_e8m0, h, alpha, xh_e2m1, xh_e8m0),
+        "backward_bf16_square_double_mxfp8": lambda x_bf16, x_fp8, row_scales, column_scales: _square_double_into(x_bf16, x_fp8, row_scales, column_scales),
+        # like the reference binding (bindings.cpp:466-479) the raw op takes x_fp4 already padded to 256 rows
+        "mxfp4_transpose_mxfp8": lambda x_fp4, scales, x_fp8, shared_exps: _mxfp4_transpose_mxfp8_into(x_fp4, scales, x_fp8, shared_exps, x_fp4.size(0)),
     }
     for name, schema in defs.items():
         try:

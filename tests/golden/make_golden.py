@@ -13,7 +13,10 @@ copied into this repo):
     (torch path, lines 136-193)
   * /root/reference/tests/mxfp8_test.py : _pseudoquant_mxfp8 (lines 27-46, decorator stripped)
 
-Usage:  python tests/golden/make_golden.py
+  * /root/reference/tests/quartet_test.py : _backward_quantize_ref, _backward_bf16_square_double_mxfp8,
+    _mxfp4_transpose_mxfp8 (+ its _rtne_fp4 / _dq_fp4) and qutlass/utils.py pad_to_block  -> backward_vectors.npz
+
+Usage:  python tests/golden/make_golden.py [forward|backward|all]
 """
 import ast
 import os
@@ -27,10 +30,11 @@ REF = os.environ.get("QUTLASS_REFERENCE", "/root/reference")
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
-def lift(path, names):
+def lift(path, names, extra=None):
     src = open(path).read()
     tree = ast.parse(src)
     ns = {"torch": torch, "np": np, "hadamard": hadamard}
+    ns.update(extra or {})
     for node in tree.body:
         if isinstance(node, ast.FunctionDef) and node.name in names:
             node.decorator_list = []      # e.g. @torch.compile on _pseudoquant_mxfp8: run it eagerly
@@ -172,5 +176,79 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
 
 
+def main_backward():
+    """Golden vectors of the backward re-quantisers from the reference's own test oracles (tests/quartet_test.py)."""
+    ut = lift(f"{REF}/qutlass/utils.py", ["pad_to_block"])
+    qt = lift(f"{REF}/tests/quartet_test.py",
+              ["get_hadamard_matrix", "_rtne_fp4", "_dq_fp4", "_backward_quantize_ref",
+               "_backward_bf16_square_double_mxfp8", "_mxfp4_transpose_mxfp8"], extra={"pad_to_block": ut["pad_to_block"]})
+    dev = torch.device("cpu")
+    out = {}
+    H = qt["get_hadamard_matrix"](32, torch.bfloat16, dev)
+    out["had32_bits"] = bits(H)
+
+    # ---- backward_t_bf16: x [B, N, M] -> quantise x^T along N (tests/quartet_test.py:220-226)
+    torch.manual_seed(3)
+    x = torch.randn(2, 64, 96, dtype=torch.bfloat16) * 25.0
+    x[0, :32, 5] = 0            # an all-zero group of the transposed matrix
+    x[1, 32:, 7] = 0
+    x[1, 40, 7] = 1.0           # single spike: amax exactly a power of two
+    xh_dq, (e2m1, e8m0) = qt["_backward_quantize_ref"](x.transpose(-2, -1), H)
+    out["t_x_bits"] = bits(x)
+    out["t_e2m1"] = e2m1.numpy()
+    out["t_e8m0"] = u8(e8m0)
+    out["t_dq"] = xh_dq.numpy()
+
+    # ---- backward_qt_bf16: MXFP4 input (abs_max forward quantisation emulated by the same oracle), alpha = 3
+    #      (tests/quartet_test.py:228-239)
+    _, (xq, xs) = qt["_backward_quantize_ref"](x, H)           # [2, 64, 48] bytes, [2, 64, 3] scales
+    x_dq = qt["_dq_fp4"](xq, xs, alpha=3.0)[0]
+    xh_dq, (e2m1, e8m0) = qt["_backward_quantize_ref"](x_dq.transpose(-2, -1), H)
+    out["qt_in_e2m1"] = xq.numpy()
+    out["qt_in_e8m0"] = u8(xs)
+    out["qt_e2m1"] = e2m1.numpy()
+    out["qt_e8m0"] = u8(e8m0)
+    out["qt_dq"] = xh_dq.numpy()
+
+    # ---- backward_bf16_square_double_mxfp8 (tests/quartet_test.py:264-291,369-378); every non-zero tile has amax >= 1
+    torch.manual_seed(4)
+    xs_ = torch.randn(200, 128, dtype=torch.bfloat16) * 25.0
+    xs_[32:64, 32:64] = 0
+    xs_[64:96, 0:32] = 1.0
+    x_fp8, row_s, col_s = qt["_backward_bf16_square_double_mxfp8"](xs_)
+    out["sq_x_bits"] = bits(xs_)
+    out["sq_fp8"] = u8(x_fp8)
+    out["sq_row"] = u8(row_s)
+    out["sq_col"] = u8(col_s)
+    # the reference test's own input: arange(0, 256) repeated over 2694 rows (only the first 256 rows + pad kept small)
+    xa = torch.arange(0, 256, dtype=torch.bfloat16)[None, :].repeat(130, 1)
+    x_fp8, row_s, col_s = qt["_backward_bf16_square_double_mxfp8"](xa)
+    out["sqa_fp8"] = u8(x_fp8)
+    out["sqa_row"] = u8(row_s)
+    out["sqa_col"] = u8(col_s)
+
+    # ---- mxfp4_transpose_mxfp8 (tests/quartet_test.py:294-345,380-385): m = 200 -> padded to 256, n = 128
+    g = torch.Generator().manual_seed(5)
+    m, n = 200, 128
+    fp4 = torch.randint(0, 256, (m, n // 2), dtype=torch.uint8, generator=g)
+    fp4[10:42, 3] = 0                                  # an all-zero column pair over one 32-row group? (rows 10..41 straddle)
+    fp4[32:64, 8] = 0                                  # exactly one group of two output rows
+    sc = torch.randint(120, 134, (256, n // 32), dtype=torch.uint8, generator=g)
+    sc[m:] = 127                                       # the reference wrapper sets the pad rows' scales to 1.0
+    xq8, exps = qt["_mxfp4_transpose_mxfp8"](fp4, sc)
+    out["tr_fp4"] = fp4.numpy()
+    out["tr_scales"] = sc.numpy()
+    out["tr_fp8"] = u8(xq8)
+    out["tr_exps"] = u8(exps)
+
+    path = os.path.join(OUT, "backward_vectors.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("forward", "all"):
+        main()
+    if what in ("backward", "all"):
+        main_backward()
