@@ -317,15 +317,19 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const uint32_t sb = smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
         const uint32_t ssfb = sb + Cfg::B_BYTES + Cfg::SFA_BYTES;
         const uint32_t fb = full0 + 8u * stage;
-        if (is_leader) mbar_arrive_expect_tx(bar_base + 8u * stage, Cfg::TX_BYTES);
-        tma_load_2d<kCtaGroup>(sb, &tmap_b, fb, kt * BK_BYTES, nb0);
+        // profiling flags (timing only, wrong results): 1 << 20 skips the B tile loads, 1 << 21 the A tile loads
+        const uint32_t tx = Cfg::TX_BYTES - ((p.flags & (1 << 20)) ? (uint32_t)Cfg::B_BYTES * kCtaGroup : 0u) -
+                            ((p.flags & (1 << 21)) ? (uint32_t)Cfg::A_BYTES * kCtaGroup : 0u);
+        if (is_leader) mbar_arrive_expect_tx(bar_base + 8u * stage, tx);
+        if (!(p.flags & (1 << 20))) tma_load_2d<kCtaGroup>(sb, &tmap_b, fb, kt * BK_BYTES, nb0);
         tma_load_3d<kCtaGroup>(ssfb, &tmap_sfb, fb, 0, kt * SFKB, n0 / 128);
       };
       auto load_acts = [&](int stage, int m0, int kt) {
         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
         const uint32_t ssfa = sa + Cfg::A_BYTES + Cfg::B_BYTES;
         const uint32_t fb = full0 + 8u * stage;
-        if constexpr (kF8 == 2) tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, m0, kt * Cfg::BK_ELEMS);   // A [K, M]: box = 128 K-rows x 128 M-bytes
+        if (p.flags & (1 << 21)) {}
+        else if constexpr (kF8 == 2) tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, m0, kt * Cfg::BK_ELEMS);   // A [K, M]: box = 128 K-rows x 128 M-bytes
         else tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, kt * BK_BYTES, m0);
         tma_load_3d<kCtaGroup>(ssfa, &tmap_sfa, fb, 0, kt * SFKB, m0 / 128);
       };
@@ -703,6 +707,24 @@ static int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void*
     return B200Q_ECUDA;
   }
   return 0;
+}
+
+// bf16 [rows, 128] view of a flat activation tensor, box = [128 rows, 64 elements], 128B swizzle (quantize_tc.cu)
+int make_x128_tmap(void* tm, const void* ptr, int64_t rows) {
+  cuuint64_t dims[2] = {128, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {256};
+  cuuint32_t box[2] = {64, 128};
+  return encode((CUtensorMap*)tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "x[rows,128]");
+}
+
+// bf16 rotation matrix [H, H] (row k, column n contiguous), box = [min(H, 64) columns, H rows], swizzle span = box row
+int make_rot_tmap(void* tm, const void* ptr, int had) {
+  const int bw = had < 64 ? had : 64;
+  cuuint64_t dims[2] = {(cuuint64_t)had, (cuuint64_t)had};
+  cuuint64_t strides[1] = {(cuuint64_t)had * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)had};
+  const CUtensorMapSwizzle sw = bw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  return encode((CUtensorMap*)tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, sw, "rotation[H,H]");
 }
 
 // [rows, row_bytes] uint8 operand, box = [box_rows, 128 bytes], 128B swizzle, zero fill out of bounds

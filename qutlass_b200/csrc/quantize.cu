@@ -501,8 +501,28 @@ static bool use_butterfly() {
   return !(e && e[0] == '1');
 }
 
+// tcgen05 rotation kernel (quantize_tc.cu): streams at the HBM rate for any runtime R, but pays ~1.7 us more fixed
+// latency (TMA -> MMA -> TMEM -> epilogue pipeline fill) than the butterfly kernel, whose cost grows with H instead.
+// Measured crossover on B200 (profiles/r01_quant_tc.md): H >= 64 from 256 tiles of 32 KB (8 M elements), H = 32 from
+// 1024 tiles; H = 16 never.  Rotations the caller declared non-Hadamard take it from 32 tiles (the alternative there
+// is the mma.sync kernel).  B200Q_QUANT_TC=0 / 1 forces it off / on (when eligible).
+static bool use_tc(const QuantParams& p, int had, bool nv) {
+  if (!quantize_tc_eligible(p, had, nv)) return false;
+  const char* m = getenv("B200Q_QUANT_MMA");
+  if (m && m[0] == '1') return false;
+  const char* e = getenv("B200Q_QUANT_TC");
+  if (e && e[0] == '0') return false;
+  if (e && e[0] == '1') return true;
+  const int64_t tiles = p.n_chunks / 512;
+  if (g_rot_generic) return tiles >= 32;
+  if (had >= 64) return tiles >= 256;
+  if (had == 32) return tiles >= 1024;
+  return false;
+}
+
 template <bool NV, int METHOD, bool MASK>
 static int dispatch_had(int had, const QuantParams& p, cudaStream_t stream) {
+  if (use_tc(p, had, NV)) return launch_quantize_tc(p, had, NV, METHOD, stream);
   switch (had) {
     case 16:
       if constexpr (NV) return launch<16, NV, METHOD, MASK>(p, stream);

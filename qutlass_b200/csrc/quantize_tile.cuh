@@ -132,15 +132,13 @@ __device__ __forceinline__ void tile_rotate_hadamard(float* v, float c_scale) {
   for (int i = 0; i < 16; ++i) B200Q_UNPK(v, i, __fmul2_rn(B200Q_PK(v, i), c2));
 }
 
-// Per-group scale, e2m1 conversion and all stores (codes, row-major and blocked scales, clip mask) of lane L's chunk.
+// Per-group scale and e2m1 conversion of ONE rotated 32-element chunk held in v[0..31] (scaled in place): 32 codes in
+// out[0..3], the scale byte(s) in sf_bytes (MX: 1 byte, NV: 2 bytes little-endian), the clip mask word.
 template <bool NV, int METHOD, bool MASK>
-__device__ __forceinline__ void tile_quantise_store(const QuantParams& p, float* v, int64_t tile, int lane, float gs,
-                                                    float gs_rcp) {
-    // ---- quantise
-    const int64_t chunk = tile * 32 + lane;
-    uint32_t out[4];
-    uint32_t mask_word = 0;
-    uint32_t sf_bytes = 0;  // MX: 1 byte, NV: 2 bytes (little-endian)
+__device__ __forceinline__ void chunk_quantise(float* v, float gs, float gs_rcp, uint32_t (&out)[4], uint32_t& sf_bytes,
+                                               uint32_t& mask_word) {
+    mask_word = 0;
+    sf_bytes = 0;
     if constexpr (!NV) {
       float scale;
       if constexpr (METHOD == B200Q_METHOD_QUEST) {
@@ -216,8 +214,14 @@ __device__ __forceinline__ void tile_quantise_store(const QuantParams& p, float*
 #pragma unroll
       for (int i = 0; i < 32; ++i) mask_word |= (fabsf(v[i]) < 6.f) ? (1u << i) : 0u;
     }
+}
 
-    // ---- stores
+// chunk_quantise + all stores (codes, row-major and blocked scales, clip mask) of one chunk (= flat element index / 32).
+template <bool NV, int METHOD, bool MASK>
+__device__ __forceinline__ void chunk_quantise_store(const QuantParams& p, float* v, int64_t chunk, float gs, float gs_rcp) {
+    uint32_t out[4];
+    uint32_t mask_word, sf_bytes;
+    chunk_quantise<NV, METHOD, MASK>(v, gs, gs_rcp, out, sf_bytes, mask_word);
     if (chunk < p.n_chunks) {
       p.q[chunk] = make_uint4(out[0], out[1], out[2], out[3]);
       if constexpr (MASK) {
@@ -238,6 +242,13 @@ __device__ __forceinline__ void tile_quantise_store(const QuantParams& p, float*
         }
       }
     }
+}
+
+// lane L of a warp-tile owns chunk tile * 32 + L
+template <bool NV, int METHOD, bool MASK>
+__device__ __forceinline__ void tile_quantise_store(const QuantParams& p, float* v, int64_t tile, int lane, float gs,
+                                                    float gs_rcp) {
+  chunk_quantise_store<NV, METHOD, MASK>(p, v, tile * 32 + lane, gs, gs_rcp);
 }
 
 // Zero the padding of the blocked scale buffer (rows >= rows, cols >= cols) so the buffer is written completely;
@@ -261,5 +272,9 @@ __device__ __forceinline__ void zero_fill_sf_padding(const QuantParams& p, int64
 // host side (quantize.cu): argument checks + the launch-independent fields of QuantParams
 int fill_params(QuantParams& p, const void* x, const void* rot, void* q, void* sf_rm, void* sf_blk, int64_t numel,
                 int64_t row_len, int had, int group);
+
+// tensor-core (tcgen05) rotation kernel, quantize_tc.cu: any runtime rotation, numel % 128 == 0
+bool quantize_tc_eligible(const QuantParams& p, int had, bool nv);
+int launch_quantize_tc(const QuantParams& p, int had, bool nv, int method, cudaStream_t stream);
 
 }  // namespace b200q

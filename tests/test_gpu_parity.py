@@ -196,6 +196,68 @@ def test_quantize_arbitrary_rotation_on_tensor_cores(kind, had):
     assert (dq != dq_ref).mean() <= (1e-3 if kind == "mx" else 1e-2)
 
 
+@pytest.mark.parametrize("kind,had", [("mx", 32), ("mx", 64), ("mx", 128), ("nv", 16), ("nv", 32), ("nv", 64), ("nv", 128)])
+@pytest.mark.parametrize("method", ["abs_max", "quest"])
+@pytest.mark.parametrize("shape", [(384, 2048), (132, 160), (1000, 4096)])
+def test_quantize_tcgen05_kernel_vs_oracle(kind, had, method, shape, monkeypatch):
+    """The tcgen05 rotation kernel (quantize_tc.cu; default for large inputs, forced here with B200Q_QUANT_TC=1) against
+    the oracle: codes, row-major scales, the blocked copy and the clip mask.  (132, 160): 5 / 10 scales per row, so a
+    128-element row of the kernel's flat view straddles matrix rows (byte-granular blocked stores) and the last tile
+    is partial; (1000, 4096): 8 tiles per CTA-round with a ragged row count."""
+    monkeypatch.setenv("B200Q_QUANT_TC", "1")
+    rows, k = shape
+    if (rows * k) % had:
+        pytest.skip("numel % H")
+    x = H.random_bf16((rows, k), seed=had + rows)
+    R = O.hadamard_matrix(had)
+    xt, Rt = H.bf16_tensor_from_f32(x), H.bf16_tensor_from_f32(R)
+    if kind == "mx":
+        group, tol_sf, tol = 32, 1e-4, 1e-4
+        ref = O.quantize_mx(x, R, method)
+        out = Q.fusedQuantizeMx(xt, Rt, method=method, return_mask=(method == "quest"))
+        deq = O.dequant_mx
+    else:
+        group, tol_sf, tol = 16, 1e-3, 1e-2
+        ref = O.quantize_nv(x, R, 6.0, method)
+        out = Q.fusedQuantizeNv(xt, Rt, torch.tensor([6.0], device="cuda"), method=method)
+        deq = O.dequant_nv
+    torch.cuda.synchronize()
+    cols = k // group
+    sf = _flat_sf(out[1], rows, cols)
+    assert (sf != ref["sf"].reshape(rows, cols)).mean() <= tol_sf
+    dq = deq(H.u8_of(out[0]), sf)
+    assert (dq != deq(ref["q"].reshape(rows, -1), ref["sf"].reshape(rows, cols))).mean() <= tol
+    if kind == "mx" and method == "quest":
+        assert (H.u8_of(out[2]).reshape(-1).view(np.uint32) != ref["mask"]).mean() <= 1e-4
+    np.testing.assert_array_equal(H.u8_of(Q.to_blocked(out[1])), H.blocked_sf(sf))
+
+
+def test_quantize_tcgen05_kernel_is_the_large_input_default_and_matches_the_butterfly_kernel(monkeypatch):
+    """4096 x 4096, Hadamard-128 (bench.py's activation tensor) dispatches to the tcgen05 kernel; forcing the butterfly
+    kernel gives the same bytes up to summation-order rounding (<= 1e-5 of the codes), any non-symmetric runtime rotation
+    agrees with the oracle (the rotation is an MN-major tensor-core operand: a transposed R would show here)."""
+    x = torch.randn(4096, 4096, dtype=torch.bfloat16, device="cuda", generator=torch.Generator("cuda").manual_seed(3)) * 25
+    Rt = H.bf16_tensor_from_f32(O.hadamard_matrix(128))
+    q1, sf1 = Q.fusedQuantizeMx(x, Rt, method="abs_max")
+    b1 = Q.to_blocked(sf1).clone()
+    monkeypatch.setenv("B200Q_QUANT_TC", "0")
+    q0, sf0 = Q.fusedQuantizeMx(x, Rt, method="abs_max")
+    b0 = Q.to_blocked(sf0)
+    torch.cuda.synchronize()
+    assert (q0 != q1).float().mean().item() <= 1e-5
+    assert (sf0.view(torch.uint8) != sf1.view(torch.uint8)).float().mean().item() <= 1e-5
+    assert (b0.view(torch.uint8) != b1.view(torch.uint8)).float().mean().item() <= 1e-5
+    monkeypatch.setenv("B200Q_QUANT_TC", "1")
+    for had in (32, 64, 128):
+        xs = H.random_bf16((256, 1024), seed=had)
+        R = O.bf16_round(np.random.default_rng(had).standard_normal((had, had)).astype(np.float32) * had ** -0.5)
+        ref = O.quantize_mx(xs, R, "quest")
+        q, sf = Q.fusedQuantizeMx(H.bf16_tensor_from_f32(xs), H.bf16_tensor_from_f32(R), method="quest")
+        torch.cuda.synchronize()
+        dq = O.dequant_mx(H.u8_of(q), _flat_sf(sf, 256, 32))
+        assert (dq != O.dequant_mx(ref["q"].reshape(256, -1), ref["sf"].reshape(256, -1))).mean() <= 1e-3
+
+
 def test_error_behaviour():
     R = torch.eye(32, dtype=torch.bfloat16, device="cuda")
     x = torch.zeros(4, 64, dtype=torch.bfloat16, device="cuda")
@@ -223,7 +285,9 @@ def test_error_behaviour():
     with pytest.raises(ImportError):
         Q.matmul_mxf4_bf16_tn(a, a, sf, sf, al, backend="flashinfer")
     with pytest.raises(NotImplementedError):
-        Q.backward_t_bf16(a, a)
+        Q.matmul_ada_mxf4_bf16_tn(a, a, sf, sf, al)     # sm_120-only prototype: errors on sm_100 in the reference too
+    with pytest.raises(AssertionError):
+        Q.backward_t_bf16(a, a)                         # uint8 input: the reference asserts the dtypes (__init__.py:226)
     with pytest.raises(RuntimeError, match="A must be float8_e4m3fn"):
         Q.matmul_mxf8_bf16_nn(a, a, sf, sf, al)
     with pytest.raises(RuntimeError, match="A must be float8_e4m3fn"):

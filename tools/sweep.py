@@ -81,6 +81,10 @@ if __name__ == "__main__":
         F = lambda base, n: base | (n << 12)
         gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 256)], [(0, 2), (F(256, 4), 2), (F(256, 10), 2), (F(512, 6), 2), (F(512, 14), 2), (F(768, 6), 2)])
         gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 192)], [(0, 2), (F(512, 6), 2), (F(768, 6), 2)])
+    if "gemml2" in which:
+        # is the mainloop bound by operand traffic (L2 -> SM / shared-memory writes)?  1 = no D stores, 1<<20 = no B loads, 1<<21 = no A loads
+        B_, A_ = 1 << 20, 1 << 21
+        gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 256), (2, 192), (1, 256)], [(0, 2), (1, 2), (B_, 2), (B_ | 1, 2), (A_, 2), (A_ | 1, 2), (A_ | B_ | 1, 2)])
     if "gemmq" in which:
         gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (1, 2), (4, 2)])
         gemm_sweep("nv", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (4, 2)])
