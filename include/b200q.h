@@ -42,7 +42,9 @@ typedef struct CUstream_st* b200q_stream_t;
  * and falls back to a generic x @ R for any other matrix. */
 #define B200Q_ROT_TRUSTED_HADAMARD 0x100
 /* OR into `method`: the caller knows rot is NOT of that form (e.g. identity, a learned rotation): the rotation then
- * runs on the tensor-core (mma.sync) kernel for had >= 32 instead of the butterfly kernel's scalar fallback. */
+ * runs on the tensor cores (tcgen05 kernel from 1 M elements, mma.sync kernel below that, had >= 32) instead of the
+ * butterfly kernel's scalar fallback.  Large Hadamard inputs take the tcgen05 kernel too (it streams at the HBM rate
+ * for any R); the choice never changes the results beyond fp32 summation order. */
 #define B200Q_ROT_GENERIC 0x200
 
 #define B200Q_KIND_MXF4 0      /* e2m1 x e2m1, ue8m0 scales, group 32          */
@@ -120,7 +122,8 @@ int b200q_gemm_fp4(const void* A, const void* B, const void* SFA, const void* SF
 
 /*
  * Same, with an explicit kernel configuration (tuning / tests):
- *   cta_group 1|2, block_n in {64,128,256} (0 = heuristic for both).
+ *   cta_group 1|2, block_n in {64,128,192,256} (0 = heuristic for both); cta_group 4 with block_n 192|256 = CTA pairs in
+ *   clusters of four whose two pairs multicast their A tiles to each other (experiment: bit-identical, not faster).
  */
 int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA, const void* SFB,
                        const float* alpha_dev, void* D_bf16, int M, int N, int K, int kind,

@@ -215,13 +215,18 @@ __device__ __forceinline__ void quantiser_role(const FuseParams& fp, uint4* stag
 #undef B200Q_QCASE
 }
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS, int kF8, int kFuse>
+// kMC (CTA pairs only): clusters of FOUR CTAs = two pairs working on N-adjacent output tiles of the same 256 rows.  The
+// pairs share their A tiles: every CTA loads 64 of its 128 A rows and multicasts them to its counterpart in the other
+// pair (rank ^ 2), which halves the A traffic over the L2 -> SM crossbar.  A stage may be refilled only when BOTH pairs'
+// MMAs have read it (the stage-empty barriers collect one tcgen05.commit from each pair leader).
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS, int kF8, int kFuse, int kMC = 0>
 __global__ void __launch_bounds__(kGemmThreads + 32 * kFuse, 1)
 gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb,
                 const __grid_constant__ CUtensorMap tmap_d, const GemmParams p, const FuseParams fp) {
   static_assert(kFuse == 0 || ((kFuse == 2 || kFuse == 4) && kCtaGroup == 2 && A_ROWS == 128 && !kF8),
                 "fused quantise+GEMM: CTA pairs, FP4 only, 2 or 4 quantiser warps");
+  static_assert(kMC == 0 || (kCtaGroup == 2 && A_ROWS == 128 && kF8 != 2 && kFuse == 0), "multicast clusters: plain CTA-pair GEMM only");
   using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ACC = Cfg::ACC_STAGES;
@@ -244,12 +249,23 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+  const uint32_t crank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;   // 0..1, kMC: 0..3
+  const uint32_t cta_rank = crank & 1u;                                  // rank inside the CTA pair
+  const uint32_t pair = kMC ? (crank >> 1) : 0u;                         // which pair of the cluster
+  const uint32_t leader_rank = crank & ~1u;                              // cluster rank of this pair's leader
   const bool is_leader = cta_rank == 0;
-  const int cluster_id = blockIdx.x / kCtaGroup;
-  const int num_clusters = gridDim.x / kCtaGroup;
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  constexpr int kClusterCtas = kCtaGroup * (kMC ? 2 : 1);
+  const int cluster_id = blockIdx.x / kClusterCtas;
+  const int num_clusters = gridDim.x / kClusterCtas;
   const bool nfast = (p.flags & 2048) != 0;   // tile walk: M-fastest (B tiles shared by concurrent clusters); profiling flag 2048: N-fastest
+  // kMC: a cluster tile is two N-adjacent tiles (one per pair); an odd tile count leaves the second pair an empty tile
+  const int tiles_n_eff = kMC ? (p.tiles_n + 1) / 2 : p.tiles_n;
+  const int total_tiles = p.tiles_m * tiles_n_eff;
+  auto tile_mn = [&](int tile, int& tm, int& tn) {
+    tm = nfast ? tile / tiles_n_eff : tile % p.tiles_m;
+    const int t = nfast ? tile - tm * tiles_n_eff : tile / p.tiles_m;
+    tn = kMC ? t * 2 + (int)pair : t;
+  };
 
   // a dependent grid (e.g. the tail GEMM of a split launch) may start its prologue / weight loads while this one runs
   pdl_launch_dependents();
@@ -263,7 +279,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     prefetch_tensormap(&tmap_d);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);     // one arrive.expect_tx by the leader's producer; bytes from both CTAs
-      mbar_init(empty_bar(s), 1);    // one tcgen05.commit (multicast to both CTAs)
+      mbar_init(empty_bar(s), kMC ? 2 : 1);    // one tcgen05.commit (multicast to both CTAs) per pair of the cluster
     }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -291,7 +307,8 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     {
       const bool elected = elect_one();
       // completion goes to the leader's barrier (own barrier when kCtaGroup == 1)
-      const uint32_t full0 = (kCtaGroup == 2) ? mapa(bar_base, 0) : bar_base;
+      const uint32_t full0 = (kCtaGroup == 2) ? mapa(bar_base, leader_rank) : bar_base;
+      const uint16_t mc_mask = (uint16_t)((1u << crank) | (1u << (crank ^ 2u)));
       int my_tiles = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) ++my_tiles;
       const int total_kt = my_tiles * p.k_tiles;
@@ -303,8 +320,8 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       struct Cursor { int tile, kt, m0, n0, nb0, tm; };
       auto set_tile = [&](Cursor& c) {
         // fused: N-fastest (the first wave touches only the first row blocks of A); otherwise M-fastest
-        const int tm = nfast ? c.tile / p.tiles_n : c.tile % p.tiles_m;
-        const int tn = nfast ? c.tile - tm * p.tiles_n : c.tile / p.tiles_m;
+        int tm, tn;
+        tile_mn(c.tile, tm, tn);
         c.tm = tm;
         c.m0 = (tm * kCtaGroup + (int)cta_rank) * BM;            // this CTA's A rows
         c.n0 = tn * BN;
@@ -329,6 +346,8 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const uint32_t ssfa = sa + Cfg::A_BYTES + Cfg::B_BYTES;
         const uint32_t fb = full0 + 8u * stage;
         if (p.flags & (1 << 21)) {}
+        else if constexpr (kMC != 0)      // my 64 rows of the A tile, to me and to my counterpart in the other pair
+          tma_load_2d_multicast<2>(sa + pair * (64 * BK_BYTES), &tmap_a, fb, kt * BK_BYTES, m0 + (int)pair * 64, mc_mask);
         else if constexpr (kF8 == 2) tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, m0, kt * Cfg::BK_ELEMS);   // A [K, M]: box = 128 K-rows x 128 M-bytes
         else tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, kt * BK_BYTES, m0);
         tma_load_3d<kCtaGroup>(ssfa, &tmap_sfa, fb, 0, kt * SFKB, m0 / 128);
@@ -403,7 +422,8 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int tn = nfast ? tile % p.tiles_n : tile / p.tiles_m;
+        int tm_, tn;
+        tile_mn(tile, tm_, tn);
         const int n0 = tn * BN;
         const uint32_t sfb_shift = (uint32_t)((n0 % 128) / 32);     // 0 or 2 columns into the first SFB block
         mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2);
@@ -448,8 +468,9 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                                    tsfb + chunk * (4 * NB), (kt > 0 || kb > 0) ? 1u : 0u);
             }
           }
-          tc_commit<kCtaGroup>(bar_base + 8u * (STAGES + stage));              // stage free once these MMAs have read it
-          if (kt == p.k_tiles - 1) tc_commit<kCtaGroup>(tfull_bar(acc));   // accumulator complete
+          // stage free once these MMAs have read it (kMC: tell all four CTAs -- the other pair multicasts into our stages)
+          tc_commit<kCtaGroup>(bar_base + 8u * (STAGES + stage), kMC ? (uint16_t)0xF : (uint16_t)3);
+          if (kt == p.k_tiles - 1) tc_commit<kCtaGroup>(tfull_bar(acc), (uint16_t)(3u << leader_rank));   // accumulator complete
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -476,7 +497,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const uint32_t stg = stg_base + ew * Cfg::STG_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t tempty_leader = (kCtaGroup == 2) ? mapa(tempty_bar(0), 0) : tempty_bar(0);
+    const uint32_t tempty_leader = (kCtaGroup == 2) ? mapa(tempty_bar(0), leader_rank) : tempty_bar(0);
     pdl_wait();   // D must not be written before the predecessor kernel has finished (it may still read that memory)
     const float alpha = __ldg(p.alpha);
     if constexpr (kFuse != 0) {
@@ -488,8 +509,8 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                   tfull_bar(0));
     }
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const int tm = nfast ? tile / p.tiles_n : tile % p.tiles_m;
-      const int tn = nfast ? tile - tm * p.tiles_n : tile / p.tiles_m;
+      int tm, tn;
+      tile_mn(tile, tm, tn);
       const int m0 = (tm * kCtaGroup + (int)cta_rank) * BM;
       const int n0 = tn * BN;
       mbar_wait(tfull_bar(acc), acc_phase, 6);
@@ -755,11 +776,12 @@ static int make_d_tmap(CUtensorMap* tm, const void* ptr, int64_t M, int64_t N, i
                 chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "D");
 }
 
-template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, int kF8 = 0, int kFuse = 0>
+template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, int kF8 = 0, int kFuse = 0, int kMC = 0>
 static int launch_gemm(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D,
                        int M, int N, int K, int ldd, cudaStream_t stream, const FuseParams* fuse = nullptr) {
   using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
-  auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
+  auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse, kMC>;
+  constexpr int kClusterCtas = kCtaGroup * (kMC ? 2 : 1);
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -773,7 +795,7 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   if constexpr (kF8 == 2) {
     if ((rc = make_operand_tmap(&ta, A, K, M, 128, "A[K,M]"))) return rc;      // rows = K, row pitch = M bytes, box 128 x 128
   } else {
-    if ((rc = make_operand_tmap(&ta, A, M, row_bytes, A_ROWS, "A"))) return rc;
+    if ((rc = make_operand_tmap(&ta, A, M, row_bytes, kMC ? 64 : A_ROWS, "A"))) return rc;   // kMC: half tiles, multicast
   }
   if ((rc = make_operand_tmap(&tb, B, N, row_bytes, Cfg::B_ROWS, "B"))) return rc;
   if ((rc = make_sf_tmap(&tsa, SFA, ceil_div(M, 128), sf_col_blocks, Cfg::SFKB, 1, "SFA"))) return rc;
@@ -798,19 +820,32 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   } else {
     td = ta;  // unused
   }
-  const int total = p.tiles_m * p.tiles_n;
-  int clusters = num_sms() / kCtaGroup;
-  if (clusters > total) clusters = total;
+  const int total = p.tiles_m * (kMC ? (p.tiles_n + 1) / 2 : p.tiles_n);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * kCtaGroup));
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = kCtaGroup;
+  attrs[0].val.clusterDim.x = kClusterCtas;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
+  int clusters = num_sms() / kClusterCtas;
+  if constexpr (kMC != 0) {
+    // clusters of 4 must sit inside one GPC: ask how many are co-resident (a persistent grid must not exceed that)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cfg.gridDim = dim3((unsigned)(clusters * kClusterCtas));
+      cfg.attrs = attrs;
+      cfg.numAttrs = 1;
+      int n = 0;
+      B200Q_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      max_clusters = n > 0 ? n : 1;
+    }
+    if (clusters > max_clusters) clusters = max_clusters;
+  }
+  if (clusters > total) clusters = total;
+  cfg.gridDim = dim3((unsigned)(clusters * kClusterCtas));
   // programmatic dependent launch: this grid may start while the previous kernel in the stream drains; everything that
   // depends on that kernel sits behind griddepcontrol.wait inside (B200Q_NO_PDL=1 disables the attribute)
   attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -842,6 +877,11 @@ static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B
   B200Q_CASE(2, 128)
   B200Q_CASE(2, 192)
   B200Q_CASE(2, 256)
+  if constexpr (kF8 == 0) {
+    // cta_group 4 = CTA pairs in clusters of four, A tiles multicast between the two pairs
+    if (cta_group == 4 && block_n == 256) return launch_gemm<2, 256, kNV, 128, 0, 0, 1>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+    if (cta_group == 4 && block_n == 192) return launch_gemm<2, 192, kNV, 128, 0, 0, 1>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+  }
   if constexpr (kF8 == 0) {
     B200Q_CASE(1, 64)
     B200Q_CASE(1, 192)

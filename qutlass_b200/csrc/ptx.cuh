@@ -158,6 +158,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
         ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// 2-D tiled load multicast to the CTAs of `cta_mask` (same shared-memory offset in each).  kCtaGroup == 2: each
+// destination's completion is signalled on the barrier of ITS pair leader -- `bar` is the issuing CTA's own pair-leader
+// barrier as a shared::cluster address (the convention of CUTLASS' SM100_TMA_2SM_LOAD_MULTICAST: peer bit cleared).
+template <int kCtaGroup = 2>
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1,
+                                                      uint16_t cta_mask) {
+  static_assert(kCtaGroup == 2, "only the CTA-pair form is used");
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 template <int kCtaGroup = 1>
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1,
                                             int32_t c2) {

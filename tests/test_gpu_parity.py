@@ -299,7 +299,9 @@ def test_error_behaviour():
 
 
 # ----------------------------------------------------------------------------- GEMM
-CFGS = [(0, 0), (1, 64), (1, 128), (1, 192), (1, 256), (2, 128), (2, 192), (2, 256)]
+# (cta_group, block_n); (0, 0) = the planner's choice; cta_group 4 = CTA pairs in clusters of four with the A tiles
+# multicast between the two pairs (opt-in experiment: bit-identical, measured slower -- profiles/r01_notes.md)
+CFGS = [(0, 0), (1, 64), (1, 128), (1, 192), (1, 256), (2, 128), (2, 192), (2, 256), (4, 192), (4, 256)]
 
 
 @pytest.mark.parametrize("kind", ["mx", "nv"])
@@ -517,6 +519,9 @@ def test_fused_linear_equals_two_calls(fmt, had, method, shape, monkeypatch):
     m, n, k = shape
     assert _lib.load().b200q_linear_fp4_launches(m, n, k, had, 1 | Q.ROT_TRUSTED_HADAMARD, 0) >= 2   # default: two launches
     monkeypatch.setenv("B200Q_FUSE", "1")
+    # the fused kernel's quantiser warps run the butterfly arithmetic; large standalone inputs would otherwise take the
+    # tcgen05 kernel, which differs from it in fp32 summation order (<= 1e-5 of the codes, see the tcgen05 tests)
+    monkeypatch.setenv("B200Q_QUANT_TC", "0")
     R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, had, method, fmt, seed=m + n)
     lib = _lib.load()
     meth = (0 if method == "quest" else 1) | Q.ROT_TRUSTED_HADAMARD
@@ -565,6 +570,7 @@ def test_fused_linear_full_size(monkeypatch):
     """config 1 (4096 x 14336 x 4096) through the fused kernel, 20 back-to-back calls: identical to the two-kernel path."""
     m, n, k = 4096, 14336, 4096
     monkeypatch.setenv("B200Q_FUSE", "1")
+    monkeypatch.setenv("B200Q_QUANT_TC", "0")     # bit-for-bit reference = the butterfly arithmetic the fused kernel runs
     R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, 128, "abs_max", "mx", seed=3)
     for i in range(20):
         out, xq2, _ = Q.fused_linear_fp4(x, R, wq, wblk, al)
@@ -683,7 +689,7 @@ def test_full_size_properties(kind):
     np.testing.assert_array_equal(sub, full[256:384])
     twice = H.run_gemm(aq, asf, bq, bsf, kind, 2.0)
     np.testing.assert_array_equal(O.bf16_from_bits(twice), 2.0 * O.bf16_from_bits(full))
-    for cfg in ((1, 128), (1, 192), (1, 256), (2, 128), (2, 192), (2, 256)):
+    for cfg in ((1, 128), (1, 192), (1, 256), (2, 128), (2, 192), (2, 256), (4, 192), (4, 256)):
         np.testing.assert_array_equal(H.run_gemm(aq, asf, bq, bsf, kind, 1.0, cfg=cfg), full)
 
 

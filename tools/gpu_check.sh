@@ -38,7 +38,7 @@ fi
 if [[ "$what" == *ncufull* ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_fp4 -s 4 -c 2 -o gpurun_out/prof_gemm -f \
       python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:quantize_kernel -s 4 -c 1 -o gpurun_out/prof_quant -f \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:quantize_ -s 4 -c 1 -o gpurun_out/prof_quant -f \
       python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e >> gpurun_out/ncu_full.log 2>&1
   tail -3 gpurun_out/ncu_full.log
 fi
