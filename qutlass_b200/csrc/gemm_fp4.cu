@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "quantize_tile.cuh"
+#include <type_traits>
 
 #include <cuda.h>
 #include <mutex>
@@ -91,6 +92,16 @@ struct GemmCfg {
   static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-byte alignment for the 128B swizzle");
   static_assert(EPI_COLS % 32 == 0 && EPI_COLS <= 128, "epilogue register budget");
 };
+
+// Debug timeline (profiling flag 1 << 24): CTA 0 records clock64 per tile -- [0] MMA warp owns the accumulator,
+// [1] first k-tile landed, [2] last MMA issued, [3] epilogue warp 0 sees the accumulator complete, [4] drained,
+// [5] its stores issued.  Read back with b200q_debug_read_trace.
+constexpr int kTraceTiles = 32, kTraceEvents = 8;
+__device__ unsigned long long g_gemm_trace[kTraceTiles * kTraceEvents];
+__device__ __forceinline__ void trace_event(int flags, int tile_idx, int ev) {
+  if ((flags & (1 << 24)) && blockIdx.x == 0 && tile_idx < kTraceTiles && (threadIdx.x & 31) == 0)
+    g_gemm_trace[tile_idx * kTraceEvents + ev] = clock64();
+}
 
 struct GemmParams {
   const float* alpha;
@@ -417,64 +428,68 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
         return d;
       };
+      const bool skip_cp = (p.flags & 32) != 0;     // profiling flag 32: no scale copies (timing only)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      int tidx = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tidx) {
         int tm_, tn;
         tile_mn(tile, tm_, tn);
         const int n0 = tn * BN;
         const uint32_t sfb_shift = (uint32_t)((n0 % 128) / 32);     // 0 or 2 columns into the first SFB block
         mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2);
         tc_fence_after();
+        trace_event(p.flags, tidx, 0);
         const uint32_t tmem_acc = tmem_base + acc * BN;
         const uint32_t tsfb = tmem_sfb + sfb_shift;
-        int k_left = p.K;
-        for (int kt = 0; kt < p.k_tiles; ++kt, k_left -= Cfg::BK_ELEMS) {
-          mbar_wait(bar_base + 8u * stage, phase, 3);
+        // One k-tile: wait for the stage, copy its scales into TMEM (each 512-B block -> 4 columns, replicated over the 4
+        // lane quarters; the copies of K-chunk c go right before the first MMA that needs them), 4 MMAs of K = 64 (32 bytes
+        // = 2 x 16 B along the swizzled row each), free the stage.  This loop is the issue-rate limit of every tile narrower
+        // than 256 columns (ncu / the timeline probe: ~430 cycles per k-tile vs 380 of tensor time at BN = 192), so the
+        // hot instantiation (kTail = false: whole k-tile) has no K-tail predicates, no debug branches and a wait without
+        // the time-out path, which lets the compiler keep the loop state in uniform registers.
+        auto k_tile = [&](auto tail_tag, int kt, int k_left) {
+          constexpr bool kTail = decltype(tail_tag)::value;
+          mbar_wait_spin(bar_base + 8u * stage, phase);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + stage * kStage16;
           const uint32_t b_lo = a_lo + (Cfg::A_BYTES >> 4);
           const uint32_t sfa_lo = sfa_lo0 + stage * kStage16;
           const uint32_t sfb_lo = sfa_lo + (Cfg::SFA_BYTES >> 4);
           if (elected) {
-          // scales: smem -> TMEM (each 512-B block -> 4 columns, replicated over the 4 lane quarters).
-          // Order: the copies for K-chunk c are issued right before the first MMA that needs them
-          // (profiling flags: 32 = skip the copies, 64 = all copies up front).
-          auto copy_chunk = [&](int b) {
-            tmem_cp_32x128b_warpx4<kCtaGroup>(tmem_sfa + b * 4, mk(sfa_lo + b * 32, kDescHiSF));
+            auto copy_chunk = [&](int b) {
+              tmem_cp_32x128b_warpx4<kCtaGroup>(tmem_sfa + b * 4, mk(sfa_lo + b * 32, kDescHiSF));
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb)
-              tmem_cp_32x128b_warpx4<kCtaGroup>(tmem_sfb + b * (4 * NB) + nb * 4,
-                                                mk(sfb_lo + (nb * SFKB + b) * 32, kDescHiSF));
-          };
-          const bool skip_cp = (p.flags & 32) != 0;
-          const bool upfront = (p.flags & 64) != 0;
-          if (upfront && !skip_cp) {
+              for (int nb = 0; nb < NB; ++nb)
+                tmem_cp_32x128b_warpx4<kCtaGroup>(tmem_sfb + b * (4 * NB) + nb * 4,
+                                                  mk(sfb_lo + (nb * SFKB + b) * 32, kDescHiSF));
+            };
 #pragma unroll
-            for (int b = 0; b < SFKB; ++b) copy_chunk(b);
-          }
-          // 4 MMAs of K = 64 (32 bytes = 2 x 16 B along the swizzled row each); K tail issues fewer
-#pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
-            // scales per MMA: MXF4 2 bytes (sf_id 0/2 of a 4-byte cell), NVF4 a whole cell, MXF8 1 byte (sf_id = kb)
-            const uint32_t chunk = kNV ? kb : (kF8 ? 0 : (kb >> 1));
-            if (!upfront && !skip_cp && (kNV || (kF8 ? kb == 0 : (kb & 1) == 0))) copy_chunk((int)chunk);
-            if (k_left > kb * Cfg::MMA_K) {
-              const uint32_t sf_id = kNV ? 0u : (kF8 ? (uint32_t)kb : (uint32_t)((kb & 1) * 2));
-              mma_fp4_block_scaled<kCtaGroup, kNV, (kF8 != 0)>(tmem_acc, mk(a_lo + kb * kAStep16, kDescHiAB), mk(b_lo + kb * 2, kDescHiAB),
-                                                   idesc_base | (sf_id << 4) | (sf_id << 29), tmem_sfa + chunk * 4,
-                                                   tsfb + chunk * (4 * NB), (kt > 0 || kb > 0) ? 1u : 0u);
+            for (int kb = 0; kb < 4; ++kb) {
+              // scales per MMA: MXF4 2 bytes (sf_id 0/2 of a 4-byte cell), NVF4 a whole cell, MXF8 1 byte (sf_id = kb)
+              const uint32_t chunk = kNV ? kb : (kF8 ? 0 : (kb >> 1));
+              if (!skip_cp && (kNV || (kF8 ? kb == 0 : (kb & 1) == 0))) copy_chunk((int)chunk);
+              if (!kTail || k_left > kb * Cfg::MMA_K) {
+                const uint32_t sf_id = kNV ? 0u : (kF8 ? (uint32_t)kb : (uint32_t)((kb & 1) * 2));
+                mma_fp4_block_scaled<kCtaGroup, kNV, (kF8 != 0)>(tmem_acc, mk(a_lo + kb * kAStep16, kDescHiAB), mk(b_lo + kb * 2, kDescHiAB),
+                                                     idesc_base | (sf_id << 4) | (sf_id << 29), tmem_sfa + chunk * 4,
+                                                     tsfb + chunk * (4 * NB), (kb > 0) ? 1u : (kt > 0 ? 1u : 0u));
+              }
             }
-          }
-          // stage free once these MMAs have read it (kMC: tell all four CTAs -- the other pair multicasts into our stages)
-          tc_commit<kCtaGroup>(bar_base + 8u * (STAGES + stage), kMC ? (uint16_t)0xF : (uint16_t)3);
-          if (kt == p.k_tiles - 1) tc_commit<kCtaGroup>(tfull_bar(acc), (uint16_t)(3u << leader_rank));   // accumulator complete
+            // stage free once these MMAs have read it (kMC: tell all four CTAs -- the other pair multicasts into our stages)
+            tc_commit<kCtaGroup>(bar_base + 8u * (STAGES + stage), kMC ? (uint16_t)0xF : (uint16_t)3);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
+        };
+        const int full_kt = p.K / Cfg::BK_ELEMS;
+        for (int kt = 0; kt < full_kt; ++kt) k_tile(std::false_type{}, kt, Cfg::BK_ELEMS);
+        if (full_kt < p.k_tiles) k_tile(std::true_type{}, full_kt, p.K - full_kt * Cfg::BK_ELEMS);
+        if (elected) tc_commit<kCtaGroup>(tfull_bar(acc), (uint16_t)(3u << leader_rank));   // accumulator complete
+        __syncwarp();
+        trace_event(p.flags, tidx, 2);
         if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -515,6 +530,8 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int n0 = tn * BN;
       mbar_wait(tfull_bar(acc), acc_phase, 6);
       tc_fence_after();
+      const int tidx = (tile - cluster_id) / num_clusters;
+      if (ew == 0) trace_event(p.flags, tidx, 3);
       const uint32_t taddr = tmem_base + acc * BN + col0 + ((uint32_t)(q * 32) << 16);
       if constexpr (kFuse > 2) {
         // 448 threads -> 128 registers: drain chunk by chunk, keeping only packed bf16 pairs (EPI_COLS / 2 registers)
@@ -576,6 +593,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if constexpr (kCtaGroup == 2) mbar_arrive_cluster(tempty_leader + 8u * acc);
         else mbar_arrive(tempty_bar(acc));
       }
+      if (ew == 0) trace_event(p.flags, tidx, 4);
       if (p.flags & 512) __nanosleep((uint32_t)ew * (((p.flags >> 12) & 0xff) * 50u));   // profiling: stagger the warps
       if (!(p.flags & 1)) {
         if (p.tma_store) {
@@ -668,6 +686,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
         }
       }
+      if (ew == 0) trace_event(p.flags, tidx, 5);
       if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait_group<0>();   // all TMA stores of this warp have completed
@@ -841,6 +860,7 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
       int n = 0;
       B200Q_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
       max_clusters = n > 0 ? n : 1;
+      if (getenv("B200Q_GEMM_VERBOSE")) fprintf(stderr, "b200q: clusters of %d CTAs co-resident: %d (SMs %d)\n", kClusterCtas, n, num_sms());
     }
     if (clusters > max_clusters) clusters = max_clusters;
   }
@@ -982,6 +1002,14 @@ extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA,
     return run(2, 128, Bt, SFBt, (uint8_t*)D_bf16 + (int64_t)pl.n_main * 2, N - pl.n_main);
   }
   return run(cta_group, block_n, B, SFB, D_bf16, N);
+}
+
+// debug: copy the timeline of the last traced launch (B200Q_GEMM_DEBUG_FLAGS bit 24) into out[n] (synchronises)
+extern "C" int b200q_debug_read_trace(unsigned long long* out, int n) {
+  if (n > kTraceTiles * kTraceEvents) n = kTraceTiles * kTraceEvents;
+  B200Q_CUDA(cudaDeviceSynchronize());
+  B200Q_CUDA(cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(unsigned long long) * n));
+  return 0;
 }
 
 extern "C" int b200q_gemm_fp4(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha_dev,

@@ -66,9 +66,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on a barrier living in another CTA of the cluster (address from mapa)
+// arrive on a barrier living in another CTA of the cluster (address from mapa).  Default semantics (.release at CTA
+// scope), NOT .release.cluster: the cluster-scope form compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, a
+// round trip to L2 on the accumulator hand-off path (ncu: the most-sampled stall of the epilogue warps).  What the
+// arrive publishes here lives in TMEM / registers and is ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -112,6 +115,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
       __trap();
     }
   }
+}
+
+// Bare wait for the hot single-thread issue loops: no time-out / printf path (whose call keeps the loop state out of the
+// uniform registers).  Only where a lost arrival is impossible by construction or already caught by a mbar_wait elsewhere.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n"
+      "@!P bra WAIT_%=;\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
 }
 
 // ------------------------------------------------------------------ cross-CTA progress counters in global memory

@@ -85,6 +85,15 @@ if __name__ == "__main__":
         # is the mainloop bound by operand traffic (L2 -> SM / shared-memory writes)?  1 = no D stores, 1<<20 = no B loads, 1<<21 = no A loads
         B_, A_ = 1 << 20, 1 << 21
         gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 256), (2, 192), (1, 256)], [(0, 2), (1, 2), (B_, 2), (B_ | 1, 2), (A_, 2), (A_ | 1, 2), (A_ | B_ | 1, 2)])
+    if "gemmk" in which:
+        # per-tile overhead vs per-k-tile cost: time = rounds x (k_tiles x t_ktile + t_tile); fit over K
+        B_, A_ = 1 << 20, 1 << 21
+        gemm_sweep("mx", [(4096, 14336, 2048), (4096, 14336, 4096), (4096, 14336, 8192), (4096, 14336, 16384)], [(2, 256), (2, 192)],
+                   [(0, 2), (1, 2), (A_ | B_ | 1, 2), (A_ | B_ | 3, 2)])
+    if "gemmissue" in which:
+        # is the MMA-issuing warp the limiter at BN = 192?  32 = skip the scale copies (tcgen05.cp), timing only
+        B_, A_ = 1 << 20, 1 << 21
+        gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 192), (2, 256), (2, 128)], [(A_ | B_ | 1, 2), (A_ | B_ | 1 | 32, 2), (1, 2), (1 | 32, 2), (0, 2), (32, 2)])
     if "gemmq" in which:
         gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (1, 2), (4, 2)])
         gemm_sweep("nv", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (4, 2)])
