@@ -53,6 +53,11 @@ int check_device_sm100() {
   return 0;
 }
 
+int current_device() {
+  int dev;
+  return query_device(&dev) ? 0 : dev;
+}
+
 int num_sms() {
   int dev;
   if (query_device(&dev)) return 148;

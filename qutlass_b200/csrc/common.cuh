@@ -14,6 +14,23 @@ namespace b200q {
 void set_error(const char* fmt, ...);
 int check_device_sm100();          // 0 or B200Q_EUNSUPPORTED (cached per device)
 int num_sms();                     // SM count of the current device (cached)
+int current_device();              // ordinal of the current device, 0 on error
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: set it once per (kernel, device).
+// `done` is a per-instantiation bitmask of device ordinals (static in the caller).
+template <typename Kern>
+inline int ensure_dynamic_smem(Kern kern, int bytes, unsigned long long& done) {
+  const int dev = current_device() & 63;
+  if (!((done >> dev) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %d) failed: %s", bytes, cudaGetErrorString(e));
+      return B200Q_ECUDA;
+    }
+    done |= 1ull << dev;
+  }
+  return 0;
+}
 
 #define B200Q_REQUIRE(cond, ...)                 \
   do {                                           \

@@ -801,11 +801,8 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
   auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse, kMC>;
   constexpr int kClusterCtas = kCtaGroup * (kMC ? 2 : 1);
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static unsigned long long smem_attr_done = 0;   // per instantiation, one bit per device
+  if (int rc_attr = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, smem_attr_done)) return rc_attr;
   const int group = kNV ? 16 : 32;
   const int64_t sf_col_blocks = ceil_div(ceil_div(K, group), 4);
   CUtensorMap ta, tb, tsa, tsb, td;
@@ -852,17 +849,18 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   int clusters = num_sms() / kClusterCtas;
   if constexpr (kMC != 0) {
     // clusters of 4 must sit inside one GPC: ask how many are co-resident (a persistent grid must not exceed that)
-    static int max_clusters = 0;
-    if (max_clusters == 0) {
+    static int max_clusters[64] = {0};     // per device
+    int& mc = max_clusters[current_device() & 63];
+    if (mc == 0) {
       cfg.gridDim = dim3((unsigned)(clusters * kClusterCtas));
       cfg.attrs = attrs;
       cfg.numAttrs = 1;
       int n = 0;
       B200Q_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-      max_clusters = n > 0 ? n : 1;
+      mc = n > 0 ? n : 1;
       if (getenv("B200Q_GEMM_VERBOSE")) fprintf(stderr, "b200q: clusters of %d CTAs co-resident: %d (SMs %d)\n", kClusterCtas, n, num_sms());
     }
-    if (clusters > max_clusters) clusters = max_clusters;
+    if (clusters > mc) clusters = mc;
   }
   if (clusters > total) clusters = total;
   cfg.gridDim = dim3((unsigned)(clusters * kClusterCtas));
@@ -918,22 +916,27 @@ struct GemmPlan { int cta_group, block_n, n_main; };   // n_main > 0: peel colum
 static GemmPlan plan_auto(int M, int N, int K, int kind) {
   GemmPlan pl{1, 128, 0};
   int cta_group = 0, block_n = 0;
-  (void)K;
   {
-    // heuristic (measured on B200, profiles/): small M streams weights with single-CTA tiles; otherwise CTA pairs
-    // (256-row tiles halve the B traffic per flop) with the tile width that minimises rounds x width.
+    // heuristic (measured on B200, profiles/r01_plan_probe.jsonl): small M streams weights with single-CTA tiles; up to
+    // 256 rows one round of single-CTA 128 x 256 tiles; otherwise CTA pairs (256-row tiles halve the B traffic per flop)
+    // with the tile width that minimises rounds x (k_tiles x w + o) -- w / o = per-k-tile / per-tile cost of one round in
+    // us, fitted at K = 4096 and 8192: the 256-wide tile pays the single-buffered accumulator hand-off, the narrower ones
+    // are bound by the tcgen05 dispatch rate (same per-k-tile cost for 192 and 128 columns).
     if (M <= 128) { cta_group = 1; block_n = 128; }
     else if (M <= 256 && N <= 4096) { cta_group = 1; block_n = 128; }
+    else if (M <= 256 && ceil_div(M, 128) * ceil_div(N, 256) <= num_sms()) { cta_group = 1; block_n = 256; }
     else {
       cta_group = 2;
       const int64_t clusters = num_sms() / 2;
       const int64_t tm = ceil_div(M, 256);
-      int64_t best = -1;
+      const double kt = (double)ceil_div(K, (kind == B200Q_KIND_MXF8 || kind == B200Q_KIND_MXF8_NN) ? 128 : 256);
+      double best = -1.0;
       const int cands[3] = {256, 192, 128};
+      const double w[3] = {0.36, 0.30, 0.30}, o[3] = {1.2, 0.85, 0.6};
       for (int i = 0; i < 3; ++i) {
         const int bn = cands[i];
         const int64_t rounds = ceil_div(tm * ceil_div(N, bn), clusters);
-        const int64_t cost = rounds * (bn + 16);     // +16: fixed per-tile cost (accumulator hand-off)
+        const double cost = (double)rounds * (kt * w[i] + o[i]);
         if (best < 0 || cost < best) { best = cost; block_n = bn; }
       }
     }

@@ -94,12 +94,6 @@ if __name__ == "__main__":
         # is the MMA-issuing warp the limiter at BN = 192?  32 = skip the scale copies (tcgen05.cp), timing only
         B_, A_ = 1 << 20, 1 << 21
         gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 192), (2, 256), (2, 128)], [(A_ | B_ | 1, 2), (A_ | B_ | 1 | 32, 2), (1, 2), (1 | 32, 2), (0, 2), (32, 2)])
-    if "gemmsfw" in which:
-        # scale-copy warp (default) vs copies on the MMA warp (flag 1 << 25); 1 = no D stores
-        OFF = 1 << 25
-        for kind in ("mx", "nv"):
-            gemm_sweep(kind, [(4096, 14336, 4096)], [(2, 256), (2, 192), (2, 128), (1, 256)], [(0, 2), (OFF, 2), (1, 2), (1 | OFF, 2)])
-        gemm_sweep("mx", [(1024, 14336, 4096), (16384, 14336, 4096)], [(2, 256), (2, 192), (2, 128)], [(0, 2), (OFF, 2)])
     if "gemmq" in which:
         gemm_sweep("mx", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (1, 2), (4, 2)])
         gemm_sweep("nv", [(4096, 14336, 4096)], [(2, 192), (2, 256)], [(0, 2), (4, 2)])
