@@ -129,6 +129,9 @@ int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA, const void
                        const float* alpha_dev, void* D_bf16, int M, int N, int K, int kind,
                        int cta_group, int block_n, b200q_stream_t stream);
 
+/* The configuration b200q_gemm_fp4 picks for this problem (host-only: no device work, no stream). */
+int b200q_gemm_fp4_plan(int M, int N, int K, int kind, int* cta_group, int* block_n);
+
 /* Number of kernels b200q_gemm_fp4 launches for this problem (1, or 2 when the last 256-column block of N is peeled
  * into a second launch of small tiles to fill the final, mostly empty wave of CTA pairs). */
 int b200q_gemm_fp4_launches(int M, int N, int K, int kind);

@@ -21,6 +21,7 @@ SIGNATURES = {
     "b200q_swizzle_sf": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "b200q_gemm_fp4": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "b200q_gemm_fp4_cfg": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200q_gemm_fp4_plan": (_i32, [_i32, _i32, _i32, _i32, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "b200q_gemm_fp4_launches": (_i32, [_i32, _i32, _i32, _i32]),
     "b200q_linear_fp4_workspace_bytes": (_i64, [_i32]),
     "b200q_linear_fp4": (_i32, [_vp] * 11 + [_i32] * 6 + [_vp]),

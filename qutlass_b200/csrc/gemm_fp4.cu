@@ -1111,6 +1111,14 @@ extern "C" int b200q_linear_fp4(const void* x_bf16, const void* rot_bf16, void* 
   return B200Q_EINVAL;
 }
 
+extern "C" int b200q_gemm_fp4_plan(int M, int N, int K, int kind, int* cta_group, int* block_n) {
+  B200Q_REQUIRE(M > 0 && N > 0 && K > 0 && cta_group && block_n, "bad argument");
+  const GemmPlan pl = plan_auto(M, N, K, kind);
+  *cta_group = pl.cta_group;
+  *block_n = pl.block_n;
+  return 0;
+}
+
 extern "C" int b200q_gemm_fp4_launches(int M, int N, int K, int kind) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   return plan_auto(M, N, K, kind).n_main > 0 ? 2 : 1;

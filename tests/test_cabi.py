@@ -64,3 +64,26 @@ def test_product_never_imports_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                     txt = open(os.path.join(dirpath, f)).read()
                     assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_gemm_planner_choices_without_a_gpu(lib_path):
+    """b200q_gemm_fp4_plan is host-only (no device: 148 SMs assumed).  The choices below are the measured optima on B200
+    (profiles/r01_plan_probe.jsonl): weight-streaming single-CTA tiles up to 128 rows, one round of single-CTA 128 x 256
+    tiles up to 256 rows, CTA pairs beyond -- and never the dispatch-bound 128-column pair tile on the FFN shapes."""
+    from qutlass_b200 import _lib
+    lib = _lib.load()
+
+    def plan(m, n, k, kind=0):
+        cg, bn = ctypes.c_int(0), ctypes.c_int(0)
+        assert lib.b200q_gemm_fp4_plan(m, n, k, kind, ctypes.byref(cg), ctypes.byref(bn)) == 0
+        return cg.value, bn.value
+
+    assert plan(1, 14336, 4096) == (1, 128) and plan(128, 14336, 4096) == (1, 128)
+    assert plan(256, 14336, 4096) == (1, 256)
+    assert plan(4096, 14336, 4096) == (2, 256) and plan(4096, 14336, 4096, 1) == (2, 256)      # BASELINE configs 1 / 2
+    assert plan(16384, 14336, 4096) == (2, 256) and plan(2048, 28672, 8192) == (2, 256)        # config 4 shard
+    assert plan(1024, 6144, 4096) == (2, 192)
+    for m in (384, 512, 768, 1024, 1536, 2048, 3072, 8192):
+        assert plan(m, 14336, 4096)[0] == 2 and plan(m, 14336, 4096)[1] in (192, 256)
+    assert plan(4096, 4096, 14336) == (2, 256)
+    assert lib.b200q_gemm_fp4_plan(0, 1, 1, 0, ctypes.byref(ctypes.c_int()), ctypes.byref(ctypes.c_int())) != 0
