@@ -85,6 +85,21 @@ quantize_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       mbar_init(tempty_bar(a), 4);
     }
     fence_mbar_init();
+    fence_proxy_async_smem();      // the initialised barriers as the TMA unit (async proxy) must see them
+    // First ring of loads right here, before the TMEM allocation and the CTA-wide barrier: the ring is empty, and the
+    // DRAM latency of the first tile is the longest item of the kernel's fixed cost.  R as it lies in memory ([k][n],
+    // n contiguous) is an MN-major B operand: rows of min(H, 64) elements, swizzle span = row bytes (32 / 64 / 128 B);
+    // H = 128 takes two 64-column boxes, H * 128 B apart.
+    mbar_arrive_expect_tx(rot_bar, (uint32_t)(had * had * 2));
+    tma_load_2d<1>(rot_base, &tmap_r, rot_bar, 0, 0);
+    if (had == 128) tma_load_2d<1>(rot_base + 128 * 128, &tmap_r, rot_bar, 64, 0);
+    int s = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles && s < kTcStages; tile += gridDim.x, ++s) {
+      const uint32_t dst = smem_base + s * kTcStageBytes;
+      mbar_arrive_expect_tx(full_bar(s), kTcStageBytes);
+      tma_load_2d<1>(dst, &tmap_x, full_bar(s), 0, (int32_t)(tile * kTcTileRows));
+      tma_load_2d<1>(dst + kTcStageBytes / 2, &tmap_x, full_bar(s), 64, (int32_t)(tile * kTcTileRows));
+    }
   }
   if (warp == 1) {
     tmem_alloc<1>(tmem_slot, 512);
@@ -97,17 +112,11 @@ quantize_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // (the first kTcStages tiles and R were requested in the prologue above)
     const bool elected = elect_one();
-    if (elected) {
-      // R as it lies in memory ([k][n], n contiguous) is an MN-major B operand: rows of min(H, 64) elements, swizzle span
-      // = row bytes (32 / 64 / 128 B); H = 128 takes two 64-column boxes, H * 128 B apart
-      mbar_arrive_expect_tx(rot_bar, (uint32_t)(had * had * 2));
-      tma_load_2d<1>(rot_base, &tmap_r, rot_bar, 0, 0);
-      if (had == 128) tma_load_2d<1>(rot_base + 128 * 128, &tmap_r, rot_bar, 64, 0);
-    }
     int stage = 0;
-    uint32_t phase = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t phase = 1;
+    for (int64_t tile = blockIdx.x + (int64_t)kTcStages * gridDim.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(empty_bar(stage), phase ^ 1, 1);
       if (elected) {
         const uint32_t dst = smem_base + stage * kTcStageBytes;
@@ -182,19 +191,37 @@ quantize_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         acc_phase ^= 1;
         tc_fence_after();
         uint32_t out[4][4], sfb[4], mk[4];
+        if constexpr (!NV) {
+          // two chunks per TMEM round trip: two independent scale / e2m1 chains in flight
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32b_x32(lane_taddr + h * 64, r0);
-          tmem_ld_32x32b_x32(lane_taddr + h * 64 + 32, r1);
-          tmem_ld_wait();
-          if (h == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(grp));
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(lane_taddr + h * 64, r0);
+            tmem_ld_32x32b_x32(lane_taddr + h * 64 + 32, r1);
+            tmem_ld_wait();
+            if (h == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty_bar(grp));
+            }
+            chunk_quantise<NV, METHOD, MASK>(reinterpret_cast<float*>(r0), gs, gs_rcp, out[2 * h], sfb[2 * h], mk[2 * h]);
+            chunk_quantise<NV, METHOD, MASK>(reinterpret_cast<float*>(r1), gs, gs_rcp, out[2 * h + 1], sfb[2 * h + 1], mk[2 * h + 1]);
           }
-          chunk_quantise<NV, METHOD, MASK>(reinterpret_cast<float*>(r0), gs, gs_rcp, out[2 * h], sfb[2 * h], mk[2 * h]);
-          chunk_quantise<NV, METHOD, MASK>(reinterpret_cast<float*>(r1), gs, gs_rcp, out[2 * h + 1], sfb[2 * h + 1], mk[2 * h + 1]);
+        } else {
+          // NVFP4: a chunk already holds two independent 16-groups and its arithmetic needs more registers (two scales,
+          // e4m3 round trips); two chunks at a time spilled (45 local loads / stores per tile), so one chunk per round trip
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r0[32];
+            tmem_ld_32x32b_x32(lane_taddr + c * 32, r0);
+            tmem_ld_wait();
+            if (c == 3) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty_bar(grp));
+            }
+            chunk_quantise<NV, METHOD, MASK>(reinterpret_cast<float*>(r0), gs, gs_rcp, out[c], sfb[c], mk[c]);
+          }
         }
 
         // ---- codes: row-per-thread -> padded staging -> 512 contiguous bytes per warp store
