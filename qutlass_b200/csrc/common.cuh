@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 
 #include "b200q.h"
 
@@ -19,15 +20,15 @@ int current_device();              // ordinal of the current device, 0 on error
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: set it once per (kernel, device).
 // `done` is a per-instantiation bitmask of device ordinals (static in the caller).
 template <typename Kern>
-inline int ensure_dynamic_smem(Kern kern, int bytes, unsigned long long& done) {
+inline int ensure_dynamic_smem(Kern kern, int bytes, std::atomic<unsigned long long>& done) {
   const int dev = current_device() & 63;
-  if (!((done >> dev) & 1ull)) {
+  if (!((done.load(std::memory_order_acquire) >> dev) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %d) failed: %s", bytes, cudaGetErrorString(e));
       return B200Q_ECUDA;
     }
-    done |= 1ull << dev;
+    done.fetch_or(1ull << dev, std::memory_order_release);   // setting the attribute twice from two threads is harmless
   }
   return 0;
 }

@@ -801,7 +801,7 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
   auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse, kMC>;
   constexpr int kClusterCtas = kCtaGroup * (kMC ? 2 : 1);
-  static unsigned long long smem_attr_done = 0;   // per instantiation, one bit per device
+  static std::atomic<unsigned long long> smem_attr_done{0};   // per instantiation, one bit per device
   if (int rc_attr = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, smem_attr_done)) return rc_attr;
   const int group = kNV ? 16 : 32;
   const int64_t sf_col_blocks = ceil_div(ceil_div(K, group), 4);

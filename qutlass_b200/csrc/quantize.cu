@@ -449,7 +449,7 @@ template <int HAD, bool NV, int METHOD, bool MASK>
 static int launch_mma(const QuantParams& p, cudaStream_t stream) {
   auto kern = quantize_mma_kernel<HAD, NV, METHOD, MASK>;
   constexpr int smem = kMmaStages * kTileBytes;
-  static unsigned long long smem_attr_done = 0;   // per instantiation, one bit per device
+  static std::atomic<unsigned long long> smem_attr_done{0};   // per instantiation, one bit per device
   if (int rc_attr = ensure_dynamic_smem(kern, smem, smem_attr_done)) return rc_attr;
   const int64_t n_tiles = (p.n_chunks * 32 + kTileElems - 1) / kTileElems;
   int64_t ctas = n_tiles;

@@ -305,7 +305,7 @@ bool quantize_tc_eligible(const QuantParams& p, int had, bool nv) {
 template <bool NV, int METHOD, bool MASK>
 static int launch_tc(const QuantParams& p, int had, cudaStream_t stream) {
   auto kern = quantize_tc_kernel<NV, METHOD, MASK>;
-  static unsigned long long smem_attr_done = 0;   // per instantiation, one bit per device
+  static std::atomic<unsigned long long> smem_attr_done{0};   // per instantiation, one bit per device
   if (int rc_attr = ensure_dynamic_smem(kern, kTcSmem, smem_attr_done)) return rc_attr;
   const int64_t rows = p.n_chunks / 4;
   const int64_t n_tiles = ceil_div(rows, kTcTileRows);
