@@ -522,6 +522,8 @@ def _register_ops() -> None:
         "matmul_nvf4_bf16_tn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
         "matmul_mxf8_bf16_tn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
         "matmul_mxf8_bf16_nn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
+        # schema kept for importers; like the reference on sm_100 (gemm_ada.cu is sm_120-only) the call itself fails
+        "matmul_ada_mxf4_bf16_tn": "(Tensor A, Tensor B, Tensor A_sf, Tensor B_sf, Tensor alpha) -> Tensor",
         "fusedQuantizeMxQuest": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf) -> (Tensor, Tensor)",
         "fusedQuantizeMxAbsMax": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf) -> (Tensor, Tensor)",
         "fusedQuantizeNvQuest": "(Tensor A, Tensor R, Tensor OUT, Tensor OUT_sf, Tensor global_scale) -> (Tensor, Tensor)",
@@ -537,6 +539,7 @@ def _register_ops() -> None:
         "matmul_nvf4_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_nvf4_bf16_tn(A, B, A_sf, B_sf, alpha),
         "matmul_mxf8_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_mxf8_bf16_tn(A, B, A_sf, B_sf, alpha),
         "matmul_mxf8_bf16_nn": lambda A, B, A_sf, B_sf, alpha: matmul_mxf8_bf16_nn(A, B, A_sf, B_sf, alpha),
+        "matmul_ada_mxf4_bf16_tn": lambda A, B, A_sf, B_sf, alpha: matmul_ada_mxf4_bf16_tn(A, B, A_sf, B_sf, alpha),
         "fusedQuantizeMxQuest": lambda A, R, OUT, OUT_sf: (_quantize_mx_into(A, R, OUT, OUT_sf, None, None, METHOD_QUEST), (OUT, OUT_sf))[1],
         "fusedQuantizeMxAbsMax": lambda A, R, OUT, OUT_sf: (_quantize_mx_into(A, R, OUT, OUT_sf, None, None, METHOD_ABSMAX), (OUT, OUT_sf))[1],
         "fusedQuantizeNvQuest": lambda A, R, OUT, OUT_sf, gs: (_quantize_nv_into(A, R, OUT, OUT_sf, None, gs, METHOD_QUEST), (OUT, OUT_sf))[1],

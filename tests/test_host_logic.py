@@ -27,8 +27,11 @@ def test_surface_matches_reference_names():
     assert inspect.signature(qutlass.fusedQuantizeNv).parameters["method"].default == "abs_max"
     assert inspect.signature(qutlass.matmul_mxf4_bf16_tn).parameters["backend"].default == "cutlass"
     assert inspect.signature(qutlass.utils.to_blocked).parameters["use_triton_kernel"].default is False
-    for op in ("matmul_mxf4_bf16_tn", "matmul_nvf4_bf16_tn", "fusedQuantizeMxQuest", "fusedQuantizeMxAbsMax",
-               "fusedQuantizeNvQuest", "fusedQuantizeNvAbsMax", "fusedQuantizeMxQuestWithMask", "matmul_mxf8_bf16_tn"):
+    # every schema of the reference's op library (qutlass/csrc/bindings.cpp:498-515)
+    for op in ("matmul_mxf4_bf16_tn", "matmul_nvf4_bf16_tn", "matmul_ada_mxf4_bf16_tn", "matmul_mxf8_bf16_tn",
+               "matmul_mxf8_bf16_nn", "fusedQuantizeMxQuest", "fusedQuantizeMxAbsMax", "fusedQuantizeNvQuest",
+               "fusedQuantizeNvAbsMax", "fusedQuantizeMxQuestWithMask", "backward_t_bf16", "backward_qt_bf16",
+               "backward_bf16_square_double_mxfp8", "mxfp4_transpose_mxfp8"):
         assert hasattr(torch.ops._qutlass_C, op)
 
 
