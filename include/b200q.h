@@ -173,6 +173,10 @@ int b200q_linear_fp4_host(const void* x_host, const void* rot_bf16, const void* 
                           const float* alpha_dev, const float* global_scale_dev,
                           void* d_host, void* ws, int M, int N, int K, int had, int kind,
                           b200q_stream_t stream);
+/* Host-only query: the row slabs b200q_linear_fp4_host pipelines for M rows -- slab i = rows [bounds[i], bounds[i+1]),
+ * every bound but the last a multiple of 128 (block-aligned scales); a short first slab starts the result copy early.
+ * `bounds` needs room for 17 ints (`capacity`); returns the slab count (<= 16) or a negative error code. */
+int b200q_linear_host_slabs(int M, int* bounds, int capacity);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Transposing re-quantisers of the QAT backward pass.  Same argument order as the

@@ -27,6 +27,7 @@ SIGNATURES = {
     "b200q_linear_fp4": (_i32, [_vp] * 11 + [_i32] * 6 + [_vp]),
     "b200q_linear_fp4_launches": (_i32, [_i32] * 6),
     "b200q_linear_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "b200q_linear_host_slabs": (_i32, [_i32, ctypes.POINTER(ctypes.c_int), _i32]),
     "b200q_backward_t_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "b200q_backward_qt_bf16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "b200q_backward_bf16_square_double_mxfp8": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 
 #include "b200q.h"
@@ -31,6 +32,18 @@ inline int ensure_dynamic_smem(Kern kern, int bytes, std::atomic<unsigned long l
     done.fetch_or(1ull << dev, std::memory_order_release);   // setting the attribute twice from two threads is harmless
   }
   return 0;
+}
+
+// Programmatic dependent launch of the quantise kernels: fills attr[0] and returns the attribute count (0 with
+// B200Q_NO_PDL=1, which switches PDL off everywhere, or =2, which keeps it for the GEMM only).  A kernel launched with it
+// may be scheduled while the previous kernel in the stream drains; inside, everything that touches global memory sits
+// behind griddepcontrol.wait (ptx::pdl_wait), which returns once that kernel has completed and its writes are visible.
+inline unsigned pdl_attribute(cudaLaunchAttribute* attr) {
+  const char* e = getenv("B200Q_NO_PDL");
+  if (e && (e[0] == '1' || e[0] == '2')) return 0;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  return 1;
 }
 
 #define B200Q_REQUIRE(cond, ...)                 \

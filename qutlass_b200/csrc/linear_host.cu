@@ -47,9 +47,34 @@ static SideStreams& side_streams() {
   }
   return r;
 }
+
+// Slabs of whole 128-row blocks (each slab's blocked scales are self-contained): slab i = rows [bounds[i], bounds[i+1]).
+// The call is bound by the result copy (D2H), which can only start once the first slab has been uploaded and computed:
+// so the first slab is a single 128-row block, the second one fills up to the regular slab size, the rest are regular.
+static int slab_bounds(int M, int* bounds) {
+  int slab_rows = 512;
+  if (ceil_div(M, slab_rows) + 1 > kMaxSlabs) slab_rows = (int)round_up(ceil_div(M, kMaxSlabs - 1), 128);
+  int n = 0;
+  bounds[0] = 0;
+  if (M > slab_rows) {
+    bounds[++n] = 128;
+    bounds[++n] = slab_rows;
+  }
+  while (bounds[n] < M) {
+    const int64_t next = (int64_t)bounds[n] + slab_rows;
+    bounds[n + 1] = next < M ? (int)next : M;
+    ++n;
+  }
+  return n;
+}
 }  // namespace b200q
 
 using namespace b200q;
+
+extern "C" int b200q_linear_host_slabs(int M, int* bounds, int capacity) {
+  B200Q_REQUIRE(M > 0 && bounds && capacity >= kMaxSlabs + 1, "need M > 0 and room for %d row bounds", kMaxSlabs + 1);
+  return slab_bounds(M, bounds);
+}
 
 extern "C" int64_t b200q_linear_workspace_bytes(int M, int N, int K, int kind) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
@@ -70,18 +95,16 @@ extern "C" int b200q_linear_fp4_host(const void* x_host, const void* rot_bf16, c
   SideStreams& ss = side_streams();
   B200Q_REQUIRE(ss.ok, "could not create helper streams/events");
 
-  // slabs of whole 128-row blocks (each slab's blocked scales are self-contained)
-  int slab_rows = 512;
-  if (ceil_div(M, slab_rows) > kMaxSlabs) slab_rows = (int)round_up(ceil_div(M, kMaxSlabs), 128);
-  const int n_slabs = (int)ceil_div(M, slab_rows);
+  int bounds[kMaxSlabs + 1];
+  const int n_slabs = slab_bounds(M, bounds);
   const int64_t sf_cols = round_up(ceil_div(K, group), 4);
 
   B200Q_CUDA(cudaEventRecord(ss.fork, s));
   B200Q_CUDA(cudaStreamWaitEvent(ss.h2d, ss.fork, 0));
   B200Q_CUDA(cudaStreamWaitEvent(ss.d2h, ss.fork, 0));
   for (int i = 0; i < n_slabs; ++i) {
-    const int r0 = i * slab_rows;
-    const int rows = (M - r0 < slab_rows) ? (M - r0) : slab_rows;
+    const int r0 = bounds[i];
+    const int rows = bounds[i + 1] - r0;
     uint8_t* xs = base + w.off_x + (int64_t)r0 * K * 2;
     uint8_t* qs = base + w.off_q + (int64_t)r0 * K / 2;
     uint8_t* sfs = base + w.off_sf + (int64_t)r0 * sf_cols;       // r0 is a multiple of 128: block-aligned

@@ -34,6 +34,9 @@ __global__ void __launch_bounds__(kThreads, 3) quantize_kernel(const QuantParams
   // let a dependent kernel launched with the PDL attribute (our GEMM) start its prologue and weight loads now;
   // it waits (griddepcontrol.wait) for this whole grid before touching the activations written here
   ptx::pdl_launch_dependents();
+  // launched as a programmatic dependent itself (launch()): the grid may be scheduled while the previous kernel in the
+  // stream drains, but x / R / global_scale may be its outputs and it may still read our output buffers
+  ptx::pdl_wait();
 
   // first tile's loads go out before anything else (they overlap the rotation check)
   uint4* stage = s_stage[warp];
@@ -480,11 +483,17 @@ static int launch(const QuantParams& p, cudaStream_t stream) {
   const int64_t max_ctas = (int64_t)num_sms() * (p.trust_hadamard ? occ_trust : occ_check);
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attribute(attr);
   if (p.trust_hadamard)
-    quantize_kernel<HAD, NV, METHOD, MASK, true><<<(unsigned)ctas, kThreads, 0, stream>>>(p);
+    B200Q_CUDA(cudaLaunchKernelEx(&cfg, quantize_kernel<HAD, NV, METHOD, MASK, true>, p));
   else
-    quantize_kernel<HAD, NV, METHOD, MASK, false><<<(unsigned)ctas, kThreads, 0, stream>>>(p);
-  B200Q_CUDA(cudaGetLastError());
+    B200Q_CUDA(cudaLaunchKernelEx(&cfg, quantize_kernel<HAD, NV, METHOD, MASK, false>, p));
   return 0;
 }
 

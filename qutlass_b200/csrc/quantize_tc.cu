@@ -86,6 +86,10 @@ quantize_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     }
     fence_mbar_init();
     fence_proxy_async_smem();      // the initialised barriers as the TMA unit (async proxy) must see them
+    // Launched as a programmatic dependent (launch_tc): everything above overlapped the tail of the previous kernel in the
+    // stream; x, R and global_scale may be its outputs and our output buffers may still be read by it, so every access
+    // to global memory sits behind griddepcontrol.wait (a no-op for a plain launch).
+    pdl_wait();
     // First ring of loads right here, before the TMEM allocation and the CTA-wide barrier: the ring is empty, and the
     // DRAM latency of the first tile is the longest item of the kernel's fixed cost.  R as it lies in memory ([k][n],
     // n contiguous) is an MN-major B operand: rows of min(H, 64) elements, swizzle span = row bytes (32 / 64 / 128 B);
@@ -106,6 +110,7 @@ quantize_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     tmem_relinquish<1>();
   }
   tc_fence_before();
+  pdl_wait();          // every thread: nothing below may touch global memory before the previous kernel has completed
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_gen, 0);
@@ -316,8 +321,15 @@ static int launch_tc(const QuantParams& p, int had, cudaStream_t stream) {
   rc = make_rot_tmap(&tr, p.rot, had);
   if (rc) return rc;
   int64_t ctas = n_tiles < num_sms() ? n_tiles : num_sms();
-  kern<<<(unsigned)ctas, kTcThreads, kTcSmem, stream>>>(tm, tr, p, had, n_tiles);
-  B200Q_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = kTcSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attribute(attr);
+  B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, tr, p, had, n_tiles));
   return 0;
 }
 

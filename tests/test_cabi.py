@@ -87,3 +87,27 @@ def test_gemm_planner_choices_without_a_gpu(lib_path):
         assert plan(m, 14336, 4096)[0] == 2 and plan(m, 14336, 4096)[1] in (192, 256)
     assert plan(4096, 4096, 14336) == (2, 256)
     assert lib.b200q_gemm_fp4_plan(0, 1, 1, 0, ctypes.byref(ctypes.c_int()), ctypes.byref(ctypes.c_int())) != 0
+
+
+def test_host_entry_slab_schedule_without_a_gpu(lib_path):
+    """b200q_linear_host_slabs is host-only: the row slabs b200q_linear_fp4_host pipelines (H2D | kernels | D2H).  Slabs
+    tile [0, M) in order, every inner bound is a multiple of 128 (so each slab's blocked scales are self-contained), there
+    are at most 16, and beyond one regular slab the first is a single 128-row block (the result copy starts early)."""
+    from qutlass_b200 import _lib
+    lib = _lib.load()
+
+    def slabs(m):
+        b = (ctypes.c_int * 17)()
+        n = lib.b200q_linear_host_slabs(m, b, 17)
+        assert 1 <= n <= 16, (m, n)
+        return list(b[: n + 1])
+
+    assert slabs(1) == [0, 1] and slabs(200) == [0, 200] and slabs(512) == [0, 512]
+    assert slabs(513) == [0, 128, 512, 513]
+    assert slabs(4096) == [0, 128, 512] + list(range(1024, 4097, 512))        # BASELINE config 1: 9 slabs
+    for m in (1, 127, 128, 129, 600, 1100, 4096, 7680, 7681, 16384, 100000, 1 << 20, (1 << 20) + 77):
+        b = slabs(m)
+        assert b[0] == 0 and b[-1] == m and all(x < y for x, y in zip(b, b[1:]))
+        assert all(x % 128 == 0 for x in b[:-1])
+    assert lib.b200q_linear_host_slabs(0, (ctypes.c_int * 17)(), 17) < 0
+    assert lib.b200q_linear_host_slabs(4096, (ctypes.c_int * 4)(), 4) < 0       # not enough room for the bounds

@@ -491,6 +491,36 @@ def test_linear_host_entry_point():
     assert torch.equal(d_host.cuda(), want)
 
 
+@pytest.mark.parametrize("m,fmt", [(1100, "mx"), (640, "nv")])
+def test_linear_host_entry_point_multi_slab(m, fmt):
+    """several pipelined row slabs (128 + 384 + 512 + tail; b200q_linear_host_slabs) == one quantise + one GEMM over all rows."""
+    n, k, had = 384, 512, 32
+    lib = _lib.load()
+    kind = 0 if fmt == "mx" else 1
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(had))
+    w = H.bf16_tensor_from_f32(H.random_bf16((n, k), seed=63))
+    gs = torch.tensor([2.0], device="cuda")
+    wq, wsf = Q.fusedQuantizeMx(w, R, method="abs_max") if fmt == "mx" else Q.fusedQuantizeNv(w, R, gs, method="abs_max")
+    wblk = Q.to_blocked(wsf)
+    x_host = torch.from_numpy(O.bf16_bits(H.random_bf16((m, k), seed=64)).astype(np.int16)).view(torch.bfloat16).pin_memory()
+    d_host = torch.zeros(m, n, dtype=torch.bfloat16).pin_memory()
+    ws = torch.empty(lib.b200q_linear_workspace_bytes(m, n, k, kind), dtype=torch.uint8, device="cuda")
+    al = torch.tensor([1.0 / 9.0], device="cuda")
+    for _ in range(2):      # back to back: the second call reuses the helper streams / events
+        _lib.check(lib.b200q_linear_fp4_host(x_host.data_ptr(), R.data_ptr(), wq.data_ptr(), wblk.data_ptr(), al.data_ptr(),
+                                             gs.data_ptr(), d_host.data_ptr(), ws.data_ptr(), m, n, k, had, kind,
+                                             torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    if fmt == "mx":
+        xq, xsf = Q.fusedQuantizeMx(x_host.cuda(), R, method="abs_max")
+        want = Q.matmul_mxf4_bf16_tn(xq, wq, Q.to_blocked(xsf), wblk, al)
+    else:
+        xq, xsf = Q.fusedQuantizeNv(x_host.cuda(), R, gs, method="abs_max")
+        want = Q.matmul_nvf4_bf16_tn(xq, wq, Q.to_blocked(xsf), wblk, al)
+    torch.cuda.synchronize()
+    assert torch.equal(d_host.cuda(), want)
+
+
 # ----------------------------------------------------------------------------- fused quantise + GEMM (one persistent kernel)
 def _fused_case(m, n, k, had, method, fmt, seed):
     R = H.bf16_tensor_from_f32(O.hadamard_matrix(had))
