@@ -100,6 +100,23 @@ def _ncu_traffic_bytes():
         return None
 
 
+def _reference_gpu(kind, had, steps):
+    """GEMM / quantise / step times of the reference's CUTLASS kernels, measured by oracle/ref_gpu.py in a child process
+    AFTER our own timed regions (same box, same shape, same rotating-buffer policy)."""
+    try:
+        from oracle import ref_gpu
+        if not ref_gpu.available():
+            return {"unavailable": "oracle/_ref/qutlass_ref_C.so not built (python oracle/build_ref.py)"}
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_gpu.py"), "bench", kind, str(M), str(N), str(K),
+                            str(had), str(steps)], capture_output=True, text=True, timeout=180)
+        for l in reversed(r.stdout.strip().splitlines()):
+            if l.startswith("{"):
+                return json.loads(l)
+        return {"unavailable": ("child failed: " + (r.stderr or r.stdout)[-300:]).replace("\n", " ")}
+    except Exception as e:   # noqa: BLE001 -- a comparison leg must never take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
 def run_reference(args):
     """CPU arm: the reference's test-oracle path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -148,6 +165,7 @@ def main():
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-CUTLASS-kernel comparison leg (child process)")
     ap.add_argument("--fuse", action="store_true", help="step = the single fused quantise+GEMM kernel (B200Q_FUSE=1; measured slower)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -346,11 +364,17 @@ def main():
                        "api": "b200q_linear_fp4_host (C-ABI, pinned host buffers)"}
 
     # ---------------- cpu_baseline (rank 0, N=1 only): bounded sample on the host cores
+    # (the baseline leg is the one place of this arm that executes oracle/: the CPU port, and -- reported beside it, after
+    # every timed region of ours -- the reference's own CUDA kernels: oracle/_ref/qutlass_ref_C.so = the unmodified reference
+    # sources compiled for sm_100a by oracle/build_ref.py, run in a child process because it registers the same torch op
+    # namespace as our drop-in.  A reported comparison on the same box and shape; it can never fail the bench line.)
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import cpu_baseline as C
         r = C.time_cpu_path(M, N, K, kind, steps=1, warmup=1)
         line["cpu_baseline"] = {"value": r["tflops"], "unit": "TFLOP/s", "cores": r["threads"], "kind": "port",
                                 "sample": f"1 step of the full config (M={M}): LUT dequantise A,B + fp32 torch.matmul + bf16"}
+        if not args.no_ref_gpu:
+            line["reference_gpu"] = _reference_gpu(kind, args.had, min(args.steps, 200))
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

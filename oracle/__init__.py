@@ -12,6 +12,10 @@ helpers (``/root/reference/tests/mxfp4_test.py`` and ``nvfp4_test.py``:
 ``_rtne_fp4``, ``_dq_fp4``, ``_forward_quantize_ref``) and ``qutlass/utils.py``
 ``to_blocked`` -- see ``tests/golden/make_golden.py`` (the generator, committed)
 and ``tests/test_oracle_golden.py`` (the check).
+
+``oracle/_ref/`` (git-ignored, travels to the GPU box) holds the reference ITSELF compiled for sm_100a from the sources
+where they lie (``oracle/build_ref.py``); ``oracle/ref_gpu.py`` runs it in a child process as the GPU-side checker and
+as the kernel to beat (``tests/test_gpu_reference_lib.py``, ``bench.py``'s ``reference_gpu`` leg).
 """
 from .fp4_oracle import *  # noqa: F401,F403
 from . import bwd_oracle  # noqa: F401  (backward re-quantisers: oracle.bwd_oracle.*)

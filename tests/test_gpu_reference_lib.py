@@ -1,0 +1,122 @@
+"""GPU parity against the REAL reference kernels (run with -m gpu on a B200).
+
+oracle/build_ref.py compiles the unmodified reference sources (/root/reference/qutlass/csrc/*.cu + its vendored
+CUTLASS) for sm_100a in the build container; the resulting oracle/_ref/qutlass_ref_C.so travels to the GPU box.  It
+registers the reference's ops in torch's `_qutlass_C` library -- the namespace our drop-in registers too -- so it runs in
+a CHILD process (oracle/ref_gpu.py); tensors cross as files.  Same seeded inputs on both sides:
+
+  * quantisers: the reference's own bar against its test oracle is a mismatch fraction <= 1e-4 for MX
+    (tests/mxfp4_test.py:221) and <= 1e-1 for NV (tests/nvfp4_test.py:205); ours against the same oracle is <= 3e-6,
+    so ours against the reference's KERNEL must stay within 2e-4 (MX) / 1e-2 (NV) of the dequantised values;
+  * GEMM on IDENTICAL quantised operands: both sides are one fp32 tcgen05 accumulation chain over K in the same order,
+    alpha in fp32, one RNE to bf16 -> bit-exact.
+
+Status: written in round 1 after the GPU budget was spent, so the first execution of this file is the driver's round-end
+run.  Until it has been observed once the comparisons are `xfail(strict=False)`: they run and report XPASS / XFAIL
+without gating the suite; infrastructure trouble (library missing, child cannot start) is a skip.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import helpers as H
+from oracle import ref_gpu
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("CUDA required", allow_module_level=True)
+
+import qutlass_b200 as Q  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+first_run = pytest.mark.xfail(strict=False, reason="first execution happens at round end; see the module docstring")
+
+
+def _reference(cases, timeout=240):
+    """run `cases` through the reference library in a child process; returns its list of result dicts"""
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref/qutlass_ref_C.so not built (python oracle/build_ref.py in the build container)")
+    with tempfile.TemporaryDirectory() as wd:
+        torch.save({"cases": cases}, os.path.join(wd, "job.pt"))
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_gpu.py"), "parity", wd],
+                               capture_output=True, text=True, timeout=timeout)
+        except subprocess.TimeoutExpired:
+            pytest.skip("reference child process timed out")
+        if r.returncode != 0 or not os.path.exists(os.path.join(wd, "out.pt")):
+            pytest.skip("reference child process failed: " + (r.stderr or r.stdout)[-400:])
+        return torch.load(os.path.join(wd, "out.pt"))["results"]
+
+
+def _bf16_cpu(x: np.ndarray) -> torch.Tensor:
+    return H.bf16_tensor_from_f32(x, device="cpu")
+
+
+@first_run
+def test_quantisers_match_the_reference_kernels():
+    k = 4096
+    cases, ours = [], []
+    # 512 rows: our butterfly kernel; 2048 rows at H = 128: our tcgen05 rotation kernel (the reference's Had-128 abs_max
+    # case runs ITS sm_100 tcgen05 kernel, fused_quantize_mx_sm100.cu, the others its mma.sync kernels)
+    for fmt, method, had, gs, rows in [("mx", "abs_max", 32, 1.0, 512), ("mx", "abs_max", 128, 1.0, 512),
+                                       ("mx", "quest", 64, 1.0, 512), ("mx", "quest", 128, 1.0, 512),
+                                       ("mx", "abs_max", 128, 1.0, 2048), ("nv", "abs_max", 16, 6.0, 512),
+                                       ("nv", "abs_max", 128, 6.0, 512), ("nv", "quest", 64, 6.0, 512)]:
+        x = H.random_bf16((rows, k), seed=1000 + had + len(cases))         # randn * 25, like the reference's tests
+        R = O.hadamard_matrix(had)
+        cases.append({"op": "quantize", "fmt": fmt, "method": method, "x": _bf16_cpu(x), "R": _bf16_cpu(R), "gs": gs})
+        xt, Rt = H.bf16_tensor_from_f32(x), H.bf16_tensor_from_f32(R)
+        if fmt == "mx":
+            q, sf = Q.fusedQuantizeMx(xt, Rt, method=method)
+        else:
+            q, sf = Q.fusedQuantizeNv(xt, Rt, torch.tensor([gs], device="cuda"), method=method)
+        torch.cuda.synchronize()
+        ours.append((fmt, rows, H.u8_of(q), H.u8_of(sf)))
+    ref = _reference(cases)
+    for (fmt, rows, q, sf), r, c in zip(ours, ref, cases):
+        group = 32 if fmt == "mx" else 16
+        cols = k // group
+        sf_o = sf.reshape(-1, sf.shape[-1])[:rows, :cols]
+        sf_r = r["sf"].numpy()[:rows, :cols]
+        dq = O.dequant_mx if fmt == "mx" else O.dequant_nv
+        mism = float((dq(q, sf_o) != dq(r["q"].numpy().reshape(rows, -1), sf_r)).mean())
+        assert mism <= (2e-4 if fmt == "mx" else 1e-2), (c["fmt"], c["method"], c["R"].shape[0], mism)
+
+
+@first_run
+@pytest.mark.parametrize("fmt", ["mx", "nv"])
+def test_gemm_is_bit_identical_to_the_reference_kernel(fmt):
+    """the reference's bit-exact shapes (tests/mxfp4_test.py:223-237,255-269; nvfp4_test.py:207-224) + a Llama FFN slice,
+    on operands quantised by OUR kernels, multiplied by both GEMMs"""
+    had = 32
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(had))
+    gs = torch.tensor([1.0], device="cuda")
+    cases, ours = [], []
+    for i, (m, n, k) in enumerate([(1, 504, 4096), (504, 504, 2048), (16, 14336, 4096), (512, 1024, 4096)]):
+        a = H.bf16_tensor_from_f32(H.random_bf16((m, k), seed=70 + i))
+        b = H.bf16_tensor_from_f32(H.random_bf16((n, k), seed=80 + i))
+        if fmt == "mx":
+            (aq, asf), (bq, bsf) = Q.fusedQuantizeMx(a, R, method="abs_max"), Q.fusedQuantizeMx(b, R, method="abs_max")
+            mm = Q.matmul_mxf4_bf16_tn
+        else:
+            (aq, asf), (bq, bsf) = Q.fusedQuantizeNv(a, R, gs, method="abs_max"), Q.fusedQuantizeNv(b, R, gs, method="abs_max")
+            mm = Q.matmul_nvf4_bf16_tn
+        a_blk, b_blk = Q.to_blocked(asf), Q.to_blocked(bsf)
+        alpha = 1.0 / 9.0
+        d = mm(aq, bq, a_blk, b_blk, torch.tensor([alpha], device="cuda"))
+        torch.cuda.synchronize()
+        ours.append(H.bf16_bits_of(d))
+        cases.append({"op": "gemm", "fmt": fmt, "a": aq.cpu(), "b": bq.cpu(), "a_sf": a_blk.view(torch.uint8).cpu(),
+                      "b_sf": b_blk.view(torch.uint8).cpu(), "alpha": alpha})
+    ref = _reference(cases)
+    for got, r, c in zip(ours, ref, cases):
+        want = r["d"].numpy().view(np.uint16)
+        mism, rel = H.compare_bits(got, want)
+        assert mism == 0.0, (fmt, tuple(c["a"].shape), tuple(c["b"].shape), mism, rel)
