@@ -11,9 +11,16 @@ a CHILD process (oracle/ref_gpu.py); tensors cross as files.  Same seeded inputs
   * GEMM on IDENTICAL quantised operands: both sides are one fp32 tcgen05 accumulation chain over K in the same order,
     alpha in fp32, one RNE to bf16 -> bit-exact.
 
-Status: written in round 1 after the GPU budget was spent, so the first execution of this file is the driver's round-end
-run.  Until it has been observed once the comparisons are `xfail(strict=False)`: they run and report XPASS / XFAIL
-without gating the suite; infrastructure trouble (library missing, child cannot start) is a skip.
+Observed on a B200 at the end of round 1 (profiles/r01_ref_parity_first_run.log, r01_ref_quant_diag.jsonl): both GEMMs
+bit-identical to the reference's CUTLASS kernels on every shape; every quantiser case IDENTICAL in dequantised values and
+scale bytes (one +0 / -0 code in a million differs) -- except NVFP4 abs_max with Hadamard-128, where the reference
+dispatches to its sm_100-only kernel (bindings.cpp:413-415 -> fused_quantize_nv_sm100.cu): that kernel stores the
+e4m3-ROUNDED scale but computes the codes with the UNROUNDED one
+(cutlass_extensions/epilogue/fusion/sm100_visitor_store_tma_warpspecialized.hpp:141-148,567-591), unlike its own mma.sync
+kernels for H = 16/32/64 and for sm_120 (epilogue_quant.h:1664-1692) and unlike its test oracle (tests/nvfp4_test.py:132-170)
+-- which is why the reference's NVFP4 bar is 1e-1.  Ours follows the oracle / mma.sync arithmetic there: scales identical,
+4.8 % of the dequantised values differ, inside the reference's own tolerance.  See DESIGN.md section 4.
+Infrastructure trouble (library not built, child cannot start) is a skip, never a failure.
 """
 import os
 import subprocess
@@ -36,7 +43,6 @@ if not torch.cuda.is_available():
 import qutlass_b200 as Q  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-first_run = pytest.mark.xfail(strict=False, reason="first execution happens at round end; see the module docstring")
 
 
 def _reference(cases, timeout=240):
@@ -59,16 +65,17 @@ def _bf16_cpu(x: np.ndarray) -> torch.Tensor:
     return H.bf16_tensor_from_f32(x, device="cpu")
 
 
-@first_run
+# 512 rows: our butterfly kernel; 2048 rows at H = 128: our tcgen05 rotation kernel.  On the reference's side the two
+# Had-128 abs_max cases run ITS sm_100 tcgen05 kernels (fused_quantize_{mx,nv}_sm100.cu), all others its mma.sync kernels.
+QUANT_CASES = [("mx", "abs_max", 32, 1.0, 512), ("mx", "abs_max", 128, 1.0, 512), ("mx", "quest", 64, 1.0, 512),
+               ("mx", "quest", 128, 1.0, 512), ("mx", "abs_max", 128, 1.0, 2048), ("nv", "abs_max", 16, 6.0, 512),
+               ("nv", "abs_max", 128, 6.0, 512), ("nv", "quest", 64, 6.0, 512)]
+
+
 def test_quantisers_match_the_reference_kernels():
     k = 4096
     cases, ours = [], []
-    # 512 rows: our butterfly kernel; 2048 rows at H = 128: our tcgen05 rotation kernel (the reference's Had-128 abs_max
-    # case runs ITS sm_100 tcgen05 kernel, fused_quantize_mx_sm100.cu, the others its mma.sync kernels)
-    for fmt, method, had, gs, rows in [("mx", "abs_max", 32, 1.0, 512), ("mx", "abs_max", 128, 1.0, 512),
-                                       ("mx", "quest", 64, 1.0, 512), ("mx", "quest", 128, 1.0, 512),
-                                       ("mx", "abs_max", 128, 1.0, 2048), ("nv", "abs_max", 16, 6.0, 512),
-                                       ("nv", "abs_max", 128, 6.0, 512), ("nv", "quest", 64, 6.0, 512)]:
+    for fmt, method, had, gs, rows in QUANT_CASES:
         x = H.random_bf16((rows, k), seed=1000 + had + len(cases))         # randn * 25, like the reference's tests
         R = O.hadamard_matrix(had)
         cases.append({"op": "quantize", "fmt": fmt, "method": method, "x": _bf16_cpu(x), "R": _bf16_cpu(R), "gs": gs})
@@ -78,19 +85,24 @@ def test_quantisers_match_the_reference_kernels():
         else:
             q, sf = Q.fusedQuantizeNv(xt, Rt, torch.tensor([gs], device="cuda"), method=method)
         torch.cuda.synchronize()
-        ours.append((fmt, rows, H.u8_of(q), H.u8_of(sf)))
+        ours.append((H.u8_of(q), H.u8_of(sf)))
     ref = _reference(cases)
-    for (fmt, rows, q, sf), r, c in zip(ours, ref, cases):
-        group = 32 if fmt == "mx" else 16
-        cols = k // group
+    report = []
+    for (fmt, method, had, gs, rows), (q, sf), r in zip(QUANT_CASES, ours, ref):
+        cols = k // (32 if fmt == "mx" else 16)
         sf_o = sf.reshape(-1, sf.shape[-1])[:rows, :cols]
         sf_r = r["sf"].numpy()[:rows, :cols]
         dq = O.dequant_mx if fmt == "mx" else O.dequant_nv
         mism = float((dq(q, sf_o) != dq(r["q"].numpy().reshape(rows, -1), sf_r)).mean())
-        assert mism <= (2e-4 if fmt == "mx" else 1e-2), (c["fmt"], c["method"], c["R"].shape[0], mism)
+        sf_mism = float((sf_o != sf_r).mean())
+        # the one documented divergence (module docstring): the reference's sm_100 NVFP4 Had-128 abs_max kernel
+        quirk = (fmt, method, had) == ("nv", "abs_max", 128)
+        bar = 1e-1 if quirk else (2e-4 if fmt == "mx" else 1e-2)
+        report.append((fmt, method, had, rows, mism, sf_mism, bar))
+    bad = [r for r in report if r[4] > r[6] or r[5] > 1e-3]
+    assert not bad, report
 
 
-@first_run
 @pytest.mark.parametrize("fmt", ["mx", "nv"])
 def test_gemm_is_bit_identical_to_the_reference_kernel(fmt):
     """the reference's bit-exact shapes (tests/mxfp4_test.py:223-237,255-269; nvfp4_test.py:207-224) + a Llama FFN slice,
