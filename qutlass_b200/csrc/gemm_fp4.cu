@@ -713,6 +713,299 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------ hybrid tile pairs (explicit configuration (2, 448))
+// Every CTA pair walks "super tiles" of 256 rows x 448 columns as ONE 256-wide and ONE 192-wide tile.  A 256-column and a
+// 192-column fp32 accumulator plus the scale columns fit the 512 TMEM columns (256 + 192 + 24 / 48), so -- unlike the plain
+// (2,256) configuration, whose single accumulator costs ~1800 of ~10000 cycles per tile at the hand-off --
+// the MMA warp always finds a free accumulator: the tensor pipe never waits for a drain.  14336 = 32 x 448 and 28672 = 64 x 448,
+// so the Llama FFN shapes also lose the 11 %-full last round of tiles (512 super tiles over 74 pairs = 6.92 rounds).
+// Column order inside two neighbouring super tiles is W N | N W: every wide tile then starts on a 128-row scale block and
+// every narrow tile 0 or 64 rows into one (an even TMEM column shift; odd shifts fault, profiles/r01_notes.md).
+// Requires N % 448 == 0, K % 256 == 0, ldd % 8 == 0, FP4 kinds.  Same arithmetic as every other configuration (one fp32 chain
+// per output over K, alpha once, one RNE).  STATUS: written after round 1's GPU budget was spent -- compiled, NOT yet run;
+// reachable only through the explicit configuration or B200Q_GEMM_HYBRID=1.
+template <bool kNV>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_fp4_hybrid_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bw,
+                       const __grid_constant__ CUtensorMap tmap_bn, const __grid_constant__ CUtensorMap tmap_sfa,
+                       const __grid_constant__ CUtensorMap tmap_sfb, const __grid_constant__ CUtensorMap tmap_d64,
+                       const __grid_constant__ CUtensorMap tmap_d32, const GemmParams p) {
+  using Cfg = GemmCfg<2, 256, kNV>;          // stage layout of the (2,256) configuration: the narrow tile uses 96 of the 128 B rows
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int SFKB = Cfg::SFKB;
+  constexpr int NB = 2;                      // SFB row-blocks a tile touches (wide: 2 whole blocks; narrow: 192 rows from row 0 or 64)
+  constexpr int BNW = 256, BNN = 192, SUPER = BNW + BNN;
+  constexpr int ACC = 2;
+  static_assert(Cfg::NB == NB, "scale staging of the (2,256) stage");
+  static_assert(SUPER + Cfg::SF_COLS <= 512, "TMEM: wide + narrow accumulator + scales");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t stg_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = stg_base + Cfg::STG_TOTAL;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STG_TOTAL + 8 * (2 * STAGES + 2 * ACC));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();          // 0 = leader of the pair
+  const bool is_leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int total_supers = p.tiles_m * p.tiles_n;        // tiles_n = N / 448 here
+  // super tile `sup` (M fastest), half j (0 = wide, 1 = narrow) -> row block tm, first column n0
+  auto geom = [&](int sup, int j, int& tm, int& n0) {
+    tm = sup % p.tiles_m;
+    const int sn = sup / p.tiles_m;
+    const int base = sn * SUPER;
+    n0 = (sn & 1) ? (j == 0 ? base + BNN : base) : (j == 0 ? base : base + BNW);
+  };
+
+  pdl_launch_dependents();
+
+  // ------------------------------------------------------------------ setup
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_bw);
+    prefetch_tensormap(&tmap_bn);
+    prefetch_tensormap(&tmap_sfa);
+    prefetch_tensormap(&tmap_sfb);
+    prefetch_tensormap(&tmap_d64);
+    prefetch_tensormap(&tmap_d32);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < ACC; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kEpiWarps * 2);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<2>(tmem_slot, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_gen, 0);
+  const uint32_t tmem_sfa = tmem_base + SUPER;
+  const uint32_t tmem_sfb = tmem_sfa + Cfg::SFA_COLS;
+
+  if (warp == 0) {
+    // ===================== TMA producer (same protocol as gemm_fp4_kernel) =====================
+    const bool elected = elect_one();
+    const uint32_t full0 = mapa(bar_base, 0);
+    int my_supers = 0;
+    for (int sup = cluster_id; sup < total_supers; sup += num_clusters) ++my_supers;
+    const int total_kt = my_supers * 2 * p.k_tiles;
+    const int pre = total_kt < STAGES ? total_kt : STAGES;
+    struct Cursor { int sup, j, kt, m0, n0, nb0; };
+    auto set_tile = [&](Cursor& c) {
+      int tm, n0;
+      geom(c.sup, c.j, tm, n0);
+      c.m0 = (tm * 2 + (int)cta_rank) * BM;
+      c.n0 = n0;
+      c.nb0 = n0 + (int)cta_rank * ((c.j ? BNN : BNW) / 2);
+    };
+    auto advance = [&](Cursor& c) {
+      if (++c.kt == p.k_tiles) {
+        c.kt = 0;
+        if (c.j == 0) { c.j = 1; } else { c.j = 0; c.sup += num_clusters; }
+        set_tile(c);
+      }
+    };
+    auto load_weights = [&](int stage, const Cursor& c) {
+      const uint32_t sb = smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+      const uint32_t ssfb = sb + Cfg::B_BYTES + Cfg::SFA_BYTES;
+      const uint32_t fb = full0 + 8u * stage;
+      const uint32_t b_bytes = (uint32_t)((c.j ? BNN : BNW) / 2) * BK_BYTES;
+      const uint32_t tx = 2u * ((uint32_t)Cfg::A_BYTES + b_bytes + (uint32_t)Cfg::SFA_BYTES + (uint32_t)Cfg::SFB_BYTES);
+      if (is_leader) mbar_arrive_expect_tx(bar_base + 8u * stage, tx);
+      if (c.j) tma_load_2d<2>(sb, &tmap_bn, fb, c.kt * BK_BYTES, c.nb0);
+      else tma_load_2d<2>(sb, &tmap_bw, fb, c.kt * BK_BYTES, c.nb0);
+      tma_load_3d<2>(ssfb, &tmap_sfb, fb, 0, c.kt * SFKB, c.n0 / 128);
+    };
+    auto load_acts = [&](int stage, const Cursor& c) {
+      const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+      const uint32_t ssfa = sa + Cfg::A_BYTES + Cfg::B_BYTES;
+      const uint32_t fb = full0 + 8u * stage;
+      tma_load_2d<2>(sa, &tmap_a, fb, c.kt * BK_BYTES, c.m0);
+      tma_load_3d<2>(ssfa, &tmap_sfa, fb, 0, c.kt * SFKB, c.m0 / 128);
+    };
+    Cursor cur{cluster_id, 0, 0, 0, 0, 0};
+    set_tile(cur);
+    {
+      Cursor c = cur;
+      for (int g = 0; g < pre; ++g) {          // weights do not depend on the previous kernel in the stream
+        if (elected) load_weights(g, c);
+        advance(c);
+      }
+    }
+    pdl_wait();
+    for (int g = 0; g < pre; ++g) {
+      if (elected) load_acts(g, cur);
+      advance(cur);
+    }
+    __syncwarp();
+    int stage = (pre == STAGES) ? 0 : pre;
+    uint32_t phase = (pre == STAGES) ? 1 : 0;
+    for (int g = pre; g < total_kt; ++g) {
+      mbar_wait(bar_base + 8u * (STAGES + stage), phase ^ 1, 1);
+      if (elected) {
+        load_weights(stage, cur);
+        load_acts(stage, cur);
+      }
+      __syncwarp();
+      advance(cur);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    if (is_leader) {
+      // ===================== MMA issuer =====================
+      const bool elected = elect_one();
+      constexpr uint32_t idesc_w = make_idesc_fp4(BM * 2, BNW, !kNV);
+      constexpr uint32_t idesc_n = make_idesc_fp4(BM * 2, BNN, !kNV);
+      constexpr uint32_t kDescHiAB = (1024u >> 4) | (1u << 14) | (kLayoutSw128 << 29);
+      constexpr uint32_t kDescHiSF = (128u >> 4) | (1u << 14);
+      constexpr uint32_t kStage16 = Cfg::STAGE_BYTES >> 4;
+      const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t sfa_lo0 = ((smem_base & 0x3FFFFu) >> 4) + ((Cfg::A_BYTES + Cfg::B_BYTES) >> 4);
+      auto mk = [](uint32_t lo, uint32_t hi) {
+        uint64_t d;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+        return d;
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc_phase0 = 0, acc_phase1 = 0;
+      for (int sup = cluster_id; sup < total_supers; sup += num_clusters) {
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+          int tm_, n0;
+          geom(sup, j, tm_, n0);
+          const uint32_t sfb_shift = (uint32_t)((n0 % 128) / 32);     // 0 or 2
+          mbar_wait(tempty_bar(j), (j ? acc_phase1 : acc_phase0) ^ 1, 2);
+          tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + (j ? (uint32_t)BNW : 0u);
+          const uint32_t tsfb = tmem_sfb + sfb_shift;
+          const uint32_t idesc_base = j ? idesc_n : idesc_w;
+          for (int kt = 0; kt < p.k_tiles; ++kt) {
+            mbar_wait_spin(bar_base + 8u * stage, phase);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + stage * kStage16;
+            const uint32_t b_lo = a_lo + (Cfg::A_BYTES >> 4);
+            const uint32_t sfa_lo = sfa_lo0 + stage * kStage16;
+            const uint32_t sfb_lo = sfa_lo + (Cfg::SFA_BYTES >> 4);
+            if (elected) {
+              auto copy_chunk = [&](int b) {
+                tmem_cp_32x128b_warpx4<2>(tmem_sfa + b * 4, mk(sfa_lo + b * 32, kDescHiSF));
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb)
+                  tmem_cp_32x128b_warpx4<2>(tmem_sfb + b * (4 * NB) + nb * 4, mk(sfb_lo + (nb * SFKB + b) * 32, kDescHiSF));
+              };
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) {
+                const uint32_t chunk = kNV ? kb : (kb >> 1);
+                if (kNV || (kb & 1) == 0) copy_chunk((int)chunk);
+                const uint32_t sf_id = kNV ? 0u : (uint32_t)((kb & 1) * 2);
+                mma_fp4_block_scaled<2, kNV, false>(tmem_acc, mk(a_lo + kb * 2, kDescHiAB), mk(b_lo + kb * 2, kDescHiAB),
+                                                    idesc_base | (sf_id << 4) | (sf_id << 29), tmem_sfa + chunk * 4,
+                                                    tsfb + chunk * (4 * NB), (kb > 0) ? 1u : (kt > 0 ? 1u : 0u));
+              }
+              tc_commit<2>(bar_base + 8u * (STAGES + stage), (uint16_t)3);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (elected) tc_commit<2>(tfull_bar(j), (uint16_t)3);
+          __syncwarp();
+          if (j) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9): 4 TMEM lane quarters x 2 column halves of the tile =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const uint32_t stg = stg_base + ew * Cfg::STG_BYTES;
+    uint32_t acc_phase0 = 0, acc_phase1 = 0;
+    const uint32_t tempty_leader = mapa(tempty_bar(0), 0);
+    pdl_wait();
+    const float alpha = __ldg(p.alpha);
+    // convert + stage + TMA-store one chunk of CH (64 or 32) columns held in rr[0 .. CH)
+    auto store_chunk = [&](auto ch_tag, const uint32_t* rr, int cx, int cy) {
+      constexpr int CH = decltype(ch_tag)::value;
+      constexpr int PIECES = CH / 8;
+      if (lane == 0) bulk_wait_group_read<0>();      // staging buffer free again
+      __syncwarp();
+#pragma unroll
+      for (int jj = 0; jj < PIECES; ++jj) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(rr[jj * 8 + 2 * e]) * alpha,
+                                                    __uint_as_float(rr[jj * 8 + 2 * e + 1]) * alpha);
+          w[e] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        const int phys = (CH == 64) ? (jj ^ (lane & 7)) : (jj ^ ((lane >> 1) & 3));
+        const uint32_t addr = stg + lane * (CH * 2) + phys * 16;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CH == 64) tma_store_2d(&tmap_d64, stg, cx, cy);
+        else tma_store_2d(&tmap_d32, stg, cx, cy);
+        bulk_commit_group();
+      }
+    };
+    for (int sup = cluster_id; sup < total_supers; sup += num_clusters) {
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        int tm, n0;
+        geom(sup, j, tm, n0);
+        const int m0 = (tm * 2 + (int)cta_rank) * BM;
+        const int cols = (j ? BNN : BNW) / 2;            // 128 or 96 columns per warp
+        const int col0 = half * cols;
+        mbar_wait(tfull_bar(j), j ? acc_phase1 : acc_phase0, 6);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (j ? (uint32_t)BNW : 0u) + (uint32_t)col0 + ((uint32_t)(q * 32) << 16);
+        uint32_t r[128];
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_32x32b_x32(taddr + 32, r + 32);
+        tmem_ld_32x32b_x32(taddr + 64, r + 64);
+        if (j == 0) tmem_ld_32x32b_x32(taddr + 96, r + 96);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + 8u * j);      // accumulator j is free again
+        if (j) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+        store_chunk(std::integral_constant<int, 64>{}, r, n0 + col0, m0 + q * 32);
+        if (j == 0) store_chunk(std::integral_constant<int, 64>{}, r + 64, n0 + col0 + 64, m0 + q * 32);
+        else store_chunk(std::integral_constant<int, 32>{}, r + 64, n0 + col0 + 64, m0 + q * 32);
+      }
+    }
+    if (lane == 0) bulk_wait_group<0>();
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<2>(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -879,6 +1172,63 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   return 0;
 }
 
+// hybrid tile pairs (gemm_fp4_hybrid_kernel): explicit configuration (2, 448)
+static bool hybrid_eligible(int M, int N, int K, int ldd, int kind) {
+  return (kind == B200Q_KIND_MXF4 || kind == B200Q_KIND_NVF4) && M > 0 && N % 448 == 0 && K % 256 == 0 && ldd % 8 == 0;
+}
+
+template <bool kNV>
+static int launch_gemm_hybrid(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D,
+                              int M, int N, int K, int ldd, cudaStream_t stream) {
+  using Cfg = GemmCfg<2, 256, kNV>;
+  auto kern = gemm_fp4_hybrid_kernel<kNV>;
+  static std::atomic<unsigned long long> smem_attr_done{0};   // per instantiation, one bit per device
+  if (int rc_attr = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, smem_attr_done)) return rc_attr;
+  const int group = kNV ? 16 : 32;
+  const int64_t sf_col_blocks = ceil_div(ceil_div(K, group), 4);
+  CUtensorMap ta, tbw, tbn, tsa, tsb, td64, td32;
+  int rc;
+  if ((rc = make_operand_tmap(&ta, A, M, K / 2, 128, "A"))) return rc;
+  if ((rc = make_operand_tmap(&tbw, B, N, K / 2, 128, "B (wide tile)"))) return rc;
+  if ((rc = make_operand_tmap(&tbn, B, N, K / 2, 96, "B (narrow tile)"))) return rc;
+  if ((rc = make_sf_tmap(&tsa, SFA, ceil_div(M, 128), sf_col_blocks, Cfg::SFKB, 1, "SFA"))) return rc;
+  if ((rc = make_sf_tmap(&tsb, SFB, ceil_div(N, 128), sf_col_blocks, Cfg::SFKB, 2, "SFB"))) return rc;
+  if ((rc = make_d_tmap(&td64, D, M, N, ldd, 64))) return rc;
+  if ((rc = make_d_tmap(&td32, D, M, N, ldd, 32))) return rc;
+  GemmParams p;
+  p.alpha = alpha;
+  p.d = (__nv_bfloat16*)D;
+  p.M = M; p.N = N; p.K = K;
+  p.ldd = ldd;
+  p.tiles_m = (int)ceil_div(M, BM * 2);
+  p.tiles_n = N / 448;                    // super tiles along N
+  p.k_tiles = K / 256;
+  p.tma_store = 1;
+  p.flags = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 2;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  int clusters = num_sms() / 2;
+  const int total = p.tiles_m * p.tiles_n;
+  if (clusters > total) clusters = total;
+  cfg.gridDim = dim3((unsigned)(clusters * 2));
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  {
+    const char* e = getenv("B200Q_NO_PDL");
+    cfg.numAttrs = (e && e[0] == '1') ? 1 : 2;
+  }
+  B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tbw, tbn, tsa, tsb, td64, td32, p));
+  return 0;
+}
+
 template <bool kNV, int kF8>
 static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B, const void* SFA, const void* SFB,
                         const float* alpha, void* D, int M, int N, int K, int ldd, cudaStream_t s) {
@@ -887,6 +1237,15 @@ static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B
     if (cta_group == 1 && block_n == 128 && M <= 16) return launch_gemm<1, 128, kNV, 16, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
     if (cta_group == 1 && block_n == 128 && M <= 32) return launch_gemm<1, 128, kNV, 32, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
     if (cta_group == 1 && block_n == 128 && M <= 64) return launch_gemm<1, 128, kNV, 64, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+  }
+  if constexpr (kF8 == 0) {
+    if (cta_group == 2 && block_n == 448) {      // hybrid 256 + 192 tile pairs (compiled, not yet measured: explicit / opt-in only)
+      if (!hybrid_eligible(M, N, K, ldd, kNV ? B200Q_KIND_NVF4 : B200Q_KIND_MXF4)) {
+        set_error("configuration (2, 448) needs N %% 448 == 0, K %% 256 == 0 and a row pitch that is a multiple of 8 (N=%d K=%d ldd=%d)", N, K, ldd);
+        return B200Q_EINVAL;
+      }
+      return launch_gemm_hybrid<kNV>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+    }
   }
 #define B200Q_CASE(CG, BNV) \
   if (cta_group == CG && block_n == BNV) return launch_gemm<CG, BNV, kNV, 128, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
@@ -940,6 +1299,11 @@ static GemmPlan plan_auto(int M, int N, int K, int kind) {
         if (best < 0 || cost < best) { best = cost; block_n = bn; }
       }
     }
+  }
+  {
+    // opt-in (B200Q_GEMM_HYBRID=1): the 256 + 192 tile pairs wherever the CTA-pair plan applies and the shape allows them
+    const char* hyb = getenv("B200Q_GEMM_HYBRID");
+    if (hyb && hyb[0] == '1' && cta_group == 2 && hybrid_eligible(M, N, K, N, kind)) block_n = 448;
   }
   pl.cta_group = cta_group;
   pl.block_n = block_n;

@@ -111,3 +111,23 @@ def test_host_entry_slab_schedule_without_a_gpu(lib_path):
         assert all(x % 128 == 0 for x in b[:-1])
     assert lib.b200q_linear_host_slabs(0, (ctypes.c_int * 17)(), 17) < 0
     assert lib.b200q_linear_host_slabs(4096, (ctypes.c_int * 4)(), 4) < 0       # not enough room for the bounds
+
+
+def test_hybrid_tile_pairs_are_opt_in(lib_path, monkeypatch):
+    """the 256 + 192 tile-pair configuration (2, 448) is compiled but unmeasured: the planner only picks it with
+    B200Q_GEMM_HYBRID=1 and only where N % 448 == 0 and K % 256 == 0 (the Llama FFN up-projections)."""
+    from qutlass_b200 import _lib
+    lib = _lib.load()
+
+    def plan(m, n, k, kind=0):
+        cg, bn = ctypes.c_int(0), ctypes.c_int(0)
+        assert lib.b200q_gemm_fp4_plan(m, n, k, kind, ctypes.byref(cg), ctypes.byref(bn)) == 0
+        return cg.value, bn.value
+
+    monkeypatch.delenv("B200Q_GEMM_HYBRID", raising=False)
+    assert plan(4096, 14336, 4096) == (2, 256)
+    monkeypatch.setenv("B200Q_GEMM_HYBRID", "1")
+    assert plan(4096, 14336, 4096) == (2, 448) and plan(2048, 28672, 8192, 1) == (2, 448)
+    assert plan(4096, 4096, 14336) == (2, 256)          # N % 448 != 0
+    assert plan(128, 14336, 4096) == (1, 128)           # the weight-streaming regime keeps its single-CTA tiles
+    assert plan(4096, 14336, 4096, 2)[1] != 448         # MXFP8: FP4 kinds only

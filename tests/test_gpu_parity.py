@@ -321,6 +321,49 @@ def test_gemm_bit_exact_vs_oracle(kind, cfg, shape):
         assert rel <= REL_TOL and mism <= 1e-3, (mism, rel)
 
 
+# The hybrid 256 + 192 tile pairs (configuration (2, 448), gemm_fp4_hybrid_kernel) were written after round 1's GPU budget
+# was spent: compiled, never run.  An unproven tcgen05 kernel can hang, so these cases only run when asked for
+# (B200Q_TEST_HYBRID=1) -- the first thing to do with a GPU in round 2, under a `timeout`.
+import os  # noqa: E402
+hybrid_opt_in = pytest.mark.skipif(os.environ.get("B200Q_TEST_HYBRID") != "1",
+                                   reason="unproven kernel: set B200Q_TEST_HYBRID=1 (and wrap the run in a timeout)")
+
+
+@hybrid_opt_in
+@pytest.mark.parametrize("kind", ["mx", "nv"])
+@pytest.mark.parametrize("shape", [(256, 448, 256), (256, 896, 512), (300, 1344, 1024), (1, 448, 4096), (700, 2240, 2048)])
+def test_gemm_hybrid_bit_exact_vs_oracle(kind, shape):
+    m, n, k = shape
+    aq, asf = H.random_fp4_operand(m, k, kind, seed=m + 3, sf_mode="narrow")
+    bq, bsf = H.random_fp4_operand(n, k, kind, seed=n + 4, sf_mode="narrow")
+    want = H.gemm_oracle_bits(aq, asf, bq, bsf, kind, 1.0)
+    got = H.run_gemm(aq, asf, bq, bsf, kind, 1.0, cfg=(2, 448))
+    mism, rel = H.compare_bits(got, want)
+    if kind == "mx":
+        assert mism == 0.0, (mism, rel)
+    else:
+        assert rel <= REL_TOL and mism <= 1e-3, (mism, rel)
+    np.testing.assert_array_equal(got, H.run_gemm(aq, asf, bq, bsf, kind, 1.0, cfg=(2, 256)))
+
+
+@hybrid_opt_in
+@pytest.mark.parametrize("kind", ["mx", "nv"])
+def test_gemm_hybrid_full_size_identical(kind):
+    m, n, k = 4096, 14336, 4096
+    aq, asf = H.random_fp4_operand(m, k, kind, seed=71, sf_mode="wide")
+    bq, bsf = H.random_fp4_operand(n, k, kind, seed=72, sf_mode="wide")
+    np.testing.assert_array_equal(H.run_gemm(aq, asf, bq, bsf, kind, 1.0 / 9.0, cfg=(2, 448)),
+                                  H.run_gemm(aq, asf, bq, bsf, kind, 1.0 / 9.0, cfg=(2, 256)))
+
+
+@hybrid_opt_in
+def test_gemm_hybrid_rejects_ineligible_shapes():
+    aq, asf = H.random_fp4_operand(128, 256, "mx", seed=1)
+    bq, bsf = H.random_fp4_operand(512, 256, "mx", seed=2)
+    with pytest.raises(Exception, match="448"):
+        H.run_gemm(aq, asf, bq, bsf, "mx", 1.0, cfg=(2, 448))
+
+
 @pytest.mark.parametrize("kind", ["mx", "nv"])
 def test_gemm_wide_dynamic_range_within_tolerance(kind):
     m, n, k = 300, 1000, 2176
