@@ -898,7 +898,7 @@ gemm_fp4_hybrid_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           const uint32_t tsfb = tmem_sfb + sfb_shift;
           const uint32_t idesc_base = j ? idesc_n : idesc_w;
           for (int kt = 0; kt < p.k_tiles; ++kt) {
-            mbar_wait_spin(bar_base + 8u * stage, phase);
+            mbar_wait(bar_base + 8u * stage, phase, 3);   // time-out variant until the kernel has been proven on hardware (a lost arrival traps instead of hanging)
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + stage * kStage16;
             const uint32_t b_lo = a_lo + (Cfg::A_BYTES >> 4);
