@@ -46,6 +46,12 @@ typedef struct CUstream_st* b200q_stream_t;
  * butterfly kernel's scalar fallback.  Large Hadamard inputs take the tcgen05 kernel too (it streams at the HBM rate
  * for any R); the choice never changes the results beyond fp32 summation order. */
 #define B200Q_ROT_GENERIC 0x200
+/* b200q_quantize_nv only, opt-in: compute the abs_max Hadamard-128 codes with the scale BEFORE its e4m3 rounding, which is what
+ * the reference's sm_100-only kernel does (bindings.cpp:413-415 -> fused_quantize_nv_sm100.cu;
+ * cutlass_extensions/epilogue/fusion/sm100_visitor_store_tma_warpspecialized.hpp:141-148,567-591) -- unlike its mma.sync kernels
+ * (H = 16/32/64, sm_120) and its test oracle, which this library follows by default.  Ignored for other methods / sizes.
+ * UNMEASURED: added after round 1's GPU budget was spent. */
+#define B200Q_NV_SM100_CODES 0x400
 
 #define B200Q_KIND_MXF4 0      /* e2m1 x e2m1, ue8m0 scales, group 32          */
 #define B200Q_KIND_NVF4 1      /* e2m1 x e2m1, ue4m3 scales, group 16          */

@@ -273,8 +273,13 @@ def quantize_mx(x, R, method: str = "quest", arithmetic: str = "kernel"):
 
 
 # --------------------------------------------------------------------------- NV quantise
-def quantize_nv(x, R, global_scale: float, method: str = "abs_max", arithmetic: str = "kernel"):
+def quantize_nv(x, R, global_scale: float, method: str = "abs_max", arithmetic: str = "kernel", sm100_codes: bool = False):
     """Fused rotate + NVFP4 quantise (group 16, e4m3 scale, fp32 global scale).
+
+    sm100_codes (abs_max only): the arithmetic of the reference's sm_100-ONLY Hadamard-128 kernel
+    (sm100_visitor_store_tma_warpspecialized.hpp:141-148,567-591): the stored scale is e4m3-rounded as usual but the codes
+    are computed with the UNROUNDED scale, q = e2m1(xh * rcp(sfv * rcp(gs))), sfv = gs * (amax * rcp(6)).  Observed on B200:
+    that kernel differs from the one below in 4.8 % of the dequantised values (profiles/r01_ref_quant_diag.jsonl).
 
     kernel flavour restates EpilogueQuantNv::op_16 (epilogue_quant.h:1604-1692):
       abs_max: SF = e4m3(gs * (amax * rcp(6)));  q = e2m1(xh * rcp(SF * rcp(gs)))  (0 if SF == 0)
@@ -300,7 +305,7 @@ def quantize_nv(x, R, global_scale: float, method: str = "abs_max", arithmetic: 
             amax = np.abs(xh).max(axis=-1).astype(np.float32)
             sfv = _f32(gs * _f32(amax * _f32(one / np.float32(6))))
             sf = e4m3_encode(sfv)
-            sfq = e4m3_decode(sf).astype(np.float32)
+            sfq = sfv if sm100_codes else e4m3_decode(sf).astype(np.float32)
             with np.errstate(divide="ignore", invalid="ignore"):
                 out_scale = np.where(sfq != 0, _f32(one / _f32(sfq * _f32(one / gs))), np.float32(0)).astype(np.float32)
         else:

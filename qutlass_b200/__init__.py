@@ -17,6 +17,7 @@ device every compute entry point raises.
 """
 from __future__ import annotations
 
+import os
 from typing import Literal
 
 import torch
@@ -34,6 +35,7 @@ __all__ = [
 METHOD_QUEST, METHOD_ABSMAX = 0, 1
 ROT_TRUSTED_HADAMARD = 0x100   # include/b200q.h: B200Q_ROT_TRUSTED_HADAMARD
 ROT_GENERIC = 0x200            # include/b200q.h: B200Q_ROT_GENERIC (known non-Hadamard -> tensor-core rotation)
+NV_SM100_CODES = 0x400         # include/b200q.h: B200Q_NV_SM100_CODES (opt-in reference-sm_100 arithmetic, NVFP4 abs_max H=128)
 KIND_MXF4, KIND_NVF4, KIND_MXF8, KIND_MXF8_NN = 0, 1, 2, 3
 
 
@@ -231,11 +233,16 @@ def _quantize_nv_into(a, r, out, out_sf, out_sf_blocked, global_scale, method: i
     _check(global_scale.dim() == 1 and global_scale.size(0) == 1, "global_scale must be a scalar")
     _check(had in (16, 32, 64, 128), f"Unsupported rotation size {had}; expected 16, 32, 64, or 128.")
     _check(a.size(-1) % 32 == 0, "last dimension of A must be a multiple of 32")
+    flags = method | _rotation_hint(r)
+    if had == 128 and method == METHOD_ABSMAX and os.environ.get("B200Q_NV128_REFERENCE_CODES") == "1":
+        # opt-in (unmeasured): the reference's sm_100-only kernel for this one case derives the codes from the UNROUNDED scale
+        # (include/b200q.h: B200Q_NV_SM100_CODES); default = its other kernels' / its test oracle's arithmetic
+        flags |= NV_SM100_CODES
     with _DeviceGuard(a.device):
         _lib.check(_lib.load().b200q_quantize_nv(
             a.data_ptr(), r.data_ptr(), out.data_ptr(), out_sf.data_ptr() if out_sf is not None else None,
             out_sf_blocked.data_ptr() if out_sf_blocked is not None else None, global_scale.data_ptr(),
-            a.numel(), a.size(-1), had, method | _rotation_hint(r), _stream(a)))
+            a.numel(), a.size(-1), had, flags, _stream(a)))
 
 
 def fusedQuantizeMx(a: torch.Tensor, b: torch.Tensor, *, method: Literal["quest", "abs_max"] = "quest",

@@ -610,8 +610,15 @@ extern "C" int b200q_quantize_nv(const void* x_bf16, const void* rot_bf16, void*
   p.gs = global_scale_dev;
   p.trust_hadamard = (method & B200Q_ROT_TRUSTED_HADAMARD) ? 1 : 0;
   g_rot_generic = (method & B200Q_ROT_GENERIC) != 0 && !p.trust_hadamard;
-  method &= ~(B200Q_ROT_TRUSTED_HADAMARD | B200Q_ROT_GENERIC);
+  const bool sm100_codes = (method & B200Q_NV_SM100_CODES) != 0;
+  method &= ~(B200Q_ROT_TRUSTED_HADAMARD | B200Q_ROT_GENERIC | B200Q_NV_SM100_CODES);
   cudaStream_t s = (cudaStream_t)stream;
+  // opt-in: bit-compatibility with the ONE case where the reference's sm_100 dispatch deviates from its other kernels and
+  // from its test oracle (abs_max, Hadamard-128: bindings.cpp:413-415 -> fused_quantize_nv_sm100.cu).  Always the tcgen05 kernel.
+  if (sm100_codes && method == B200Q_METHOD_ABSMAX && had == 128) {
+    B200Q_REQUIRE(quantize_tc_eligible(p, had, true), "B200Q_NV_SM100_CODES needs 16-byte aligned rotation / 8-byte aligned scale buffers");
+    return launch_quantize_tc(p, had, true, method, s, true);
+  }
   if (method == B200Q_METHOD_QUEST) return dispatch_had<true, B200Q_METHOD_QUEST, false>(had, p, s);
   if (method == B200Q_METHOD_ABSMAX) return dispatch_had<true, B200Q_METHOD_ABSMAX, false>(had, p, s);
   set_error("invalid method %d, must be quest (0) or abs_max (1)", method);

@@ -132,3 +132,26 @@ def test_gemm_is_bit_identical_to_the_reference_kernel(fmt):
         want = r["d"].numpy().view(np.uint16)
         mism, rel = H.compare_bits(got, want)
         assert mism == 0.0, (fmt, tuple(c["a"].shape), tuple(c["b"].shape), mism, rel)
+
+
+@pytest.mark.skipif(os.environ.get("B200Q_TEST_NV128_QUIRK") != "1",
+                    reason="opt-in arithmetic added after round 1's GPU budget was spent: set B200Q_TEST_NV128_QUIRK=1")
+def test_nv128_reference_codes_flag_matches_the_reference_sm100_kernel(monkeypatch):
+    """B200Q_NV128_REFERENCE_CODES=1 (C-ABI: B200Q_NV_SM100_CODES): NVFP4 abs_max Hadamard-128 with the codes taken from the
+    unrounded scale -- then the one documented divergence from the reference's sm_100 kernel must vanish too."""
+    rows, k, had, gs = 512, 4096, 128, 6.0
+    x = H.random_bf16((rows, k), seed=1134)
+    R = O.hadamard_matrix(had)
+    monkeypatch.setenv("B200Q_NV128_REFERENCE_CODES", "1")
+    q, sf = Q.fusedQuantizeNv(H.bf16_tensor_from_f32(x), H.bf16_tensor_from_f32(R), torch.tensor([gs], device="cuda"),
+                              method="abs_max")
+    torch.cuda.synchronize()
+    ref = _reference([{"op": "quantize", "fmt": "nv", "method": "abs_max", "x": _bf16_cpu(x), "R": _bf16_cpu(R), "gs": gs}])[0]
+    cols = k // 16
+    sf_o = H.u8_of(sf).reshape(-1, sf.shape[-1])[:rows, :cols]
+    sf_r = ref["sf"].numpy()[:rows, :cols]
+    np.testing.assert_array_equal(sf_o, sf_r)
+    mism = float((O.dequant_nv(H.u8_of(q), sf_o) != O.dequant_nv(ref["q"].numpy().reshape(rows, -1), sf_r)).mean())
+    assert mism <= 2e-4, mism
+    want = O.quantize_nv(x, R, gs, "abs_max", sm100_codes=True)
+    assert float((O.dequant_nv(H.u8_of(q), sf_o) != O.dequant_nv(want["q"].reshape(rows, -1), want["sf"].reshape(rows, cols))).mean()) <= 1e-2
