@@ -73,6 +73,28 @@ def run_parity(workdir: str) -> None:
             q, sf = _quantize(torch, ops, case["fmt"], case["method"], x, R, gs)
             torch.cuda.synchronize()
             out.append({"q": q.cpu(), "sf": sf.view(torch.uint8).cpu()})
+        elif case["op"] == "quantize_mask":
+            # fusedQuantizeMx(..., method="quest", return_mask=True) (qutlass/__init__.py:166-172)
+            x, R = case["x"].to(dev), case["R"].to(dev)
+            rows, k = x.numel() // x.size(-1), x.size(-1)
+            pr, pc = _padded(rows, k // 32)
+            q = torch.empty(*x.shape[:-1], k // 2, dtype=torch.uint8, device=dev)
+            sf = torch.empty(pr, pc, dtype=torch.float8_e8m0fnu, device=dev)
+            mask = torch.empty(*x.shape[:-1], k // 8, dtype=torch.uint8, device=dev)
+            ops.fusedQuantizeMxQuestWithMask(x, R, q, sf, mask)
+            torch.cuda.synchronize()
+            out.append({"q": q.cpu(), "sf": sf.view(torch.uint8).cpu(), "mask": mask.cpu()})
+        elif case["op"] == "gemm_f8":
+            # matmul_mxf8_bf16_tn / _nn (qutlass/__init__.py:134-146): e4m3 operands, e8m0 blocked scales
+            a = case["a"].to(dev).view(torch.float8_e4m3fn)
+            b = case["b"].to(dev).view(torch.float8_e4m3fn)
+            a_sf = case["a_sf"].to(dev).view(torch.float8_e8m0fnu)
+            b_sf = case["b_sf"].to(dev).view(torch.float8_e8m0fnu)
+            alpha = torch.tensor([case["alpha"]], dtype=torch.float32, device=dev)
+            op = ops.matmul_mxf8_bf16_nn if case.get("nn") else ops.matmul_mxf8_bf16_tn
+            d = op(a, b, a_sf, b_sf, alpha)
+            torch.cuda.synchronize()
+            out.append({"d": d.view(torch.int16).cpu()})
         elif case["op"] == "gemm":
             sf_dt = torch.float8_e8m0fnu if case["fmt"] == "mx" else torch.float8_e4m3fn
             a, b = case["a"].to(dev), case["b"].to(dev)

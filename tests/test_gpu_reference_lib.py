@@ -134,6 +134,80 @@ def test_gemm_is_bit_identical_to_the_reference_kernel(fmt):
         assert mism == 0.0, (fmt, tuple(c["a"].shape), tuple(c["b"].shape), mism, rel)
 
 
+# ----------------------------------------------------------------------------- wider comparisons, not yet observed
+# Written after the last GPU-minute of round 1: their first execution is the driver's round-end run, so they report
+# (XPASS / XFAIL) without gating the suite; round 2 reads the outcome and makes them strict.
+unobserved = pytest.mark.xfail(strict=False, reason="first execution at the end of round 1 -- reported, not gating")
+
+
+@unobserved
+def test_remaining_quantiser_sizes_match_the_reference_kernels():
+    k, rows = 2048, 256
+    todo = [("mx", "quest", 32, 1.0), ("mx", "abs_max", 64, 1.0), ("nv", "abs_max", 32, 6.0), ("nv", "abs_max", 64, 6.0),
+            ("nv", "quest", 16, 6.0), ("nv", "quest", 32, 6.0), ("nv", "quest", 128, 6.0), ("nv", "abs_max", 64, 1.0)]
+    cases, ours = [], []
+    for i, (fmt, method, had, gs) in enumerate(todo):
+        x = H.random_bf16((rows, k), seed=2000 + i)
+        R = O.hadamard_matrix(had)
+        cases.append({"op": "quantize", "fmt": fmt, "method": method, "x": _bf16_cpu(x), "R": _bf16_cpu(R), "gs": gs})
+        xt, Rt = H.bf16_tensor_from_f32(x), H.bf16_tensor_from_f32(R)
+        q, sf = (Q.fusedQuantizeMx(xt, Rt, method=method) if fmt == "mx" else
+                 Q.fusedQuantizeNv(xt, Rt, torch.tensor([gs], device="cuda"), method=method))
+        torch.cuda.synchronize()
+        ours.append((H.u8_of(q), H.u8_of(sf)))
+    ref = _reference(cases)
+    report = []
+    for (fmt, method, had, gs), (q, sf), r in zip(todo, ours, ref):
+        cols = k // (32 if fmt == "mx" else 16)
+        sf_o = sf.reshape(-1, sf.shape[-1])[:rows, :cols]
+        sf_r = r["sf"].numpy()[:rows, :cols]
+        dq = O.dequant_mx if fmt == "mx" else O.dequant_nv
+        mism = float((dq(q, sf_o) != dq(r["q"].numpy().reshape(rows, -1), sf_r)).mean())
+        report.append((fmt, method, had, gs, mism, float((sf_o != sf_r).mean())))
+    assert all(m <= (2e-4 if f == "mx" else 1e-2) and s <= 1e-3 for f, _, _, _, m, s in report), report
+
+
+@unobserved
+def test_clip_mask_matches_the_reference_kernel():
+    """fusedQuantizeMx(method="quest", return_mask=True): codes, scales and the packed clip mask (Hadamard-32: the only size
+    the reference's mask kernel supports, bindings.cpp:277-286)"""
+    rows, k, had = 256, 2048, 32
+    x = H.random_bf16((rows, k), seed=2100)
+    R = O.hadamard_matrix(had)
+    q, sf, mask = Q.fusedQuantizeMx(H.bf16_tensor_from_f32(x), H.bf16_tensor_from_f32(R), method="quest", return_mask=True)
+    torch.cuda.synchronize()
+    r = _reference([{"op": "quantize_mask", "x": _bf16_cpu(x), "R": _bf16_cpu(R)}])[0]
+    cols = k // 32
+    sf_o = H.u8_of(sf).reshape(-1, sf.shape[-1])[:rows, :cols]
+    sf_r = r["sf"].numpy()[:rows, :cols]
+    assert float((sf_o != sf_r).mean()) <= 1e-4
+    assert float((O.dequant_mx(H.u8_of(q), sf_o) != O.dequant_mx(r["q"].numpy().reshape(rows, -1), sf_r)).mean()) <= 2e-4
+    assert float((H.u8_of(mask).reshape(-1) != r["mask"].numpy().reshape(-1)).mean()) <= 2e-4
+
+
+@unobserved
+@pytest.mark.parametrize("nn", [False, True])
+def test_mxfp8_gemm_is_bit_identical_to_the_reference_kernel(nn):
+    cases, ours = [], []
+    for i, (m, n, k) in enumerate([(16, 1024, 4096), (496, 512, 2048), (1024, 1536, 512)]):
+        aq, asf = H.random_f8_operand(m, k, seed=300 + i)
+        bq, bsf = H.random_f8_operand(n, k, seed=400 + i)
+        a_blk, b_blk = H.blocked_sf(asf), H.blocked_sf(bsf)
+        a_np = np.ascontiguousarray(aq.T) if nn else aq                      # nn: A stored [K, M]
+        a = torch.from_numpy(a_np).cuda().view(torch.float8_e4m3fn)
+        b = torch.from_numpy(bq).cuda().view(torch.float8_e4m3fn)
+        mm = Q.matmul_mxf8_bf16_nn if nn else Q.matmul_mxf8_bf16_tn
+        d = mm(a, b, H.sf_torch(a_blk, "mx"), H.sf_torch(b_blk, "mx"), torch.tensor([0.5], device="cuda"))
+        torch.cuda.synchronize()
+        ours.append(H.bf16_bits_of(d))
+        cases.append({"op": "gemm_f8", "nn": nn, "a": torch.from_numpy(a_np), "b": torch.from_numpy(bq),
+                      "a_sf": torch.from_numpy(a_blk), "b_sf": torch.from_numpy(b_blk), "alpha": 0.5})
+    ref = _reference(cases)
+    for got, r, c in zip(ours, ref, cases):
+        mism, rel = H.compare_bits(got, r["d"].numpy().view(np.uint16))
+        assert mism == 0.0, (nn, tuple(c["a"].shape), tuple(c["b"].shape), mism, rel)
+
+
 @pytest.mark.skipif(os.environ.get("B200Q_TEST_NV128_QUIRK") != "1",
                     reason="opt-in arithmetic added after round 1's GPU budget was spent: set B200Q_TEST_NV128_QUIRK=1")
 def test_nv128_reference_codes_flag_matches_the_reference_sm100_kernel(monkeypatch):
