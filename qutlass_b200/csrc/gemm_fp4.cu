@@ -1142,8 +1142,9 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   int clusters = num_sms() / kClusterCtas;
   if constexpr (kMC != 0) {
     // clusters of 4 must sit inside one GPC: ask how many are co-resident (a persistent grid must not exceed that)
-    static int max_clusters[64] = {0};     // per device
-    int& mc = max_clusters[current_device() & 63];
+    static std::atomic<int> max_clusters[64];     // per device (zero-initialised); racing first calls store the same value
+    std::atomic<int>& mc_a = max_clusters[current_device() & 63];
+    int mc = mc_a.load(std::memory_order_acquire);
     if (mc == 0) {
       cfg.gridDim = dim3((unsigned)(clusters * kClusterCtas));
       cfg.attrs = attrs;
@@ -1151,6 +1152,7 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
       int n = 0;
       B200Q_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
       mc = n > 0 ? n : 1;
+      mc_a.store(mc, std::memory_order_release);
       if (getenv("B200Q_GEMM_VERBOSE")) fprintf(stderr, "b200q: clusters of %d CTAs co-resident: %d (SMs %d)\n", kClusterCtas, n, num_sms());
     }
     if (clusters > mc) clusters = mc;

@@ -474,10 +474,15 @@ static int resident_ctas_per_sm(K kern, int threads, int dyn_smem) {
 template <int HAD, bool NV, int METHOD, bool MASK>
 static int launch(const QuantParams& p, cudaStream_t stream) {
   // exactly one persistent wave: SMs x (resident CTAs per SM as the occupancy calculator reports it)
-  static int occ_trust = 0, occ_check = 0;
-  if (!occ_trust) {
+  // occupancy of the two instantiations: a property of the (identical) devices of the node; racing first calls compute the
+  // same values, the atomics only keep the publication well-defined
+  static std::atomic<int> occ_trust_a{0}, occ_check_a{0};
+  int occ_trust = occ_trust_a.load(std::memory_order_acquire), occ_check = occ_check_a.load(std::memory_order_acquire);
+  if (!occ_trust || !occ_check) {
     occ_trust = resident_ctas_per_sm(quantize_kernel<HAD, NV, METHOD, MASK, true>, kThreads, 0);
     occ_check = resident_ctas_per_sm(quantize_kernel<HAD, NV, METHOD, MASK, false>, kThreads, 0);
+    occ_check_a.store(occ_check, std::memory_order_release);
+    occ_trust_a.store(occ_trust, std::memory_order_release);
   }
   int64_t ctas = ceil_div(p.n_tiles, kWarpsPerCta);
   const int64_t max_ctas = (int64_t)num_sms() * (p.trust_hadamard ? occ_trust : occ_check);

@@ -1,24 +1,31 @@
 #!/usr/bin/env python
-"""Which device kernels changed between two builds?  Compares the SASS (cuobjdump -sass) of every kernel in two objects /
-shared libraries by mangled name.  Used to prove that adding an opt-in kernel left the GPU-validated ones byte-identical.
-usage: python tools/sass_diff.py OLD.{o,so} NEW.{o,so}"""
-import re, subprocess, sys
+"""Which device kernels changed between two builds?  Extracts every kernel's instruction stream (cuobjdump -sass, addresses
+and encodings stripped) from two objects / shared libraries and reports the kernels of OLD that have no instruction-identical
+kernel in NEW (a renamed template instantiation with the same code counts as unchanged).  Used to prove that adding opt-in
+kernels left the GPU-validated ones untouched.
+usage: python tools/sass_diff.py OLD.{o,so} NEW.{o,so}      exit status 1 if a kernel of OLD changed or vanished"""
+import collections, re, subprocess, sys
 
 
 def funcs(path):
     txt = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
-    parts = re.split(r"\n\s*Function : ", txt)[1:]
-    return {f.split("\n")[0].strip(): "\n".join(f.split("\n")[1:]) for f in parts}
+    out = {}
+    for f in re.split(r"\n\s*Function : ", txt)[1:]:
+        ins = [m.group(1).strip() for m in (re.search(r"/\*[0-9a-f]{4,5}\*/\s+(.*?);", l) for l in f.split("\n")[1:]) if m]
+        out[f.split("\n")[0].strip()] = "\n".join(ins)
+    return out
 
 
 if __name__ == "__main__":
     a, b = funcs(sys.argv[1]), funcs(sys.argv[2])
-    changed = [k for k in a if k in b and a[k] != b[k]]
-    print(f"{len(a)} kernels in OLD, {len(b)} in NEW: {sum(1 for k in a if k in b and a[k] == b[k])} identical, "
-          f"{len(changed)} changed, {len([k for k in a if k not in b])} removed, {len([k for k in b if k not in a])} new")
-    for k in changed:
-        print("changed:", k)
-    for k in b:
-        if k not in a:
-            print("new:", k)
-    sys.exit(1 if changed else 0)
+    have = collections.Counter(b.values())
+    missing = [k for k in a if have[a[k]] == 0]
+    old_bodies = set(a.values())
+    new = [k for k in b if b[k] not in old_bodies]
+    print(f"{len(a)} kernels in OLD, {len(b)} in NEW: {len(a) - len(missing)} of OLD instruction-identical in NEW, "
+          f"{len(missing)} changed or removed, {len(new)} kernels with new code")
+    for k in missing:
+        print("changed/removed:", k)
+    for k in new:
+        print("new:", k)
+    sys.exit(1 if missing else 0)
