@@ -724,6 +724,15 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 // Requires N % 448 == 0, K % 256 == 0, ldd % 8 == 0, FP4 kinds.  Same arithmetic as every other configuration (one fp32 chain
 // per output over K, alpha once, one RNE).  STATUS: written after round 1's GPU budget was spent -- compiled, NOT yet run;
 // reachable only through the explicit configuration or B200Q_GEMM_HYBRID=1.
+// super tile `sup` (row blocks fastest), half j (0 = the 256-wide tile, 1 = the 192-wide one) -> row block tm, first column n0.
+// Shared by the kernel and the host-only query b200q_debug_hybrid_tile (tests/test_cabi.py checks coverage and alignment).
+__host__ __device__ __forceinline__ void hybrid_tile_geom(int sup, int j, int tiles_m, int& tm, int& n0) {
+  tm = sup % tiles_m;
+  const int sn = sup / tiles_m;
+  const int base = sn * 448;
+  n0 = (sn & 1) ? (j == 0 ? base + 192 : base) : (j == 0 ? base : base + 256);
+}
+
 template <bool kNV>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_fp4_hybrid_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bw,
@@ -760,12 +769,8 @@ gemm_fp4_hybrid_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const int num_clusters = gridDim.x >> 1;
   const int total_supers = p.tiles_m * p.tiles_n;        // tiles_n = N / 448 here
   // super tile `sup` (M fastest), half j (0 = wide, 1 = narrow) -> row block tm, first column n0
-  auto geom = [&](int sup, int j, int& tm, int& n0) {
-    tm = sup % p.tiles_m;
-    const int sn = sup / p.tiles_m;
-    const int base = sn * SUPER;
-    n0 = (sn & 1) ? (j == 0 ? base + BNN : base) : (j == 0 ? base : base + BNW);
-  };
+  static_assert(SUPER == 448 && BNN == 192 && BNW == 256, "hybrid_tile_geom");
+  auto geom = [&](int sup, int j, int& tm, int& n0) { hybrid_tile_geom(sup, j, p.tiles_m, tm, n0); };
 
   pdl_launch_dependents();
 
@@ -1378,6 +1383,13 @@ extern "C" int b200q_debug_read_trace(unsigned long long* out, int n) {
   if (n > kTraceTiles * kTraceEvents) n = kTraceTiles * kTraceEvents;
   B200Q_CUDA(cudaDeviceSynchronize());
   B200Q_CUDA(cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(unsigned long long) * n));
+  return 0;
+}
+
+// host-only: the tile walk of the hybrid (2, 448) configuration (no device needed)
+extern "C" int b200q_debug_hybrid_tile(int sup, int half, int tiles_m, int* tm, int* n0) {
+  B200Q_REQUIRE(sup >= 0 && (half == 0 || half == 1) && tiles_m > 0 && tm && n0, "bad argument");
+  hybrid_tile_geom(sup, half, tiles_m, *tm, *n0);
   return 0;
 }
 

@@ -131,3 +131,37 @@ def test_hybrid_tile_pairs_are_opt_in(lib_path, monkeypatch):
     assert plan(4096, 4096, 14336) == (2, 256)          # N % 448 != 0
     assert plan(128, 14336, 4096) == (1, 128)           # the weight-streaming regime keeps its single-CTA tiles
     assert plan(4096, 14336, 4096, 2)[1] != 448         # MXFP8: FP4 kinds only
+
+
+def test_hybrid_tile_walk_covers_the_output_with_legal_scale_alignment(lib_path):
+    """gemm_fp4_hybrid_kernel's tile walk (hybrid_tile_geom, shared by the kernel and this host-only debug export): super
+    tiles of 448 columns = one 256-wide + one 192-wide tile, laid out W N | N W.  Checked here without a GPU: the tiles of a
+    row block partition [0, N) exactly; every wide tile starts on a 128-row scale block (its two SFB blocks are whole);
+    every narrow tile starts 0 or 64 rows into one (an EVEN TMEM column shift -- odd shifts fault on the hardware) and its
+    192 rows stay inside the two SFB blocks the producer loads; and the M-fastest order keeps a CTA pair on one row block
+    per super tile."""
+    lib = ctypes.CDLL(lib_path)
+    fn = lib.b200q_debug_hybrid_tile
+    fn.argtypes = [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2
+    for n, tiles_m in ((448, 1), (896, 3), (14336, 16), (28672, 8)):
+        supers_n = n // 448
+        for tm_want in range(tiles_m):
+            spans = []
+            for sn in range(supers_n):
+                sup = sn * tiles_m + tm_want
+                for half, width in ((0, 256), (1, 192)):
+                    tm, n0 = ctypes.c_int(), ctypes.c_int()
+                    assert fn(sup, half, tiles_m, ctypes.byref(tm), ctypes.byref(n0)) == 0
+                    assert tm.value == tm_want
+                    start = n0.value
+                    if half == 0:
+                        assert start % 128 == 0
+                    else:
+                        assert start % 128 in (0, 64) and ((start % 128) // 32) % 2 == 0
+                    first_block = start // 128
+                    assert start + width <= (first_block + 2) * 128          # inside the 2 SFB row blocks that are loaded
+                    assert (first_block + 1) * 128 < n + 128                   # second block exists in the padded scale buffer
+                    spans.append((start, start + width))
+            spans.sort()
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
