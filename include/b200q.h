@@ -46,12 +46,17 @@ typedef struct CUstream_st* b200q_stream_t;
  * butterfly kernel's scalar fallback.  Large Hadamard inputs take the tcgen05 kernel too (it streams at the HBM rate
  * for any R); the choice never changes the results beyond fp32 summation order. */
 #define B200Q_ROT_GENERIC 0x200
-/* b200q_quantize_nv only, opt-in: compute the abs_max Hadamard-128 codes with the scale BEFORE its e4m3 rounding, which is what
- * the reference's sm_100-only kernel does (bindings.cpp:413-415 -> fused_quantize_nv_sm100.cu;
- * cutlass_extensions/epilogue/fusion/sm100_visitor_store_tma_warpspecialized.hpp:141-148,567-591) -- unlike its mma.sync kernels
- * (H = 16/32/64, sm_120) and its test oracle, which this library follows by default.  Ignored for other methods / sizes.
- * UNMEASURED: added after round 1's GPU budget was spent. */
+/* NVFP4 abs_max with Hadamard-128 -- the ONE case where the reference's sm_100 dispatch (bindings.cpp:413-415 ->
+ * fused_quantize_nv_sm100.cu:192-207) deviates from its other kernels (mma.sync, H = 16/32/64, sm_120) and from its own test
+ * oracle (tests/nvfp4_test.py:132-170): that kernel stores the e4m3-ROUNDED scale but derives the codes from the UNROUNDED one
+ * (cutlass_extensions/epilogue/fusion/sm100_visitor_store_tma_warpspecialized.hpp:141-148,567-591).  This library targets
+ * sm_100 only, so b200q_quantize_nv reproduces that kernel by DEFAULT (validated on B200 against the compiled reference:
+ * scales identical, dequantised values identical up to <= 2e-4 +0/-0 codes).  OR B200Q_NV_ORACLE_CODES into `method` to get the
+ * oracle / mma.sync arithmetic instead (codes from the rounded scale: slightly more accurate dequantisation; differs from
+ * the reference's sm_100 output in 4.8 % of the values / 9.2 % of the code bytes, scales identical).  Ignored for every other
+ * method / size.  B200Q_NV_SM100_CODES (round-1 opt-in for the now-default behaviour) is still accepted and has no effect. */
 #define B200Q_NV_SM100_CODES 0x400
+#define B200Q_NV_ORACLE_CODES 0x800
 
 #define B200Q_KIND_MXF4 0      /* e2m1 x e2m1, ue8m0 scales, group 32          */
 #define B200Q_KIND_NVF4 1      /* e2m1 x e2m1, ue4m3 scales, group 16          */
@@ -62,11 +67,28 @@ typedef struct CUstream_st* b200q_stream_t;
                                   matmul_host_mxf8_bf16_nn (gemm.cu:388-434).  D[m,n] = sum_k A[k,m] B[n,k]; the scales
                                   of A stay in the blocked layout of the LOGICAL [M, K/32] matrix                */
 
+/* OR into `kind` of b200q_gemm_fp4 / b200q_gemm_fp4_cfg: the caller guarantees that B and SFB are NOT written by the kernels
+ * in front of this GEMM on `stream` (inference: weights quantised once).  The GEMM is a programmatic dependent launch; with
+ * this flag its first ring of weight loads is issued before the grid dependency resolves (overlaps the tail of the
+ * activation quantiser: -1.5 .. -2.3 us per call).  Without it (default) every global read waits for the preceding kernel,
+ * which is what the reference's own pattern quantise(a); quantise(b); matmul(...) and QAT (weights re-quantised every step)
+ * need.  b200q_linear_fp4 / b200q_linear_fp4_host take pre-quantised weights by contract and always set it. */
+#define B200Q_GEMM_STATIC_WEIGHTS 0x100
+
 /* ABI version of this header (bumped on incompatible change). */
 int b200q_abi_version(void);
 
 /* Thread-local message for the most recent failure on this thread ("" if none). */
 const char* b200q_last_error(void);
+
+/* The library reads its environment switches (B200Q_NO_PDL, B200Q_QUANT_TC, B200Q_FUSE, ... -- README "environment switches")
+ * ONCE, at first use; call this after changing one inside a running process (tests, probe tools). */
+void b200q_reload_env(void);
+/* 1 if this library was built with -DB200Q_PROFILING (B200Q_GEMM_DEBUG_FLAGS honoured: timing-only switches that skip
+ * loads / copies / stores and therefore produce WRONG results), 0 for the product build (the variable is ignored). */
+int b200q_profiling_build(void);
+/* Host-only: hits / misses of the calling thread's tensor-map cache since it was last read (then reset). */
+int b200q_debug_tmap_cache_stats(unsigned long long* hits, unsigned long long* misses);
 
 /*
  * Fused rotate + MXFP4 quantise.

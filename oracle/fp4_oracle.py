@@ -273,9 +273,12 @@ def quantize_mx(x, R, method: str = "quest", arithmetic: str = "kernel"):
 
 
 # --------------------------------------------------------------------------- NV quantise
-def quantize_nv(x, R, global_scale: float, method: str = "abs_max", arithmetic: str = "kernel", sm100_codes: bool = False):
+def quantize_nv(x, R, global_scale: float, method: str = "abs_max", arithmetic: str = "kernel", sm100_codes=None):
     """Fused rotate + NVFP4 quantise (group 16, e4m3 scale, fp32 global scale).
 
+    sm100_codes: None (default) = what the reference does ON sm_100, i.e. True exactly for abs_max with a 128 x 128 rotation
+    (bindings.cpp:413-415 dispatches that one case to fused_quantize_nv_sm100.cu) and False otherwise; pass False to get
+    the mma.sync kernels' / the reference test oracle's arithmetic for that case too (B200Q_NV_ORACLE_CODES in the C-ABI).
     sm100_codes (abs_max only): the arithmetic of the reference's sm_100-ONLY Hadamard-128 kernel
     (sm100_visitor_store_tma_warpspecialized.hpp:141-148,567-591): the stored scale is e4m3-rounded as usual but the codes
     are computed with the UNROUNDED scale, q = e2m1(xh * rcp(sfv * rcp(gs))), sfv = gs * (amax * rcp(6)).  Observed on B200:
@@ -288,6 +291,8 @@ def quantize_nv(x, R, global_scale: float, method: str = "abs_max", arithmetic: 
     ref64 flavour restates tests/nvfp4_test.py:132-170 (abs_max only; equals the kernel
     semantics when global_scale == 6)."""
     assert method in ("quest", "abs_max")
+    if sm100_codes is None:
+        sm100_codes = method == "abs_max" and np.asarray(R).shape[0] == 128 and arithmetic == "kernel"
     x = np.asarray(x)
     xh = rotate(x.reshape(-1), R, arithmetic).reshape(-1, 16)
     if arithmetic == "ref64":

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 from .utils import (get_padded_shape_mx, get_padded_shape_nv, pad_to_block, to_blocked,  # noqa: F401
-                    _attach_blocked, _version_of)
+                    _attach_blocked, _detach_blocked, _version_of)
 
 __all__ = [
     "matmul_mxf4_bf16_tn", "matmul_nvf4_bf16_tn", "fusedQuantizeMx", "fusedQuantizeNv",
@@ -35,8 +35,10 @@ __all__ = [
 METHOD_QUEST, METHOD_ABSMAX = 0, 1
 ROT_TRUSTED_HADAMARD = 0x100   # include/b200q.h: B200Q_ROT_TRUSTED_HADAMARD
 ROT_GENERIC = 0x200            # include/b200q.h: B200Q_ROT_GENERIC (known non-Hadamard -> tensor-core rotation)
-NV_SM100_CODES = 0x400         # include/b200q.h: B200Q_NV_SM100_CODES (opt-in reference-sm_100 arithmetic, NVFP4 abs_max H=128)
+NV_SM100_CODES = 0x400         # include/b200q.h: B200Q_NV_SM100_CODES (accepted, no effect: the behaviour is the default now)
+NV_ORACLE_CODES = 0x800        # include/b200q.h: B200Q_NV_ORACLE_CODES (NVFP4 abs_max H=128: the reference ORACLE's arithmetic)
 KIND_MXF4, KIND_NVF4, KIND_MXF8, KIND_MXF8_NN = 0, 1, 2, 3
+GEMM_STATIC_WEIGHTS = 0x100    # include/b200q.h: B200Q_GEMM_STATIC_WEIGHTS (OR into kind)
 
 
 def _check(cond: bool, msg: str) -> None:
@@ -85,7 +87,8 @@ def _check_contig(name: str, tensors) -> None:
 
 
 # --------------------------------------------------------------------------------------- GEMM
-def _matmul_fp4(name: str, a, b, a_sf, b_sf, alpha, kind: int, sf_dtype, min_k_bytes: int, cfg=(0, 0)):
+def _matmul_fp4(name: str, a, b, a_sf, b_sf, alpha, kind: int, sf_dtype, min_k_bytes: int, cfg=(0, 0),
+                static_weights: bool = False):
     """reference checks: qutlass/csrc/bindings.cpp:32-102"""
     _check_contig(name, [("A", a), ("B", b), ("A_sf", a_sf), ("B_sf", b_sf)])
     _check_cuda_same(name, [("A", a), ("B", b), ("A_sf", a_sf), ("B_sf", b_sf), ("alpha", alpha)])
@@ -118,7 +121,7 @@ def _matmul_fp4(name: str, a, b, a_sf, b_sf, alpha, kind: int, sf_dtype, min_k_b
     with _DeviceGuard(a.device):
         _lib.check(_lib.load().b200q_gemm_fp4_cfg(
             a.data_ptr(), b.data_ptr(), a_sf.data_ptr(), b_sf.data_ptr(), alpha.data_ptr(), out.data_ptr(),
-            m, n, k, kind, cfg[0], cfg[1], _stream(a)))
+            m, n, k, kind | (GEMM_STATIC_WEIGHTS if static_weights else 0), cfg[0], cfg[1], _stream(a)))
     return out
 
 
@@ -132,17 +135,26 @@ def _backend_gate(backend: str) -> None:
 
 
 def matmul_mxf4_bf16_tn(a: torch.Tensor, b: torch.Tensor, a_sf: torch.Tensor, b_sf: torch.Tensor,
-                        alpha: torch.Tensor, backend: Literal["cutlass", "flashinfer"] = "cutlass") -> torch.Tensor:
-    """D = bf16(alpha * dq(a) @ dq(b).T), MXFP4 (reference: qutlass/__init__.py:34-76)."""
+                        alpha: torch.Tensor, backend: Literal["cutlass", "flashinfer"] = "cutlass", *,
+                        static_weights: bool = False) -> torch.Tensor:
+    """D = bf16(alpha * dq(a) @ dq(b).T), MXFP4 (reference: qutlass/__init__.py:34-76).
+
+    ``static_weights=True`` (extension, keyword-only): the caller guarantees ``b`` / ``b_sf`` are not produced by the
+    kernels right in front of this call on the stream (weights quantised once); the GEMM then prefetches them while the
+    preceding kernel drains (include/b200q.h: B200Q_GEMM_STATIC_WEIGHTS).  The default is safe for any call order."""
     _backend_gate(backend)
-    return _matmul_fp4("matmul_mxf4_bf16_tn", a, b, a_sf, b_sf, alpha, KIND_MXF4, torch.float8_e8m0fnu, 32)
+    return _matmul_fp4("matmul_mxf4_bf16_tn", a, b, a_sf, b_sf, alpha, KIND_MXF4, torch.float8_e8m0fnu, 32,
+                       static_weights=static_weights)
 
 
 def matmul_nvf4_bf16_tn(a: torch.Tensor, b: torch.Tensor, a_sf: torch.Tensor, b_sf: torch.Tensor,
-                        alpha: torch.Tensor, backend: Literal["cutlass", "flashinfer"] = "cutlass") -> torch.Tensor:
-    """D = bf16(alpha * dq(a) @ dq(b).T), NVFP4 (reference: qutlass/__init__.py:89-131)."""
+                        alpha: torch.Tensor, backend: Literal["cutlass", "flashinfer"] = "cutlass", *,
+                        static_weights: bool = False) -> torch.Tensor:
+    """D = bf16(alpha * dq(a) @ dq(b).T), NVFP4 (reference: qutlass/__init__.py:89-131).  ``static_weights``: see
+    matmul_mxf4_bf16_tn."""
     _backend_gate(backend)
-    return _matmul_fp4("matmul_nvf4_bf16_tn", a, b, a_sf, b_sf, alpha, KIND_NVF4, torch.float8_e4m3fn, 16)
+    return _matmul_fp4("matmul_nvf4_bf16_tn", a, b, a_sf, b_sf, alpha, KIND_NVF4, torch.float8_e4m3fn, 16,
+                       static_weights=static_weights)
 
 
 def matmul_mxf8_bf16_tn(a: torch.Tensor, b: torch.Tensor, block_scale_a: torch.Tensor, block_scale_b: torch.Tensor,
@@ -165,7 +177,9 @@ def matmul_mxf8_bf16_nn(a: torch.Tensor, b: torch.Tensor, block_scale_a: torch.T
 
 
 # --------------------------------------------------------------------------------------- quantise
-_ROT_CACHE = {}   # id(tensor) -> (weakref, _version, is_hadamard)
+_ROT_CACHE = {}   # id(tensor) -> (weakref, _version, data_ptr, is_hadamard)
+_ROT_INSPECTIONS = [0]   # host inspections so far (each is one blocking D2H copy)
+_ROT_MAX_INSPECTIONS = 64
 
 
 def _rotation_hint(r: torch.Tensor) -> int:
@@ -174,16 +188,23 @@ def _rotation_hint(r: torch.Tensor) -> int:
     The reference's API takes *any* matrix at run time (README "loaded at runtime"); the kernel can verify the
     Sylvester-Hadamard structure itself on the device (graph-safe) but that check is redundant work on every
     call.  Here the (<= 32 KB) matrix is inspected ONCE on the host -- one small D2H copy -- and the result is
-    remembered for as long as that tensor object lives unmodified.  During CUDA-graph capture (no host sync
-    allowed) an unseen matrix simply gets no hint and the device-side check runs."""
+    remembered for as long as that tensor object lives unmodified.  No hint (0: the device-side check runs, always
+    correct) whenever the host cannot vouch for the matrix: during CUDA-graph capture, for inference-mode tensors
+    (no version counter: an in-place edit would go unnoticed), and once a caller has shown that it builds a new
+    rotation tensor for every call (more than _ROT_MAX_INSPECTIONS inspections -- each is a device synchronisation)."""
     import weakref
     key = id(r)
     ent = _ROT_CACHE.get(key)
     ver = _version_of(r)
-    if ent is not None and ent[0]() is r and ent[1] == ver:
-        return ROT_TRUSTED_HADAMARD if ent[2] else ROT_GENERIC
+    if ver < 0:
+        return 0
+    if ent is not None and ent[0]() is r and ent[1] == ver and ent[2] == r.data_ptr():
+        return ROT_TRUSTED_HADAMARD if ent[3] else ROT_GENERIC
     if r.is_cuda and torch.cuda.is_current_stream_capturing():
         return 0
+    if _ROT_INSPECTIONS[0] >= _ROT_MAX_INSPECTIONS:
+        return 0
+    _ROT_INSPECTIONS[0] += 1
     h = r.size(0)
     m = r.detach().to("cpu").view(torch.int16)                 # bit patterns (synchronises once)
     idx = torch.arange(h)
@@ -199,7 +220,7 @@ def _rotation_hint(r: torch.Tensor) -> int:
     if len(_ROT_CACHE) > 64:
         for k in [k for k, v in _ROT_CACHE.items() if v[0]() is None]:
             _ROT_CACHE.pop(k, None)
-    _ROT_CACHE[key] = (weakref.ref(r), ver, is_h)
+    _ROT_CACHE[key] = (weakref.ref(r), ver, r.data_ptr(), is_h)
     return ROT_TRUSTED_HADAMARD if is_h else ROT_GENERIC
 
 
@@ -219,6 +240,8 @@ def _quantize_mx_into(a, r, out, out_sf, out_sf_blocked, out_mask, method: int):
     had = _quant_checks("fusedQuantizeMx", a, r, [out, out_sf])
     _check(had in (32, 64, 128), f"Unsupported rotation size {had}; expected 32, 64, or 128.")
     _check(a.size(-1) % 32 == 0, "last dimension of A must be a multiple of 32")
+    if out_sf is not None:
+        _detach_blocked(out_sf)     # OUT_sf is overwritten through its data pointer: a blocked copy attached earlier is stale
     with _DeviceGuard(a.device):
         _lib.check(_lib.load().b200q_quantize_mx(
             a.data_ptr(), r.data_ptr(), out.data_ptr(), out_sf.data_ptr() if out_sf is not None else None,
@@ -234,10 +257,12 @@ def _quantize_nv_into(a, r, out, out_sf, out_sf_blocked, global_scale, method: i
     _check(had in (16, 32, 64, 128), f"Unsupported rotation size {had}; expected 16, 32, 64, or 128.")
     _check(a.size(-1) % 32 == 0, "last dimension of A must be a multiple of 32")
     flags = method | _rotation_hint(r)
-    if had == 128 and method == METHOD_ABSMAX and os.environ.get("B200Q_NV128_REFERENCE_CODES") == "1":
-        # opt-in (unmeasured): the reference's sm_100-only kernel for this one case derives the codes from the UNROUNDED scale
-        # (include/b200q.h: B200Q_NV_SM100_CODES); default = its other kernels' / its test oracle's arithmetic
-        flags |= NV_SM100_CODES
+    if out_sf is not None:
+        _detach_blocked(out_sf)
+    if had == 128 and method == METHOD_ABSMAX and os.environ.get("B200Q_NV128_ORACLE_CODES") == "1":
+        # abs_max + Hadamard-128: by default bit-compatible with the reference's sm_100-only kernel (codes from the UNROUNDED
+        # scale, include/b200q.h / DESIGN.md section 4); this switch selects the arithmetic of its other kernels / test oracle
+        flags |= NV_ORACLE_CODES
     with _DeviceGuard(a.device):
         _lib.check(_lib.load().b200q_quantize_nv(
             a.data_ptr(), r.data_ptr(), out.data_ptr(), out_sf.data_ptr() if out_sf is not None else None,
@@ -347,6 +372,8 @@ def fused_linear_fp4(x: torch.Tensor, rot: torch.Tensor, w_q: torch.Tensor, w_sf
     blocked = torch.empty(padded_rows * padded_cols, dtype=sf_dtype, device=x.device)
     out = torch.empty(m, n, dtype=torch.bfloat16, device=x.device)
     meth = (METHOD_QUEST if method == "quest" else METHOD_ABSMAX) | _rotation_hint(rot)
+    if nv and had == 128 and method == "abs_max" and os.environ.get("B200Q_NV128_ORACLE_CODES") == "1":
+        meth |= NV_ORACLE_CODES
     with _DeviceGuard(x.device):
         stream = _stream(x)
         capturing = torch.cuda.is_current_stream_capturing()

@@ -10,12 +10,18 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200q.so")
+# B200Q_LIB=prof selects the profiling build (python -m qutlass_b200.build --profiling): probe tools only
+if os.environ.get("B200Q_LIB") == "prof":
+    LIB_PATH = os.path.join(_HERE, "lib", "libb200q_prof.so")
 
 # name -> (restype, argtypes); must match include/b200q.h exactly (tests/test_cabi.py checks the header)
 _vp, _i64, _i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
 SIGNATURES = {
     "b200q_abi_version": (_i32, []),
     "b200q_last_error": (ctypes.c_char_p, []),
+    "b200q_reload_env": (None, []),
+    "b200q_profiling_build": (_i32, []),
+    "b200q_debug_tmap_cache_stats": (_i32, [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]),
     "b200q_quantize_mx": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "b200q_quantize_nv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "b200q_swizzle_sf": (_i32, [_vp, _vp, _i64, _i64, _vp]),
@@ -56,6 +62,11 @@ def load() -> ctypes.CDLL:
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def reload_env() -> None:
+    """Re-read the library's environment switches (they are cached at first use; include/b200q.h: b200q_reload_env)."""
+    load().b200q_reload_env()
 
 
 def check(rc: int) -> None:

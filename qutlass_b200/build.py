@@ -1,7 +1,11 @@
 """Build libb200q.so (hand-written sm_100a CUDA behind the C-ABI in include/b200q.h).
 
 In-tree build: the .so lands in qutlass_b200/lib/ so it travels with the repo snapshot to
-the GPU box.  nvcc cross-compiles without a GPU.  Usage: python -m qutlass_b200.build [--force]
+the GPU box.  nvcc cross-compiles without a GPU.  Usage: python -m qutlass_b200.build [--force] [--profiling]
+
+--profiling builds a SECOND library, lib/libb200q_prof.so, with -DB200Q_PROFILING: the only build in which
+B200Q_GEMM_DEBUG_FLAGS (timing-only switches that skip loads / copies / stores -> wrong results) is honoured.
+The probe tools under tools/ select it with B200Q_LIB=prof; the product library ignores the variable.
 """
 from __future__ import annotations
 
@@ -36,8 +40,9 @@ def _nvcc() -> str:
     return cand
 
 
-def _digest() -> str:
+def _digest(extra: str = "") -> str:
     h = hashlib.sha256()
+    h.update(extra.encode())
     for name in sorted(os.listdir(CSRC)) + ["../../include/b200q.h"]:
         p = os.path.join(CSRC, name)
         if os.path.isfile(p):
@@ -47,19 +52,22 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, profiling: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
-    stamp = os.path.join(LIBDIR, "libb200q.sha256")
-    digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
-        return LIB
+    lib = os.path.join(LIBDIR, "libb200q_prof.so") if profiling else LIB
+    objdir = OBJDIR + ("_prof" if profiling else "")
+    flags = NVCC_FLAGS + (["-DB200Q_PROFILING"] if profiling else [])
+    os.makedirs(objdir, exist_ok=True)
+    stamp = lib.replace(".so", ".sha256")
+    digest = _digest("prof" if profiling else "")
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return lib
     nvcc = _nvcc()
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
     def compile_one(src):
-        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -69,14 +77,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:
         f.write(digest)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, profiling="--profiling" in sys.argv))

@@ -14,6 +14,42 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static Env g_env;
+static std::atomic<int> g_env_ready{0};
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
+static void load_env() {
+  Env e;
+  e.no_pdl = env_int("B200Q_NO_PDL", 0);
+  if (e.no_pdl < 0 || e.no_pdl > 2) e.no_pdl = 0;
+  e.tail_split = env_int("B200Q_TAIL_SPLIT", 0) == 1;
+  e.gemm_hybrid = env_int("B200Q_GEMM_HYBRID", 0) == 1;
+  e.fuse = env_int("B200Q_FUSE", 0) == 1;
+  e.fuse_warps = env_int("B200Q_FUSE_WARPS", 4) == 2 ? 2 : 4;
+  e.quant_mma = env_int("B200Q_QUANT_MMA", 0) == 1;
+  e.quant_tc = env_int("B200Q_QUANT_TC", -1);
+  if (e.quant_tc != 0 && e.quant_tc != 1) e.quant_tc = -1;
+#ifdef B200Q_PROFILING
+  e.gemm_flags = env_int("B200Q_GEMM_DEBUG_FLAGS", 0);
+#else
+  e.gemm_flags = 0;
+#endif
+  e.verbose = getenv("B200Q_GEMM_VERBOSE") != nullptr;
+  e.gemm_skew = env_int("B200Q_GEMM_SKEW", -1);
+  e.no_tmap_cache = env_int("B200Q_NO_TMAP_CACHE", 0) == 1;
+  g_env = e;
+  g_env_ready.store(1, std::memory_order_release);
+}
+
+const Env& env() {
+  if (!g_env_ready.load(std::memory_order_acquire)) load_env();   // racing first calls store identical values
+  return g_env;
+}
+
 static int g_sm_major[64];
 static int g_sm_count[64];
 static bool g_dev_init[64];
@@ -67,4 +103,12 @@ int num_sms() {
 }  // namespace b200q
 
 extern "C" int b200q_abi_version(void) { return 1; }
+extern "C" void b200q_reload_env(void) { b200q::load_env(); }
+extern "C" int b200q_profiling_build(void) {
+#ifdef B200Q_PROFILING
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" const char* b200q_last_error(void) { return b200q::g_err; }

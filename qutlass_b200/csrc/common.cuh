@@ -18,6 +18,25 @@ int check_device_sm100();          // 0 or B200Q_EUNSUPPORTED (cached per device
 int num_sms();                     // SM count of the current device (cached)
 int current_device();              // ordinal of the current device, 0 on error
 
+// Environment switches, read ONCE (first use) instead of getenv() on every launch; b200q_reload_env() re-reads them
+// (tests and probe tools that flip a switch inside one process call it).  Switches that change RESULTS (the GEMM's
+// profiling flags: skip loads / copies / stores) exist only in a library built with -DB200Q_PROFILING; the product
+// build ignores B200Q_GEMM_DEBUG_FLAGS entirely.
+struct Env {
+  int no_pdl;        // B200Q_NO_PDL: 0 = PDL everywhere, 1 = off, 2 = GEMM only
+  int tail_split;    // B200Q_TAIL_SPLIT=1
+  int gemm_hybrid;   // B200Q_GEMM_HYBRID=1
+  int fuse;          // B200Q_FUSE=1
+  int fuse_warps;    // B200Q_FUSE_WARPS: 4 (default) or 2
+  int quant_mma;     // B200Q_QUANT_MMA=1
+  int quant_tc;      // B200Q_QUANT_TC: -1 unset, 0, 1
+  int gemm_flags;    // B200Q_GEMM_DEBUG_FLAGS (profiling builds only, else 0)
+  int verbose;       // B200Q_GEMM_VERBOSE
+  int gemm_skew;     // B200Q_GEMM_SKEW: -1 unset (planner decides), else forced k-tile skew of the split accumulator
+  int no_tmap_cache; // B200Q_NO_TMAP_CACHE=1
+};
+const Env& env();
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: set it once per (kernel, device).
 // `done` is a per-instantiation bitmask of device ordinals (static in the caller).
 template <typename Kern>
@@ -39,8 +58,7 @@ inline int ensure_dynamic_smem(Kern kern, int bytes, std::atomic<unsigned long l
 // may be scheduled while the previous kernel in the stream drains; inside, everything that touches global memory sits
 // behind griddepcontrol.wait (ptx::pdl_wait), which returns once that kernel has completed and its writes are visible.
 inline unsigned pdl_attribute(cudaLaunchAttribute* attr) {
-  const char* e = getenv("B200Q_NO_PDL");
-  if (e && (e[0] == '1' || e[0] == '2')) return 0;
+  if (env().no_pdl) return 0;
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   return 1;

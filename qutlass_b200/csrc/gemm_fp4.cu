@@ -112,7 +112,9 @@ struct GemmParams {
   int tiles_n;        // ceil(N / BN)
   int k_tiles;        // ceil(K / 256)
   int tma_store;      // 1: TMA-store epilogue (needs N % 8 == 0); 0: direct global stores
-  int flags;          // profiling: bit0 skip stores, bit1 skip TMEM loads
+  int flags;          // profiling builds only (-DB200Q_PROFILING): bit0 skip stores, bit1 skip TMEM loads, ...; else 0
+  int static_weights; // 1: the caller guarantees B / SFB are not produced by the preceding kernels of the stream
+                      //    (B200Q_GEMM_STATIC_WEIGHTS): their first ring of loads may be issued before griddepcontrol.wait
 };
 
 // Fused quantise + GEMM (kFuse): the activations are rotated + quantised by 4 extra warps of the SAME persistent kernel
@@ -377,6 +379,9 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
         }
       };
+      // Only with static_weights: by default B / SFB may come from the kernel right in front of us (QAT re-quantises the
+      // weights every step; the reference's own pattern is quantise(a); quantise(b); matmul), so every global read waits.
+      if (!p.static_weights) pdl_wait();
       {
         Cursor c = cur;
         for (int g = 0; g < pre; ++g) {          // ring is empty: no wait needed for the first STAGES slots
@@ -713,7 +718,13 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-// ------------------------------------------------------------------ hybrid tile pairs (explicit configuration (2, 448))
+// ------------------------------------------------------------------ hybrid tile pairs (PROFILING BUILDS ONLY, configuration (2, 448))
+// Measured on B200 at the start of round 2 (profiles/r02_notes.md): bit-identical, and NOT faster -- config 1 GEMM 5380 vs
+// 5449 TFLOP/s (MX), 5066 vs 5076 (NV) -- although it removes the accumulator hand-off bubble of the (2,256) tile completely.
+// The part is power-limited under FP4 MMA load: closing an idle gap lowers the clock instead of the run time.  The kernel is
+// therefore NOT part of the product library; it stays in the profiling build (-DB200Q_PROFILING) as the bubble-free control
+// of the tensor-rate measurements (tools/fp4_peak_probe.py).
+#ifdef B200Q_PROFILING
 // Every CTA pair walks "super tiles" of 256 rows x 448 columns as ONE 256-wide and ONE 192-wide tile.  A 256-column and a
 // 192-column fp32 accumulator plus the scale columns fit the 512 TMEM columns (256 + 192 + 24 / 48), so -- unlike the plain
 // (2,256) configuration, whose single accumulator costs ~1800 of ~10000 cycles per tile at the hand-off --
@@ -847,9 +858,10 @@ gemm_fp4_hybrid_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     };
     Cursor cur{cluster_id, 0, 0, 0, 0, 0};
     set_tile(cur);
+    if (!p.static_weights) pdl_wait();         // see gemm_fp4_kernel: weights are prefetched early only on the caller's word
     {
       Cursor c = cur;
-      for (int g = 0; g < pre; ++g) {          // weights do not depend on the previous kernel in the stream
+      for (int g = 0; g < pre; ++g) {
         if (elected) load_weights(g, c);
         advance(c);
       }
@@ -1010,6 +1022,7 @@ gemm_fp4_hybrid_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     tmem_dealloc<2>(tmem_base, 512);
   }
 }
+#endif  // B200Q_PROFILING
 
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1029,8 +1042,46 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// A tensor map is a pure function of (address, type, dims, strides, box, swizzle): encodings are memoised per thread in a
+// small direct-mapped table keyed on exactly those values, so a steady-state caller (same buffers every step, the
+// reference benchmarks' pattern) pays five table look-ups per GEMM instead of five driver calls.  Never stale: the key
+// IS the content.  B200Q_NO_TMAP_CACHE=1 bypasses it.
+struct TmapKey {
+  const void* ptr;
+  uint64_t dims[3], strides[2];
+  uint32_t box[3];
+  uint32_t dt, rank, sw;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && dt == o.dt && rank == o.rank && sw == o.sw && dims[0] == o.dims[0] && dims[1] == o.dims[1] &&
+           dims[2] == o.dims[2] && strides[0] == o.strides[0] && strides[1] == o.strides[1] && box[0] == o.box[0] &&
+           box[1] == o.box[1] && box[2] == o.box[2];
+  }
+};
+struct alignas(64) TmapEntry {
+  CUtensorMap map;
+  TmapKey key;
+  bool valid;
+};
+constexpr int kTmapCacheSlots = 256;
+static thread_local TmapEntry g_tmap_cache[kTmapCacheSlots];
+static thread_local unsigned long long g_tmap_hits = 0, g_tmap_misses = 0;
+
 static int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* ptr, const cuuint64_t* dims,
                   const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapSwizzle sw, const char* what) {
+  TmapKey key = {};
+  key.ptr = ptr;
+  key.dt = (uint32_t)dt; key.rank = (uint32_t)rank; key.sw = (uint32_t)sw;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides[i];
+  uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull;
+  h ^= (key.dims[0] * 31 + key.dims[1]) * 0xC2B2AE3D27D4EB4Full + key.box[1] * 0x165667B19E3779F9ull + key.box[0] + key.dims[2] * 7 + key.dt * 131 + key.sw;
+  TmapEntry& e = g_tmap_cache[(h >> 32) % kTmapCacheSlots];
+  const bool use_cache = !env().no_tmap_cache;
+  if (use_cache && e.valid && e.key == key) {
+    *tm = e.map;
+    ++g_tmap_hits;
+    return 0;
+  }
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
@@ -1043,6 +1094,12 @@ static int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void*
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
     return B200Q_ECUDA;
+  }
+  ++g_tmap_misses;
+  if (use_cache) {
+    e.map = *tm;
+    e.key = key;
+    e.valid = true;
   }
   return 0;
 }
@@ -1095,7 +1152,7 @@ static int make_d_tmap(CUtensorMap* tm, const void* ptr, int64_t M, int64_t N, i
 
 template <int kCtaGroup, int BN, bool kNV, int A_ROWS = 128, int kF8 = 0, int kFuse = 0, int kMC = 0>
 static int launch_gemm(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D,
-                       int M, int N, int K, int ldd, cudaStream_t stream, const FuseParams* fuse = nullptr) {
+                       int M, int N, int K, int ldd, cudaStream_t stream, bool static_w, const FuseParams* fuse = nullptr) {
   using Cfg = GemmCfg<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse>;
   auto kern = gemm_fp4_kernel<kCtaGroup, BN, kNV, A_ROWS, kF8, kFuse, kMC>;
   constexpr int kClusterCtas = kCtaGroup * (kMC ? 2 : 1);
@@ -1123,12 +1180,10 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   p.tiles_n = (int)ceil_div(N, BN);
   p.k_tiles = (int)ceil_div(K, Cfg::BK_ELEMS);
   p.tma_store = (ldd % 8 == 0) ? 1 : 0;
-  {
-    const char* f = getenv("B200Q_GEMM_DEBUG_FLAGS");
-    p.flags = f ? atoi(f) : 0;
-    if (p.flags & 4) p.tma_store = 0;
-    if ((p.flags & 128) && p.tma_store) p.tma_store = 2;   // coalesced st.global from the staged tile
-  }
+  p.static_weights = static_w ? 1 : 0;
+  p.flags = env().gemm_flags;                              // always 0 unless the library was built with -DB200Q_PROFILING
+  if (p.flags & 4) p.tma_store = 0;
+  if ((p.flags & 128) && p.tma_store) p.tma_store = 2;     // coalesced st.global from the staged tile
   if (p.tma_store) {
     if ((rc = make_d_tmap(&td, D, M, N, ldd, Cfg::EPI_CHUNK))) return rc;
   } else {
@@ -1158,7 +1213,7 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
       B200Q_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
       mc = n > 0 ? n : 1;
       mc_a.store(mc, std::memory_order_release);
-      if (getenv("B200Q_GEMM_VERBOSE")) fprintf(stderr, "b200q: clusters of %d CTAs co-resident: %d (SMs %d)\n", kClusterCtas, n, num_sms());
+      if (env().verbose) fprintf(stderr, "b200q: clusters of %d CTAs co-resident: %d (SMs %d)\n", kClusterCtas, n, num_sms());
     }
     if (clusters > mc) clusters = mc;
   }
@@ -1169,16 +1224,14 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  {
-    const char* e = getenv("B200Q_NO_PDL");
-    cfg.numAttrs = (e && e[0] == '1') ? 1 : 2;
-  }
+  cfg.numAttrs = env().no_pdl == 1 ? 1 : 2;
   FuseParams fpv = {};
   if (fuse) fpv = *fuse;
   B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tsa, tsb, td, p, fpv));
   return 0;
 }
 
+#ifdef B200Q_PROFILING
 // hybrid tile pairs (gemm_fp4_hybrid_kernel): explicit configuration (2, 448)
 static bool hybrid_eligible(int M, int N, int K, int ldd, int kind) {
   return (kind == B200Q_KIND_MXF4 || kind == B200Q_KIND_NVF4) && M > 0 && N % 448 == 0 && K % 256 == 0 && ldd % 8 == 0;
@@ -1186,7 +1239,7 @@ static bool hybrid_eligible(int M, int N, int K, int ldd, int kind) {
 
 template <bool kNV>
 static int launch_gemm_hybrid(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D,
-                              int M, int N, int K, int ldd, cudaStream_t stream) {
+                              int M, int N, int K, int ldd, cudaStream_t stream, bool static_w) {
   using Cfg = GemmCfg<2, 256, kNV>;
   auto kern = gemm_fp4_hybrid_kernel<kNV>;
   static std::atomic<unsigned long long> smem_attr_done{0};   // per instantiation, one bit per device
@@ -1212,6 +1265,7 @@ static int launch_gemm_hybrid(const void* A, const void* B, const void* SFA, con
   p.k_tiles = K / 256;
   p.tma_store = 1;
   p.flags = 0;
+  p.static_weights = static_w ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -1228,34 +1282,34 @@ static int launch_gemm_hybrid(const void* A, const void* B, const void* SFA, con
   attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  {
-    const char* e = getenv("B200Q_NO_PDL");
-    cfg.numAttrs = (e && e[0] == '1') ? 1 : 2;
-  }
+  cfg.numAttrs = env().no_pdl == 1 ? 1 : 2;
   B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tbw, tbn, tsa, tsb, td64, td32, p));
   return 0;
 }
+#endif  // B200Q_PROFILING
 
 template <bool kNV, int kF8>
 static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B, const void* SFA, const void* SFB,
-                        const float* alpha, void* D, int M, int N, int K, int ldd, cudaStream_t s) {
+                        const float* alpha, void* D, int M, int N, int K, int ldd, cudaStream_t s, bool sw) {
   // small M: same 128-wide single-CTA tile, fewer A rows staged (more weight k-tiles in flight)
   if constexpr (kF8 != 2) {
-    if (cta_group == 1 && block_n == 128 && M <= 16) return launch_gemm<1, 128, kNV, 16, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
-    if (cta_group == 1 && block_n == 128 && M <= 32) return launch_gemm<1, 128, kNV, 32, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
-    if (cta_group == 1 && block_n == 128 && M <= 64) return launch_gemm<1, 128, kNV, 64, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+    if (cta_group == 1 && block_n == 128 && M <= 16) return launch_gemm<1, 128, kNV, 16, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s, sw);
+    if (cta_group == 1 && block_n == 128 && M <= 32) return launch_gemm<1, 128, kNV, 32, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s, sw);
+    if (cta_group == 1 && block_n == 128 && M <= 64) return launch_gemm<1, 128, kNV, 64, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s, sw);
   }
+#ifdef B200Q_PROFILING
   if constexpr (kF8 == 0) {
-    if (cta_group == 2 && block_n == 448) {      // hybrid 256 + 192 tile pairs (compiled, not yet measured: explicit / opt-in only)
+    if (cta_group == 2 && block_n == 448) {      // hybrid 256 + 192 tile pairs (profiling builds only: measured not faster)
       if (!hybrid_eligible(M, N, K, ldd, kNV ? B200Q_KIND_NVF4 : B200Q_KIND_MXF4)) {
         set_error("configuration (2, 448) needs N %% 448 == 0, K %% 256 == 0 and a row pitch that is a multiple of 8 (N=%d K=%d ldd=%d)", N, K, ldd);
         return B200Q_EINVAL;
       }
-      return launch_gemm_hybrid<kNV>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+      return launch_gemm_hybrid<kNV>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s, sw);
     }
   }
+#endif
 #define B200Q_CASE(CG, BNV) \
-  if (cta_group == CG && block_n == BNV) return launch_gemm<CG, BNV, kNV, 128, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+  if (cta_group == CG && block_n == BNV) return launch_gemm<CG, BNV, kNV, 128, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s, sw);
   B200Q_CASE(1, 128)
   B200Q_CASE(1, 256)
   B200Q_CASE(2, 128)
@@ -1263,8 +1317,8 @@ static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B
   B200Q_CASE(2, 256)
   if constexpr (kF8 == 0) {
     // cta_group 4 = CTA pairs in clusters of four, A tiles multicast between the two pairs
-    if (cta_group == 4 && block_n == 256) return launch_gemm<2, 256, kNV, 128, 0, 0, 1>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
-    if (cta_group == 4 && block_n == 192) return launch_gemm<2, 192, kNV, 128, 0, 0, 1>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s);
+    if (cta_group == 4 && block_n == 256) return launch_gemm<2, 256, kNV, 128, 0, 0, 1>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s, sw);
+    if (cta_group == 4 && block_n == 192) return launch_gemm<2, 192, kNV, 128, 0, 0, 1>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s, sw);
   }
   if constexpr (kF8 == 0) {
     B200Q_CASE(1, 64)
@@ -1307,18 +1361,15 @@ static GemmPlan plan_auto(int M, int N, int K, int kind) {
       }
     }
   }
-  {
-    // opt-in (B200Q_GEMM_HYBRID=1): the 256 + 192 tile pairs wherever the CTA-pair plan applies and the shape allows them
-    const char* hyb = getenv("B200Q_GEMM_HYBRID");
-    if (hyb && hyb[0] == '1' && cta_group == 2 && hybrid_eligible(M, N, K, N, kind)) block_n = 448;
-  }
+#ifdef B200Q_PROFILING
+  if (env().gemm_hybrid && cta_group == 2 && hybrid_eligible(M, N, K, N, kind)) block_n = 448;
+#endif
   pl.cta_group = cta_group;
   pl.block_n = block_n;
   // Measured (profiles/r01_notes.md): the peeled launch costs more than the saved part of a round (92.5 vs 89.4 us at
   // config 1 with (2,128) tail tiles, 97.1 us with (1,64)), because a tile's sequential k-loop, not the tile count, sets
   // the length of the last round.  Kept as an opt-in experiment: B200Q_TAIL_SPLIT=1.
-  const char* split_env = getenv("B200Q_TAIL_SPLIT");
-  if (split_env && split_env[0] == '1' && cta_group == 2 && block_n == 256 && N % 8 == 0 && kind != B200Q_KIND_MXF8 && kind != B200Q_KIND_MXF8_NN) {
+  if (env().tail_split && cta_group == 2 && block_n == 256 && N % 8 == 0 && kind != B200Q_KIND_MXF8 && kind != B200Q_KIND_MXF8_NN) {
     // Wave quantisation: with T tiles over C CTA pairs the last round is only (T mod C)/C full.  When that round is
     // less than half full and peeling the LAST 256-column block of N saves a whole round, that block runs as a second
     // launch of narrower (2,128) tiles that fits in one wave (it starts as the main grid drains: PDL, disjoint D
@@ -1343,6 +1394,8 @@ extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA,
                                   int block_n, b200q_stream_t stream) {
   int rc = check_device_sm100();
   if (rc) return rc;
+  const bool static_w = (kind & B200Q_GEMM_STATIC_WEIGHTS) != 0;
+  kind &= ~B200Q_GEMM_STATIC_WEIGHTS;
   B200Q_REQUIRE(A && B && SFA && SFB && alpha_dev && D_bf16, "null pointer argument");
   B200Q_REQUIRE(kind == B200Q_KIND_MXF4 || kind == B200Q_KIND_NVF4 || kind == B200Q_KIND_MXF8 || kind == B200Q_KIND_MXF8_NN,
                 "invalid kind %d", kind);
@@ -1361,10 +1414,10 @@ extern "C" int b200q_gemm_fp4_cfg(const void* A, const void* B, const void* SFA,
   }
   cudaStream_t s = (cudaStream_t)stream;
   auto run = [&](int cg, int bn, const void* Bp, const void* SFBp, void* Dp, int n_sub) -> int {
-    if (kind == B200Q_KIND_NVF4) return dispatch_cfg<true, 0>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
-    if (kind == B200Q_KIND_MXF8) return dispatch_cfg<false, 1>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
-    if (kind == B200Q_KIND_MXF8_NN) return dispatch_cfg<false, 2>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
-    return dispatch_cfg<false, 0>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s);
+    if (kind == B200Q_KIND_NVF4) return dispatch_cfg<true, 0>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s, static_w);
+    if (kind == B200Q_KIND_MXF8) return dispatch_cfg<false, 1>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s, static_w);
+    if (kind == B200Q_KIND_MXF8_NN) return dispatch_cfg<false, 2>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s, static_w);
+    return dispatch_cfg<false, 0>(cg, bn, A, Bp, SFA, SFBp, alpha_dev, Dp, M, n_sub, K, N, s, static_w);
   };
   if (pl.n_main > 0) {
     const int group = kind == B200Q_KIND_NVF4 ? 16 : 32;
@@ -1386,10 +1439,11 @@ extern "C" int b200q_debug_read_trace(unsigned long long* out, int n) {
   return 0;
 }
 
-// host-only: the tile walk of the hybrid (2, 448) configuration (no device needed)
-extern "C" int b200q_debug_hybrid_tile(int sup, int half, int tiles_m, int* tm, int* n0) {
-  B200Q_REQUIRE(sup >= 0 && (half == 0 || half == 1) && tiles_m > 0 && tm && n0, "bad argument");
-  hybrid_tile_geom(sup, half, tiles_m, *tm, *n0);
+extern "C" int b200q_debug_tmap_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+  B200Q_REQUIRE(hits && misses, "bad argument");
+  *hits = g_tmap_hits;
+  *misses = g_tmap_misses;
+  g_tmap_hits = g_tmap_misses = 0;
   return 0;
 }
 
@@ -1405,8 +1459,7 @@ namespace b200q {
 // standalone quantise kernel takes (104.8 us fused with the producer never waiting vs 103.7 us for the two launches,
 // 93.8 us with the quantisers idle).  So the default is the two launches; B200Q_FUSE=1 opts into the single kernel.
 static bool fusion_enabled() {
-  const char* e = getenv("B200Q_FUSE");
-  return e && e[0] == '1';
+  return env().fuse != 0;
 }
 // the fused kernel needs: trusted Hadamard rotation, whole warp-tiles per row (K % 1024 == 0), TMA-store epilogue
 // (N % 8 == 0), the CTA-pair plan (M > 256 or wide N) and FP4 operands
@@ -1449,13 +1502,13 @@ extern "C" int b200q_linear_fp4(const void* x_bf16, const void* rot_bf16, void* 
             : b200q_quantize_mx(x_bf16, rot_bf16, xq_e2m1, x_sf_rowmajor, x_sf_blocked, nullptr, (int64_t)M * K, K, had,
                                 method, stream);
     if (rc) return rc;
-    return b200q_gemm_fp4(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, kind, stream);
+    return b200q_gemm_fp4(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, kind | B200Q_GEMM_STATIC_WEIGHTS, stream);
   }
   B200Q_REQUIRE(Wq && Wsf_blocked && alpha_dev && D_bf16, "null pointer argument");
   B200Q_REQUIRE((((uintptr_t)xq_e2m1 | (uintptr_t)Wq | (uintptr_t)x_sf_blocked | (uintptr_t)Wsf_blocked | (uintptr_t)D_bf16) & 15) == 0,
                 "xq, Wq, scale buffers and D must be 16-byte aligned");
   B200Q_REQUIRE(((uintptr_t)ws & 3) == 0, "workspace must be 4-byte aligned");
-  const int m = method & ~(B200Q_ROT_TRUSTED_HADAMARD | B200Q_ROT_GENERIC);
+  const int m = method & ~(B200Q_ROT_TRUSTED_HADAMARD | B200Q_ROT_GENERIC | B200Q_NV_SM100_CODES | B200Q_NV_ORACLE_CODES);
   B200Q_REQUIRE(m == B200Q_METHOD_QUEST || m == B200Q_METHOD_ABSMAX, "invalid method %d, must be quest (0) or abs_max (1)", m);
   B200Q_REQUIRE(had == 32 || had == 64 || had == 128 || (nv && had == 16),
                 nv ? "Unsupported rotation size %d; expected 16, 32, 64, or 128." : "Unsupported rotation size %d; expected 32, 64, or 128.", had);
@@ -1465,21 +1518,18 @@ extern "C" int b200q_linear_fp4(const void* x_bf16, const void* rot_bf16, void* 
   if (rc) return rc;
   fp.q.gs = global_scale_dev;
   fp.q.trust_hadamard = 1;
+  fp.q.nv_sm100_codes = (nv && had == 128 && m == B200Q_METHOD_ABSMAX && !(method & B200Q_NV_ORACLE_CODES)) ? 1 : 0;
   fp.ctr = (uint32_t*)ws;
   fp.tiles_per_row = (uint32_t)(K / 1024);
   fp.had = had;
   fp.method = m;
   const GemmPlan pl = plan_auto(M, N, K, kind);
   cudaStream_t s = (cudaStream_t)stream;
-  int qwarps = 4;
-  {
-    const char* e = getenv("B200Q_FUSE_WARPS");
-    if (e && e[0] == '2') qwarps = 2;
-  }
+  const int qwarps = env().fuse_warps;
 #define B200Q_FCASE(BNV, QW)                                                                                                  \
   if (pl.block_n == BNV && qwarps == QW)                                                                                      \
-    return nv ? launch_gemm<2, BNV, true, 128, false, QW>(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, N, s, &fp) \
-              : launch_gemm<2, BNV, false, 128, false, QW>(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, N, s, &fp);
+    return nv ? launch_gemm<2, BNV, true, 128, false, QW>(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, N, s, true, &fp) \
+              : launch_gemm<2, BNV, false, 128, false, QW>(xq_e2m1, Wq, x_sf_blocked, Wsf_blocked, alpha_dev, D_bf16, M, N, K, N, s, true, &fp);
   B200Q_FCASE(256, 4)
   B200Q_FCASE(192, 4)
   B200Q_FCASE(128, 4)

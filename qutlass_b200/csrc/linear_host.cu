@@ -121,7 +121,7 @@ extern "C" int b200q_linear_fp4_host(const void* x_host, const void* rot_bf16, c
       rc = b200q_quantize_mx(xs, rot_bf16, qs, nullptr, sfs, nullptr, (int64_t)rows * K, K, had, B200Q_METHOD_ABSMAX,
                              stream);
     if (rc) return rc;
-    rc = b200q_gemm_fp4(qs, Wq, sfs, Wsf_blocked, alpha_dev, ds, rows, N, K, kind, stream);
+    rc = b200q_gemm_fp4(qs, Wq, sfs, Wsf_blocked, alpha_dev, ds, rows, N, K, kind | B200Q_GEMM_STATIC_WEIGHTS, stream);   // pre-quantised weights by contract
     if (rc) return rc;
     B200Q_CUDA(cudaEventRecord(ss.out_ready[i], s));
     B200Q_CUDA(cudaStreamWaitEvent(ss.d2h, ss.out_ready[i], 0));

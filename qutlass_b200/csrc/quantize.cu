@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kMmaThreads) quantize_mma_kernel(const QuantPa
                 float sfv = gs * (amax * rcp_approx_ftz(6.0f));
                 const __nv_fp8_e4m3 t(sfv);
                 sfb = *reinterpret_cast<const uint8_t*>(&t);
-                sfv = float(t);
+                if (!p.nv_sm100_codes) sfv = float(t);      // reference sm_100 Hadamard-128 flavour: codes from the unrounded scale
                 out_scale = (sfv != 0.f) ? rcp_approx_ftz(sfv * gs_rcp) : 0.f;
               }
               sf_bytes |= (uint32_t)sfb << (8 * h16);
@@ -508,8 +508,7 @@ static bool use_butterfly() {
   // The tensor-core (mma.sync) kernel handles ANY rotation at full speed: it is used when the caller says the rotation
   // is not a Hadamard matrix (B200Q_ROT_GENERIC) or when B200Q_QUANT_MMA=1 forces it.
   if (g_rot_generic) return false;
-  const char* e = getenv("B200Q_QUANT_MMA");
-  return !(e && e[0] == '1');
+  return !env().quant_mma;
 }
 
 // tcgen05 rotation kernel (quantize_tc.cu): streams at the HBM rate for any runtime R, but pays ~1.7 us more fixed
@@ -519,11 +518,9 @@ static bool use_butterfly() {
 // is the mma.sync kernel).  B200Q_QUANT_TC=0 / 1 forces it off / on (when eligible).
 static bool use_tc(const QuantParams& p, int had, bool nv) {
   if (!quantize_tc_eligible(p, had, nv)) return false;
-  const char* m = getenv("B200Q_QUANT_MMA");
-  if (m && m[0] == '1') return false;
-  const char* e = getenv("B200Q_QUANT_TC");
-  if (e && e[0] == '0') return false;
-  if (e && e[0] == '1') return true;
+  if (env().quant_mma) return false;
+  if (env().quant_tc == 0) return false;
+  if (env().quant_tc == 1) return true;
   const int64_t tiles = p.n_chunks / 512;
   if (g_rot_generic) return tiles >= 32;
   if (had >= 64) return tiles >= 256;
@@ -570,6 +567,7 @@ int fill_params(QuantParams& p, const void* x, const void* rot, void* q, void* s
   p.padded_rows = round_up(p.rows, 128);
   p.padded_cols = round_up(p.cols, 4);
   p.trust_hadamard = 0;
+  p.nv_sm100_codes = 0;
   return 0;
 }
 
@@ -615,15 +613,13 @@ extern "C" int b200q_quantize_nv(const void* x_bf16, const void* rot_bf16, void*
   p.gs = global_scale_dev;
   p.trust_hadamard = (method & B200Q_ROT_TRUSTED_HADAMARD) ? 1 : 0;
   g_rot_generic = (method & B200Q_ROT_GENERIC) != 0 && !p.trust_hadamard;
-  const bool sm100_codes = (method & B200Q_NV_SM100_CODES) != 0;
-  method &= ~(B200Q_ROT_TRUSTED_HADAMARD | B200Q_ROT_GENERIC | B200Q_NV_SM100_CODES);
+  const bool oracle_codes = (method & B200Q_NV_ORACLE_CODES) != 0;
+  method &= ~(B200Q_ROT_TRUSTED_HADAMARD | B200Q_ROT_GENERIC | B200Q_NV_SM100_CODES | B200Q_NV_ORACLE_CODES);
   cudaStream_t s = (cudaStream_t)stream;
-  // opt-in: bit-compatibility with the ONE case where the reference's sm_100 dispatch deviates from its other kernels and
-  // from its test oracle (abs_max, Hadamard-128: bindings.cpp:413-415 -> fused_quantize_nv_sm100.cu).  Always the tcgen05 kernel.
-  if (sm100_codes && method == B200Q_METHOD_ABSMAX && had == 128) {
-    B200Q_REQUIRE(quantize_tc_eligible(p, had, true), "B200Q_NV_SM100_CODES needs 16-byte aligned rotation / 8-byte aligned scale buffers");
-    return launch_quantize_tc(p, had, true, method, s, true);
-  }
+  // The ONE case where the reference's sm_100 dispatch deviates from its other kernels and from its test oracle (abs_max,
+  // Hadamard-128: bindings.cpp:413-415 -> fused_quantize_nv_sm100.cu): reproduced by default, see b200q.h.
+  p.nv_sm100_codes = (method == B200Q_METHOD_ABSMAX && had == 128 && !oracle_codes) ? 1 : 0;
+
   if (method == B200Q_METHOD_QUEST) return dispatch_had<true, B200Q_METHOD_QUEST, false>(had, p, s);
   if (method == B200Q_METHOD_ABSMAX) return dispatch_had<true, B200Q_METHOD_ABSMAX, false>(had, p, s);
   set_error("invalid method %d, must be quest (0) or abs_max (1)", method);

@@ -49,7 +49,7 @@ constexpr int kTcSmem = kTcStages * kTcStageBytes + kTcRotBytes + kTcOutBytes + 
 static_assert(kTcEpiWarps == 4 * kTcAcc, "one group of 4 epilogue warps (one per TMEM lane quarter) per accumulator stage");
 static_assert(kTcSmem <= 227 * 1024, "shared memory budget");
 
-template <bool NV, int METHOD, bool MASK, bool NVQ = false>
+template <bool NV, int METHOD, bool MASK>
 __global__ void __launch_bounds__(kTcThreads, 1)
 quantize_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_r, const QuantParams p,
                    const int had, const int64_t n_tiles) {
@@ -182,6 +182,7 @@ quantize_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       const int q = warp & 3;                  // TMEM lane quarter this warp may access
       const int grp = ew >> 2;                 // accumulator stage / tile residue this warp's group owns
       uint8_t* ostage = smem_gen + kTcStages * kTcStageBytes + kTcRotBytes + ew * kTcOutWarpBytes;
+      const bool nvq = NV && METHOD == B200Q_METHOD_ABSMAX && p.nv_sm100_codes != 0;
       float gs = 1.f, gs_rcp = 1.f;
       if constexpr (NV) {
         gs = *p.gs;
@@ -209,8 +210,8 @@ quantize_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
               __syncwarp();
               if (lane == 0) mbar_arrive(tempty_bar(grp));
             }
-            chunk_quantise<NV, METHOD, MASK, NVQ>(reinterpret_cast<float*>(r0), gs, gs_rcp, out[2 * h], sfb[2 * h], mk[2 * h]);
-            chunk_quantise<NV, METHOD, MASK, NVQ>(reinterpret_cast<float*>(r1), gs, gs_rcp, out[2 * h + 1], sfb[2 * h + 1], mk[2 * h + 1]);
+            chunk_quantise<NV, METHOD, MASK>(reinterpret_cast<float*>(r0), gs, gs_rcp, out[2 * h], sfb[2 * h], mk[2 * h], nvq);
+            chunk_quantise<NV, METHOD, MASK>(reinterpret_cast<float*>(r1), gs, gs_rcp, out[2 * h + 1], sfb[2 * h + 1], mk[2 * h + 1], nvq);
           }
         } else {
           // NVFP4: a chunk already holds two independent 16-groups and its arithmetic needs more registers (two scales,
@@ -225,7 +226,7 @@ quantize_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
               __syncwarp();
               if (lane == 0) mbar_arrive(tempty_bar(grp));
             }
-            chunk_quantise<NV, METHOD, MASK, NVQ>(reinterpret_cast<float*>(r0), gs, gs_rcp, out[c], sfb[c], mk[c]);
+            chunk_quantise<NV, METHOD, MASK>(reinterpret_cast<float*>(r0), gs, gs_rcp, out[c], sfb[c], mk[c], nvq);
           }
         }
 
@@ -307,9 +308,9 @@ bool quantize_tc_eligible(const QuantParams& p, int had, bool nv) {
   return true;
 }
 
-template <bool NV, int METHOD, bool MASK, bool NVQ = false>
+template <bool NV, int METHOD, bool MASK>
 static int launch_tc(const QuantParams& p, int had, cudaStream_t stream) {
-  auto kern = quantize_tc_kernel<NV, METHOD, MASK, NVQ>;
+  auto kern = quantize_tc_kernel<NV, METHOD, MASK>;
   static std::atomic<unsigned long long> smem_attr_done{0};   // per instantiation, one bit per device
   if (int rc_attr = ensure_dynamic_smem(kern, kTcSmem, smem_attr_done)) return rc_attr;
   const int64_t rows = p.n_chunks / 4;
@@ -333,9 +334,7 @@ static int launch_tc(const QuantParams& p, int had, cudaStream_t stream) {
   return 0;
 }
 
-int launch_quantize_tc(const QuantParams& p, int had, bool nv, int method, cudaStream_t stream, bool nv_sm100_codes) {
-  // opt-in (B200Q_NV_SM100_CODES): the reference's sm_100 NVFP4 Hadamard-128 abs_max arithmetic (codes from the unrounded scale)
-  if (nv && nv_sm100_codes && method == B200Q_METHOD_ABSMAX) return launch_tc<true, B200Q_METHOD_ABSMAX, false, true>(p, had, stream);
+int launch_quantize_tc(const QuantParams& p, int had, bool nv, int method, cudaStream_t stream) {
   if (nv) {
     if (method == B200Q_METHOD_QUEST) return launch_tc<true, B200Q_METHOD_QUEST, false>(p, had, stream);
     return launch_tc<true, B200Q_METHOD_ABSMAX, false>(p, had, stream);

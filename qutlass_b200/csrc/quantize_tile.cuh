@@ -25,6 +25,7 @@ struct QuantParams {
   int64_t rows;
   int64_t padded_rows;
   int trust_hadamard;      // caller asserted R = c * Sylvester-Hadamard (B200Q_ROT_TRUSTED_HADAMARD)
+  int nv_sm100_codes;      // NVFP4 abs_max H = 128: codes from the UNROUNDED scale, like the reference's sm_100 kernel (b200q.h)
 };
 
 __device__ __forceinline__ float rcp_approx_ftz(float a) {
@@ -134,12 +135,12 @@ __device__ __forceinline__ void tile_rotate_hadamard(float* v, float c_scale) {
 
 // Per-group scale and e2m1 conversion of ONE rotated 32-element chunk held in v[0..31] (scaled in place): 32 codes in
 // out[0..3], the scale byte(s) in sf_bytes (MX: 1 byte, NV: 2 bytes little-endian), the clip mask word.
-// NVQ (NVFP4 abs_max only, opt-in B200Q_NV_SM100_CODES): the codes are computed with the scale BEFORE its e4m3 rounding, like
-// the reference's sm_100-only Hadamard-128 kernel (sm100_visitor_store_tma_warpspecialized.hpp:141-148,567-591); the
-// stored scale byte is the rounded one either way.
-template <bool NV, int METHOD, bool MASK, bool NVQ = false>
+// nvq (NVFP4 abs_max only; set for Hadamard-128 unless B200Q_NV_ORACLE_CODES): the codes are computed with the scale BEFORE
+// its e4m3 rounding, like the reference's sm_100-only Hadamard-128 kernel
+// (sm100_visitor_store_tma_warpspecialized.hpp:141-148,567-591); the stored scale byte is the rounded one either way.
+template <bool NV, int METHOD, bool MASK>
 __device__ __forceinline__ void chunk_quantise(float* v, float gs, float gs_rcp, uint32_t (&out)[4], uint32_t& sf_bytes,
-                                               uint32_t& mask_word) {
+                                               uint32_t& mask_word, bool nvq = false) {
     mask_word = 0;
     sf_bytes = 0;
     if constexpr (!NV) {
@@ -199,7 +200,7 @@ __device__ __forceinline__ void chunk_quantise(float* v, float gs, float gs_rcp,
           float sfv = gs * (amax * rcp_approx_ftz(6.0f));
           const __nv_fp8_e4m3 t(sfv);
           sfb = *reinterpret_cast<const uint8_t*>(&t);
-          if constexpr (!NVQ) sfv = float(t);
+          if (!nvq) sfv = float(t);
           out_scale = (sfv != 0.f) ? rcp_approx_ftz(sfv * gs_rcp) : 0.f;
         }
         sf_bytes |= (uint32_t)sfb << (8 * h);
@@ -224,7 +225,7 @@ template <bool NV, int METHOD, bool MASK>
 __device__ __forceinline__ void chunk_quantise_store(const QuantParams& p, float* v, int64_t chunk, float gs, float gs_rcp) {
     uint32_t out[4];
     uint32_t mask_word, sf_bytes;
-    chunk_quantise<NV, METHOD, MASK>(v, gs, gs_rcp, out, sf_bytes, mask_word);
+    chunk_quantise<NV, METHOD, MASK>(v, gs, gs_rcp, out, sf_bytes, mask_word, p.nv_sm100_codes != 0);
     if (chunk < p.n_chunks) {
       p.q[chunk] = make_uint4(out[0], out[1], out[2], out[3]);
       if constexpr (MASK) {
@@ -278,6 +279,6 @@ int fill_params(QuantParams& p, const void* x, const void* rot, void* q, void* s
 
 // tensor-core (tcgen05) rotation kernel, quantize_tc.cu: any runtime rotation, numel % 128 == 0
 bool quantize_tc_eligible(const QuantParams& p, int had, bool nv);
-int launch_quantize_tc(const QuantParams& p, int had, bool nv, int method, cudaStream_t stream, bool nv_sm100_codes = false);
+int launch_quantize_tc(const QuantParams& p, int had, bool nv, int method, cudaStream_t stream);
 
 }  // namespace b200q

@@ -36,20 +36,41 @@ def _version_of(t: torch.Tensor) -> int:
 
 
 def _attach_blocked(sf_rowmajor: torch.Tensor, blocked: torch.Tensor) -> None:
-    setattr(sf_rowmajor, _BLOCKED_ATTR, (blocked, _version_of(sf_rowmajor)))
+    """Remember the blocked copy the quantise kernel wrote next to the row-major scales it belongs to.
+
+    Only for tensors with a working version counter: an in-place edit of the row-major scales between the quantiser and
+    to_blocked (``scales[m:] = 1.0``) must invalidate the copy, and inference tensors (torch.inference_mode) do not
+    track versions -- for those nothing is attached and to_blocked runs its kernel."""
+    ver = _version_of(sf_rowmajor)
+    if ver >= 0:
+        setattr(sf_rowmajor, _BLOCKED_ATTR, (blocked, ver, sf_rowmajor.data_ptr()))
+
+
+def _detach_blocked(sf_rowmajor: torch.Tensor) -> None:
+    """Called by every path that overwrites a scale tensor through its data pointer (the raw torch.ops._qutlass_C
+    quantise ops write OUT_sf without bumping its version)."""
+    if getattr(sf_rowmajor, _BLOCKED_ATTR, None) is not None:
+        try:
+            delattr(sf_rowmajor, _BLOCKED_ATTR)
+        except AttributeError:
+            pass
 
 
 def to_blocked(input_matrix: torch.Tensor, use_triton_kernel: bool = False) -> torch.Tensor:
     """Row-major scales (H, W) -> flattened block-scaled layout (reference: qutlass/utils.py:160-193).
 
-    If `input_matrix` came straight out of fusedQuantizeMx / fusedQuantizeNv the blocked copy was
-    already written by the quantise kernel and is returned as is (no launch).  Otherwise one CUDA
-    swizzle kernel runs.  `use_triton_kernel` is accepted for drop-in compatibility and ignored
-    (there is no Triton here); like the reference's Triton path, inputs need not be pre-padded.
+    If `input_matrix` came straight out of fusedQuantizeMx / fusedQuantizeNv, has not been modified since (version
+    counter) and this is the first to_blocked call on it, the blocked copy the quantise kernel wrote in the same pass is
+    HANDED OVER (no launch; the caller now owns that buffer exclusively, exactly like the fresh tensor the reference
+    returns).  In every other case -- a second call, an edited tensor, an inference-mode tensor (no version counter), a
+    foreign scale tensor -- one CUDA swizzle kernel runs.  `use_triton_kernel` is accepted for drop-in compatibility
+    and ignored (there is no Triton here); like the reference's Triton path, inputs need not be pre-padded.
     """
     cached = getattr(input_matrix, _BLOCKED_ATTR, None)
-    if cached is not None and cached[1] == _version_of(input_matrix):
-        return cached[0]
+    if cached is not None:
+        _detach_blocked(input_matrix)
+        if cached[1] >= 0 and cached[1] == _version_of(input_matrix) and cached[2] == input_matrix.data_ptr():
+            return cached[0]
     assert input_matrix.dim() == 2, "to_blocked expects a 2-D scale matrix"
     assert input_matrix.element_size() == 1, "Expected element size to be 1 byte (8 bits)"
     if not input_matrix.is_cuda:

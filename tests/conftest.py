@@ -27,3 +27,21 @@ def _seed():
         torch.manual_seed(0)
     except Exception:
         pass
+
+
+@pytest.fixture
+def b200q_env(monkeypatch):
+    """Set / unset a B200Q_* switch of libb200q for one test.  The library caches its environment at first use
+    (include/b200q.h: b200q_reload_env), so every change is followed by a reload, and so is the clean-up."""
+    from qutlass_b200 import _lib
+
+    def set_(name, value):
+        if value is None:
+            monkeypatch.delenv(name, raising=False)
+        else:
+            monkeypatch.setenv(name, str(value))
+        _lib.reload_env()
+
+    yield set_
+    monkeypatch.undo()
+    _lib.reload_env()

@@ -19,7 +19,7 @@ def _declared():
     src = open(os.path.join(ROOT, "include", "b200q.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     decls = {}
-    for m in re.finditer(r"\b(int|int64_t|const char\*)\s+(b200q_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(int|int64_t|const char\*|void)\s+(b200q_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(3).strip()
         n = 0 if args in ("void", "") else len([a for a in args.split(",") if a.strip()])
         decls[m.group(2)] = n
@@ -113,55 +113,48 @@ def test_host_entry_slab_schedule_without_a_gpu(lib_path):
     assert lib.b200q_linear_host_slabs(4096, (ctypes.c_int * 4)(), 4) < 0       # not enough room for the bounds
 
 
-def test_hybrid_tile_pairs_are_opt_in(lib_path, monkeypatch):
-    """the 256 + 192 tile-pair configuration (2, 448) is compiled but unmeasured: the planner only picks it with
-    B200Q_GEMM_HYBRID=1 and only where N % 448 == 0 and K % 256 == 0 (the Llama FFN up-projections)."""
+def test_product_library_has_no_profiling_switches(lib_path, monkeypatch):
+    """the product library must not read timing-only switches that corrupt results.  B200Q_GEMM_DEBUG_FLAGS and
+    the hybrid (2, 448) tile pairs (measured not faster, profiles/r02_notes.md) exist only in the -DB200Q_PROFILING build."""
     from qutlass_b200 import _lib
     lib = _lib.load()
+    assert lib.b200q_profiling_build() == 0
 
     def plan(m, n, k, kind=0):
         cg, bn = ctypes.c_int(0), ctypes.c_int(0)
         assert lib.b200q_gemm_fp4_plan(m, n, k, kind, ctypes.byref(cg), ctypes.byref(bn)) == 0
         return cg.value, bn.value
 
-    monkeypatch.delenv("B200Q_GEMM_HYBRID", raising=False)
-    assert plan(4096, 14336, 4096) == (2, 256)
     monkeypatch.setenv("B200Q_GEMM_HYBRID", "1")
-    assert plan(4096, 14336, 4096) == (2, 448) and plan(2048, 28672, 8192, 1) == (2, 448)
-    assert plan(4096, 4096, 14336) == (2, 256)          # N % 448 != 0
-    assert plan(128, 14336, 4096) == (1, 128)           # the weight-streaming regime keeps its single-CTA tiles
-    assert plan(4096, 14336, 4096, 2)[1] != 448         # MXFP8: FP4 kinds only
+    monkeypatch.setenv("B200Q_GEMM_DEBUG_FLAGS", "33")
+    _lib.reload_env()
+    try:
+        assert plan(4096, 14336, 4096) == (2, 256)
+        assert b"gemm_fp4_hybrid_kernel" not in open(lib_path, "rb").read()
+    finally:
+        monkeypatch.delenv("B200Q_GEMM_HYBRID")
+        monkeypatch.delenv("B200Q_GEMM_DEBUG_FLAGS")
+        _lib.reload_env()
 
 
-def test_hybrid_tile_walk_covers_the_output_with_legal_scale_alignment(lib_path):
-    """gemm_fp4_hybrid_kernel's tile walk (hybrid_tile_geom, shared by the kernel and this host-only debug export): super
-    tiles of 448 columns = one 256-wide + one 192-wide tile, laid out W N | N W.  Checked here without a GPU: the tiles of a
-    row block partition [0, N) exactly; every wide tile starts on a 128-row scale block (its two SFB blocks are whole);
-    every narrow tile starts 0 or 64 rows into one (an EVEN TMEM column shift -- odd shifts fault on the hardware) and its
-    192 rows stay inside the two SFB blocks the producer loads; and the M-fastest order keeps a CTA pair on one row block
-    per super tile."""
-    lib = ctypes.CDLL(lib_path)
-    fn = lib.b200q_debug_hybrid_tile
-    fn.argtypes = [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2
-    for n, tiles_m in ((448, 1), (896, 3), (14336, 16), (28672, 8)):
-        supers_n = n // 448
-        for tm_want in range(tiles_m):
-            spans = []
-            for sn in range(supers_n):
-                sup = sn * tiles_m + tm_want
-                for half, width in ((0, 256), (1, 192)):
-                    tm, n0 = ctypes.c_int(), ctypes.c_int()
-                    assert fn(sup, half, tiles_m, ctypes.byref(tm), ctypes.byref(n0)) == 0
-                    assert tm.value == tm_want
-                    start = n0.value
-                    if half == 0:
-                        assert start % 128 == 0
-                    else:
-                        assert start % 128 in (0, 64) and ((start % 128) // 32) % 2 == 0
-                    first_block = start // 128
-                    assert start + width <= (first_block + 2) * 128          # inside the 2 SFB row blocks that are loaded
-                    assert (first_block + 1) * 128 < n + 128                   # second block exists in the padded scale buffer
-                    spans.append((start, start + width))
-            spans.sort()
-            assert spans[0][0] == 0 and spans[-1][1] == n
-            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+def test_environment_switches_are_cached_until_reload(lib_path, monkeypatch):
+    """The library reads its switches once (no getenv per launch); b200q_reload_env re-reads them."""
+    from qutlass_b200 import _lib
+    lib = _lib.load()
+
+    def launches():
+        return lib.b200q_gemm_fp4_launches(4096, 14336 + 256, 4096, 0)
+
+    monkeypatch.delenv("B200Q_TAIL_SPLIT", raising=False)
+    _lib.reload_env()
+    base = launches()
+    monkeypatch.setenv("B200Q_TAIL_SPLIT", "1")
+    assert launches() == base              # not re-read yet
+    _lib.reload_env()
+    after = launches()
+    monkeypatch.delenv("B200Q_TAIL_SPLIT")
+    _lib.reload_env()
+    assert launches() == base
+    assert after in (1, 2)
+
+

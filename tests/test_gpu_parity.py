@@ -96,7 +96,7 @@ def test_quantize_mx_golden_reference_vectors(golden, had, method):
 
 
 @pytest.mark.parametrize("had", [16, 32, 64, 128])
-def test_quantize_nv_golden_reference_vectors(golden, had):
+def test_quantize_nv_golden_reference_vectors(golden, had, monkeypatch):
     x = O.bf16_from_bits(golden["mx_x_bits"])
     R = O.bf16_from_bits(golden[f"had{had}_bits"])
     gst = torch.tensor([6.0], dtype=torch.float32, device="cuda")
@@ -104,7 +104,16 @@ def test_quantize_nv_golden_reference_vectors(golden, had):
     torch.cuda.synchronize()
     rows, k = x.shape
     dq = O.dequant_nv(H.u8_of(q), _flat_sf(sf_t, rows, k // 16), alpha=6.0)
-    assert (dq != golden[f"nv_h{had}_dq"]).mean() <= 1e-2
+    # golden = the reference's fp64 TEST ORACLE.  For Hadamard-128 the default follows the reference's sm_100 KERNEL, which
+    # sits 4.8 % from that oracle (the reference's own bar there is 1e-1, tests/nvfp4_test.py:204-205); the oracle-arithmetic
+    # switch brings it back under 1e-2 like every other size
+    assert (dq != golden[f"nv_h{had}_dq"]).mean() <= (1e-1 if had == 128 else 1e-2)
+    if had == 128:
+        monkeypatch.setenv("B200Q_NV128_ORACLE_CODES", "1")
+        q, sf_t = Q.fusedQuantizeNv(H.bf16_tensor_from_f32(x), H.bf16_tensor_from_f32(R), gst)
+        torch.cuda.synchronize()
+        dq = O.dequant_nv(H.u8_of(q), _flat_sf(sf_t, rows, k // 16), alpha=6.0)
+        assert (dq != golden[f"nv_h{had}_dq"]).mean() <= 1e-2
 
 
 def test_quantize_edge_cases():
@@ -199,12 +208,12 @@ def test_quantize_arbitrary_rotation_on_tensor_cores(kind, had):
 @pytest.mark.parametrize("kind,had", [("mx", 32), ("mx", 64), ("mx", 128), ("nv", 16), ("nv", 32), ("nv", 64), ("nv", 128)])
 @pytest.mark.parametrize("method", ["abs_max", "quest"])
 @pytest.mark.parametrize("shape", [(384, 2048), (132, 160), (1000, 4096)])
-def test_quantize_tcgen05_kernel_vs_oracle(kind, had, method, shape, monkeypatch):
+def test_quantize_tcgen05_kernel_vs_oracle(kind, had, method, shape, b200q_env):
     """The tcgen05 rotation kernel (quantize_tc.cu; default for large inputs, forced here with B200Q_QUANT_TC=1) against
     the oracle: codes, row-major scales, the blocked copy and the clip mask.  (132, 160): 5 / 10 scales per row, so a
     128-element row of the kernel's flat view straddles matrix rows (byte-granular blocked stores) and the last tile
     is partial; (1000, 4096): 8 tiles per CTA-round with a ragged row count."""
-    monkeypatch.setenv("B200Q_QUANT_TC", "1")
+    b200q_env("B200Q_QUANT_TC", "1")
     rows, k = shape
     if (rows * k) % had:
         pytest.skip("numel % H")
@@ -232,7 +241,7 @@ def test_quantize_tcgen05_kernel_vs_oracle(kind, had, method, shape, monkeypatch
     np.testing.assert_array_equal(H.u8_of(Q.to_blocked(out[1])), H.blocked_sf(sf))
 
 
-def test_quantize_tcgen05_kernel_is_the_large_input_default_and_matches_the_butterfly_kernel(monkeypatch):
+def test_quantize_tcgen05_kernel_is_the_large_input_default_and_matches_the_butterfly_kernel(b200q_env):
     """4096 x 4096, Hadamard-128 (bench.py's activation tensor) dispatches to the tcgen05 kernel; forcing the butterfly
     kernel gives the same bytes up to summation-order rounding (<= 1e-5 of the codes), any non-symmetric runtime rotation
     agrees with the oracle (the rotation is an MN-major tensor-core operand: a transposed R would show here)."""
@@ -240,14 +249,14 @@ def test_quantize_tcgen05_kernel_is_the_large_input_default_and_matches_the_butt
     Rt = H.bf16_tensor_from_f32(O.hadamard_matrix(128))
     q1, sf1 = Q.fusedQuantizeMx(x, Rt, method="abs_max")
     b1 = Q.to_blocked(sf1).clone()
-    monkeypatch.setenv("B200Q_QUANT_TC", "0")
+    b200q_env("B200Q_QUANT_TC", "0")
     q0, sf0 = Q.fusedQuantizeMx(x, Rt, method="abs_max")
     b0 = Q.to_blocked(sf0)
     torch.cuda.synchronize()
     assert (q0 != q1).float().mean().item() <= 1e-5
     assert (sf0.view(torch.uint8) != sf1.view(torch.uint8)).float().mean().item() <= 1e-5
     assert (b0.view(torch.uint8) != b1.view(torch.uint8)).float().mean().item() <= 1e-5
-    monkeypatch.setenv("B200Q_QUANT_TC", "1")
+    b200q_env("B200Q_QUANT_TC", "1")
     for had in (32, 64, 128):
         xs = H.random_bf16((256, 1024), seed=had)
         R = O.bf16_round(np.random.default_rng(had).standard_normal((had, had)).astype(np.float32) * had ** -0.5)
@@ -319,49 +328,6 @@ def test_gemm_bit_exact_vs_oracle(kind, cfg, shape):
         assert mism == 0.0, (mism, rel)       # pow2 scales within +-1: fp32 accumulation is exact
     else:
         assert rel <= REL_TOL and mism <= 1e-3, (mism, rel)
-
-
-# The hybrid 256 + 192 tile pairs (configuration (2, 448), gemm_fp4_hybrid_kernel) were written after round 1's GPU budget
-# was spent: compiled, never run.  An unproven tcgen05 kernel can hang, so these cases only run when asked for
-# (B200Q_TEST_HYBRID=1) -- the first thing to do with a GPU in round 2, under a `timeout`.
-import os  # noqa: E402
-hybrid_opt_in = pytest.mark.skipif(os.environ.get("B200Q_TEST_HYBRID") != "1",
-                                   reason="unproven kernel: set B200Q_TEST_HYBRID=1 (and wrap the run in a timeout)")
-
-
-@hybrid_opt_in
-@pytest.mark.parametrize("kind", ["mx", "nv"])
-@pytest.mark.parametrize("shape", [(256, 448, 256), (256, 896, 512), (300, 1344, 1024), (1, 448, 4096), (700, 2240, 2048)])
-def test_gemm_hybrid_bit_exact_vs_oracle(kind, shape):
-    m, n, k = shape
-    aq, asf = H.random_fp4_operand(m, k, kind, seed=m + 3, sf_mode="narrow")
-    bq, bsf = H.random_fp4_operand(n, k, kind, seed=n + 4, sf_mode="narrow")
-    want = H.gemm_oracle_bits(aq, asf, bq, bsf, kind, 1.0)
-    got = H.run_gemm(aq, asf, bq, bsf, kind, 1.0, cfg=(2, 448))
-    mism, rel = H.compare_bits(got, want)
-    if kind == "mx":
-        assert mism == 0.0, (mism, rel)
-    else:
-        assert rel <= REL_TOL and mism <= 1e-3, (mism, rel)
-    np.testing.assert_array_equal(got, H.run_gemm(aq, asf, bq, bsf, kind, 1.0, cfg=(2, 256)))
-
-
-@hybrid_opt_in
-@pytest.mark.parametrize("kind", ["mx", "nv"])
-def test_gemm_hybrid_full_size_identical(kind):
-    m, n, k = 4096, 14336, 4096
-    aq, asf = H.random_fp4_operand(m, k, kind, seed=71, sf_mode="wide")
-    bq, bsf = H.random_fp4_operand(n, k, kind, seed=72, sf_mode="wide")
-    np.testing.assert_array_equal(H.run_gemm(aq, asf, bq, bsf, kind, 1.0 / 9.0, cfg=(2, 448)),
-                                  H.run_gemm(aq, asf, bq, bsf, kind, 1.0 / 9.0, cfg=(2, 256)))
-
-
-@hybrid_opt_in
-def test_gemm_hybrid_rejects_ineligible_shapes():
-    aq, asf = H.random_fp4_operand(128, 256, "mx", seed=1)
-    bq, bsf = H.random_fp4_operand(512, 256, "mx", seed=2)
-    with pytest.raises(Exception, match="448"):
-        H.run_gemm(aq, asf, bq, bsf, "mx", 1.0, cfg=(2, 448))
 
 
 @pytest.mark.parametrize("kind", ["mx", "nv"])
@@ -586,15 +552,15 @@ def _fused_case(m, n, k, had, method, fmt, seed):
 @pytest.mark.parametrize("fmt,had,method", [("mx", 128, "abs_max"), ("mx", 64, "quest"), ("mx", 32, "abs_max"),
                                             ("nv", 16, "abs_max"), ("nv", 128, "quest"), ("nv", 64, "abs_max")])
 @pytest.mark.parametrize("shape", [(512, 512, 1024), (1000, 1544, 2048), (300, 4096, 1024), (2048, 2304, 4096)])
-def test_fused_linear_equals_two_calls(fmt, had, method, shape, monkeypatch):
+def test_fused_linear_equals_two_calls(fmt, had, method, shape, b200q_env):
     """b200q_linear_fp4 (quantiser warps inside the persistent GEMM) must reproduce fusedQuantize* followed by matmul_*
     bit for bit: codes, both scale layouts and the bf16 output."""
     m, n, k = shape
     assert _lib.load().b200q_linear_fp4_launches(m, n, k, had, 1 | Q.ROT_TRUSTED_HADAMARD, 0) >= 2   # default: two launches
-    monkeypatch.setenv("B200Q_FUSE", "1")
+    b200q_env("B200Q_FUSE", "1")
     # the fused kernel's quantiser warps run the butterfly arithmetic; large standalone inputs would otherwise take the
     # tcgen05 kernel, which differs from it in fp32 summation order (<= 1e-5 of the codes, see the tcgen05 tests)
-    monkeypatch.setenv("B200Q_QUANT_TC", "0")
+    b200q_env("B200Q_QUANT_TC", "0")
     R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, had, method, fmt, seed=m + n)
     lib = _lib.load()
     meth = (0 if method == "quest" else 1) | Q.ROT_TRUSTED_HADAMARD
@@ -611,11 +577,11 @@ def test_fused_linear_equals_two_calls(fmt, had, method, shape, monkeypatch):
         assert int(ws.view(torch.int32).abs().sum()) == 0           # left zeroed
 
 
-def test_fused_linear_fallback_and_graph(monkeypatch):
+def test_fused_linear_fallback_and_graph(b200q_env):
     """shapes the fused kernel does not take (K % 1024 != 0, small M) run as two launches with the same results; the
     fused kernel is CUDA-graph capturable once its workspace exists."""
     lib = _lib.load()
-    monkeypatch.setenv("B200Q_FUSE", "1")
+    b200q_env("B200Q_FUSE", "1")
     for (m, n, k) in ((512, 512, 1536), (128, 1024, 1024)):
         R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, 64, "abs_max", "mx", seed=7)
         assert lib.b200q_linear_fp4_launches(m, n, k, 64, 1 | Q.ROT_TRUSTED_HADAMARD, 0) == 2
@@ -639,17 +605,17 @@ def test_fused_linear_fallback_and_graph(monkeypatch):
         assert torch.equal(out, want)
 
 
-def test_fused_linear_full_size(monkeypatch):
+def test_fused_linear_full_size(b200q_env):
     """config 1 (4096 x 14336 x 4096) through the fused kernel, 20 back-to-back calls: identical to the two-kernel path."""
     m, n, k = 4096, 14336, 4096
-    monkeypatch.setenv("B200Q_FUSE", "1")
-    monkeypatch.setenv("B200Q_QUANT_TC", "0")     # bit-for-bit reference = the butterfly arithmetic the fused kernel runs
+    b200q_env("B200Q_FUSE", "1")
+    b200q_env("B200Q_QUANT_TC", "0")     # bit-for-bit reference = the butterfly arithmetic the fused kernel runs
     R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, 128, "abs_max", "mx", seed=3)
     for i in range(20):
         out, xq2, _ = Q.fused_linear_fp4(x, R, wq, wblk, al)
     torch.cuda.synchronize()
     assert torch.equal(xq2, xq) and torch.equal(out, want)
-    monkeypatch.delenv("B200Q_FUSE")
+    b200q_env("B200Q_FUSE", None)
     out, xq2, _ = Q.fused_linear_fp4(x, R, wq, wblk, al)          # default path: two launches behind the same call
     torch.cuda.synchronize()
     assert torch.equal(xq2, xq) and torch.equal(out, want)

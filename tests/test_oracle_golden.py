@@ -80,11 +80,18 @@ def test_nv_kernel_arithmetic_within_reference_tolerance(golden, h):
     we hold the oracle's kernel flavour to 1e-2."""
     x = O.bf16_from_bits(golden["mx_x_bits"])
     R = O.bf16_from_bits(golden[f"had{h}_bits"])
-    r = O.quantize_nv(x, R, 6.0, "abs_max", arithmetic="kernel")
     tag = f"nv_h{h}"
+    # the arithmetic of the reference's mma.sync kernels (for h = 128: what it runs on sm_120) is within 1e-2 of its test oracle
+    r = O.quantize_nv(x, R, 6.0, "abs_max", arithmetic="kernel", sm100_codes=False)
     dq = O.dequant_nv(r["q"].reshape(golden[tag + "_e2m1"].shape),
                       r["sf"].reshape(golden[tag + "_e4m3"].shape), alpha=6.0)
     assert (dq != golden[tag + "_dq"]).mean() <= 1e-2
+    # the default flavour = what the reference runs ON sm_100: for h = 128 its sm_100-only kernel (codes from the unrounded
+    # scale) sits 4.8 % away from that oracle -- inside the reference's own 1e-1 bar, and the reason the bar is that loose
+    r = O.quantize_nv(x, R, 6.0, "abs_max", arithmetic="kernel")
+    dq = O.dequant_nv(r["q"].reshape(golden[tag + "_e2m1"].shape),
+                      r["sf"].reshape(golden[tag + "_e4m3"].shape), alpha=6.0)
+    assert (dq != golden[tag + "_dq"]).mean() <= (1e-1 if h == 128 else 1e-2)
 
 
 @pytest.mark.parametrize("shape", [(128, 4), (256, 8), (384, 12), (128, 128)])
@@ -168,8 +175,9 @@ def test_sm100_nv_quirk_flavour_reproduces_the_observed_divergence():
     rows, k = 64, 4096
     x = H.random_bf16((rows, k), seed=1134)
     R = O.hadamard_matrix(128)
-    a = O.quantize_nv(x, R, 6.0, "abs_max")
-    b = O.quantize_nv(x, R, 6.0, "abs_max", sm100_codes=True)
+    a = O.quantize_nv(x, R, 6.0, "abs_max", sm100_codes=False)
+    b = O.quantize_nv(x, R, 6.0, "abs_max")                      # default = the reference's sm_100 dispatch for H = 128
+    assert np.array_equal(b["q"], O.quantize_nv(x, R, 6.0, "abs_max", sm100_codes=True)["q"])
     np.testing.assert_array_equal(a["sf"], b["sf"])
     cols = k // 16
     da = O.dequant_nv(a["q"].reshape(rows, -1), a["sf"].reshape(rows, cols))
