@@ -86,18 +86,49 @@ class ClockSampler:
 
 
 def _ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this same command (profiles/r01_ncu_gemm_summary.txt); None if absent."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_gemm_summary.txt")
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
+    `ncu --set full` capture of this same command (profiles/rNN_ncu_gemm_summary.txt); (None, None) if absent.  ncu cannot run
+    inside a timed bench, so this is a recorded figure and the line says which file it came from."""
+    cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_ncu_gemm_summary.txt")) \
+        if os.path.isdir(os.path.join(ROOT, "profiles")) else []
+    if not cands:
+        return None, None
+    p = os.path.join(ROOT, "profiles", cands[-1])
     try:
         import re
         line = open(p).readline()
         rd = re.search(r"dram__bytes_read.sum=([0-9.]+) (\w+)", line)
         wr = re.search(r"dram__bytes_write.sum=([0-9.]+) (\w+)", line)
         unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        return float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)]
+        return float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)], "profiles/" + cands[-1]
     except Exception:
-        return None
+        return None, None
+
+
+def _bind_to_gpu_numa_node(local: int):
+    """Best effort: run this rank (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA node the
+    GPU hangs off, so that N ranks do not all stage their PCIe traffic through node 0.  Returns the node or None."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        devn = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devn:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
 
 
 def _reference_gpu(kind, had, steps):
@@ -166,6 +197,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-CUTLASS-kernel comparison leg (child process)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the configs[4] (70B FFN, M=16384 sharded) leg")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="length of the sustained leg in seconds (0 = skip)")
     ap.add_argument("--fuse", action="store_true", help="step = the single fused quantise+GEMM kernel (B200Q_FUSE=1; measured slower)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -186,6 +219,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:
+        orig_affinity = os.sched_getaffinity(0)
+    except Exception:
+        orig_affinity = None
+    numa_node = _bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -245,9 +283,10 @@ def main():
 
     def gemm(i):
         s = i % NSETS
+        # the weights were quantised once at setup: the caller-side promise of b200q.h (B200Q_GEMM_STATIC_WEIGHTS)
         _lib.check(lib.b200q_gemm_fp4_cfg(aqs[s].data_ptr(), wqs[s].data_ptr(), asfs[s].data_ptr(), wsfs[s].data_ptr(),
-                                          alpha.data_ptr(), outs[s].data_ptr(), M, N, K, knd, args.cta_group,
-                                          args.block_n, stream))
+                                          alpha.data_ptr(), outs[s].data_ptr(), M, N, K, knd | Q.GEMM_STATIC_WEIGHTS,
+                                          args.cta_group, args.block_n, stream))
 
     def step_two_launches(i):
         quant(i)
@@ -258,6 +297,7 @@ def main():
     fused = args.fuse and args.cta_group == 0
     if fused:
         os.environ["B200Q_FUSE"] = "1"
+        lib.b200q_reload_env()
     launches_per_step = lib.b200q_linear_fp4_launches(M, N, K, args.had, method, knd) if fused else \
         1 + (lib.b200q_gemm_fp4_launches(M, N, K, knd) if args.cta_group == 0 else 1)
 
@@ -275,7 +315,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, per_rank=False):
+        """W untimed warm-up steps, then EXACTLY `steps` steps between two CUDA events on the launching stream, bracketed by
+        barrier + synchronize on both sides; returns the MAX over ranks (ms per step) [and every rank's own figure]."""
         for i in range(warmup):
             fn(i)
         barrier()
@@ -286,22 +328,47 @@ def main():
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        mine = ms / steps
+        ranks = [mine]
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps
+            allt = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            ranks = [float(x.item()) / steps for x in allt]
+            ms = max(float(x.item()) for x in allt)
+        return (ms / steps, ranks) if per_rank else ms / steps
+
+    def gather_obj(obj):
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
 
     flops = 2.0 * M * N * K
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ms_step = timed(step, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
+    # every rank samples ITS OWN GPU (the 2.6 % weak-scaling loss needs per-GPU clocks)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_step, ms_step_ranks = timed(step, args.steps, args.warmup, per_rank=True)
+    clocks = sampler.stop()
+    clocks_all = gather_obj(clocks)
     # dominant kernel alone (CUDA events on the launching stream), and the quantise kernel alone
-    ms_gemm = timed(gemm, args.steps, 3)
-    ms_quant = timed(quant, args.steps, 3)
+    ms_gemm, ms_gemm_ranks = timed(gemm, args.steps, 3, per_rank=True)
+    ms_quant, ms_quant_ranks = timed(quant, args.steps, 3, per_rank=True)
     ms_two = timed(step_two_launches, args.steps, 3) if fused else ms_step
+
+    # ---------------- sustained leg: the same step back to back for >= args.sustain_s seconds (power / thermal steady state)
+    sus = None
+    if args.sustain_s > 0:
+        n_sus = int(min(200000, max(args.steps, args.sustain_s * 1e3 / ms_step)))
+        sampler = ClockSampler(local)
+        sampler.start()
+        ms_sus, ms_sus_ranks = timed(step, n_sus, 0, per_rank=True)
+        clocks_sus = sampler.stop()
+        n_g = int(min(200000, max(args.steps, 0.5 * args.sustain_s * 1e3 / ms_gemm)))
+        ms_gemm_sus = timed(gemm, n_g, 0)
+        sus = dict(steps=n_sus, ms_per_step=ms_sus, ms_per_rank=ms_sus_ranks, clocks=clocks_sus, gemm_steps=n_g,
+                   ms_gemm=ms_gemm_sus, clocks_all=gather_obj(clocks_sus))
 
     value = flops * world / (ms_step * 1e-3) / 1e12
     line = {
@@ -311,7 +378,7 @@ def main():
         "config": {
             "workload": f"Llama-3-8B FFN M={M} (per GPU) N={N} K={K} {'MXFP4' if kind == 'mx' else 'NVFP4'} W4A4 abs_max, "
                         f"step = fused Hadamard-{args.had} rotate+quantise of activations + block-scaled FP4 GEMM "
-                        "(weights pre-quantised)" + (", one persistent kernel (b200q_linear_fp4)" if launches_per_step == 1 else ""),
+                        "(weights pre-quantised -> B200Q_GEMM_STATIC_WEIGHTS)" + (", one persistent kernel (b200q_linear_fp4)" if launches_per_step == 1 else ""),
             "global_batch_rows": M * world, "parallelism": f"dp{world} (M-sharded, weights broadcast once at setup)",
             "l2_policy": f"rotating {NSETS} buffer sets (activations/outputs/weights), {NSETS * 190} MB footprint > 126 MB L2",
         },
@@ -319,19 +386,31 @@ def main():
         "two_launch_step_us": ms_two * 1e3,
         "gemm_only_tflops_per_gpu": flops / (ms_gemm * 1e-3) / 1e12,
         "quantize_us": ms_quant * 1e3,
+        "per_rank": {"step_ms": ms_step_ranks, "gemm_ms": ms_gemm_ranks, "quantize_ms": ms_quant_ranks,
+                     "clocks": clocks_all},
     }
+    pk = _peaks()
+    if sus is not None:
+        line["value_sustained"] = flops * world / (sus["ms_per_step"] * 1e-3) / 1e12
+        line["sustained"] = {
+            "seconds": sus["steps"] * sus["ms_per_step"] * 1e-3, "steps": sus["steps"], "ms_per_step": sus["ms_per_step"],
+            "ms_per_rank": sus["ms_per_rank"], "clocks": sus["clocks"], "clocks_per_rank": sus["clocks_all"],
+            "gemm_only_tflops_per_gpu": flops / (sus["ms_gemm"] * 1e-3) / 1e12, "gemm_steps": sus["gemm_steps"],
+            "vs_burst": (ms_step / sus["ms_per_step"]),
+        }
     if rank == 0:
-        pk = _peaks()
         # MEASURED_PEAKS.json has no FP4 figure.  kind::mxf4 retires 4x the MACs of kind::f16 per tcgen05.mma issue slot, so the
-        # denominator is 4 x the measured cuBLAS bf16 rate -- the BURST figure, because this kernel is timed alone in a
-        # short loop (B200_PROFILING.md: burst for a kernel timed in isolation, sustained inside a long step).
+        # denominator is 4 x the measured cuBLAS bf16 rate -- the BURST figure for the kernel timed alone in a short loop, the
+        # SUSTAINED one for the >= 2 s leg (B200_PROFILING.md).  profiles/r02_fp4_peak.md holds the directly measured FP4
+        # tensor ceiling of this pool's parts under their power limit (MMA-only probe) next to it.
         fp4_peak = 4.0 * pk["bf16"]
         ach = flops / (ms_gemm * 1e-3) / 1e12
+        traffic, traffic_src = _ncu_traffic_bytes() if (kind == "mx") else (None, None)
         line["roofline"] = {
             "bound": "tensor", "achieved": ach, "peak": fp4_peak, "unit": "TFLOP/s", "frac": ach / fp4_peak,
-            "traffic": _ncu_traffic_bytes() if (kind == "mx" and world == 1) else None,
-            "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/); algorithmic bytes "
-                            f"= {M * K // 2 + N * K // 2 + (M + N) * K // group + 2 * M * N}",
+            "traffic": traffic, "traffic_source": traffic_src,
+            "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture named in traffic_source (ncu cannot "
+                            f"run inside a timed bench); algorithmic bytes = {M * K // 2 + N * K // 2 + (M + N) * K // group + 2 * M * N}",
             "peak_basis": f"4 x {pk['source']} burst cuBLAS bf16 ({pk['bf16']} TF/s) -- of measured; "
                           "no FP4 figure in MEASURED_PEAKS.json",
             "frac_of_nominal_9PF": ach / NOMINAL_FP4_TFLOPS,
@@ -343,7 +422,70 @@ def main():
                 "frac": (M * K * (2 + 0.5 + 1.0 / group)) / (ms_quant * 1e-3) / 1e9 / pk["hbm_gbs"],
             },
         }
+        if sus is not None:
+            ach_s = line["sustained"]["gemm_only_tflops_per_gpu"]
+            line["roofline"]["achieved_sustained"] = ach_s
+            line["roofline"]["peak_sustained"] = 4.0 * pk["bf16_sustained"]
+            line["roofline"]["frac_sustained"] = ach_s / (4.0 * pk["bf16_sustained"])
         line["clocks"] = clocks
+
+    # ---------------- configs[4]: Llama-3-70B FFN (N=28672, K=8192), global M=16384 SHARDED over the ranks (strong scaling)
+    if not args.no_c4:
+        from qutlass_b200.sharding import shard_rows
+        N4, K4, M4 = 28672, 8192, 16384
+        r0, rows4 = shard_rows(M4, world, rank)
+        w4q = torch.empty(N4, K4 // 2, dtype=torch.uint8, device=dev)
+        w4sf = torch.empty(((N4 + 127) // 128) * 128 * (((K4 // group) + 3) // 4) * 4, dtype=sf_dtype, device=dev)
+        if rank == 0:
+            w4 = torch.randn(N4, K4, dtype=torch.bfloat16, device=dev)
+            q_, s_ = Q.fusedQuantizeMx(w4, H, method="abs_max") if kind == "mx" else Q.fusedQuantizeNv(w4, H, gs, method="abs_max")
+            w4q.copy_(q_)
+            w4sf.copy_(Q.to_blocked(s_))
+            del w4, q_, s_
+        from qutlass_b200.sharding import broadcast_weights
+        broadcast_weights(w4q, w4sf, src=0)
+        S4 = 2   # two weight / activation / output sets: 2 x (125 MB weights + rows4 x 73 KB) > L2
+        w4qs, w4sfs = [w4q, w4q.clone()], [w4sf, w4sf.clone()]
+        x4 = [torch.randn(max(rows4, 1), K4, dtype=torch.bfloat16, device=dev) for _ in range(S4)]
+        pr4 = ((max(rows4, 1) + 127) // 128) * 128
+        pc4 = (((K4 // group) + 3) // 4) * 4
+        x4q = [torch.empty(max(rows4, 1), K4 // 2, dtype=torch.uint8, device=dev) for _ in range(S4)]
+        x4sf = [torch.empty(pr4 * pc4, dtype=sf_dtype, device=dev) for _ in range(S4)]
+        d4 = [torch.empty(max(rows4, 1), N4, dtype=torch.bfloat16, device=dev) for _ in range(S4)]
+
+        def quant4(i):
+            s_ = i % S4
+            if kind == "mx":
+                rc = lib.b200q_quantize_mx(x4[s_].data_ptr(), H.data_ptr(), x4q[s_].data_ptr(), None, x4sf[s_].data_ptr(), None,
+                                           rows4 * K4, K4, args.had, method, stream)
+            else:
+                rc = lib.b200q_quantize_nv(x4[s_].data_ptr(), H.data_ptr(), x4q[s_].data_ptr(), None, x4sf[s_].data_ptr(),
+                                           gs.data_ptr(), rows4 * K4, K4, args.had, method, stream)
+            _lib.check(rc)
+
+        def gemm4(i):
+            s_ = i % S4
+            _lib.check(lib.b200q_gemm_fp4(x4q[s_].data_ptr(), w4qs[s_].data_ptr(), x4sf[s_].data_ptr(), w4sfs[s_].data_ptr(),
+                                          alpha.data_ptr(), d4[s_].data_ptr(), rows4, N4, K4, knd | Q.GEMM_STATIC_WEIGHTS, stream))
+
+        def step4(i):
+            if rows4 > 0:
+                quant4(i)
+                gemm4(i)
+
+        st4 = max(10, min(args.steps, 100))
+        ms4, ms4_ranks = timed(step4, st4, 3, per_rank=True)
+        ms4_gemm = timed(lambda i: gemm4(i) if rows4 > 0 else None, st4, 3)
+        flops4 = 2.0 * M4 * N4 * K4
+        line["c4"] = {
+            "workload": f"Llama-3-70B FFN N={N4} K={K4} {'MXFP4' if kind == 'mx' else 'NVFP4'}, global M={M4} sharded by "
+                        f"qutlass_b200.sharding.shard_rows over {world} rank(s) ({rows4} rows on rank 0), quantise + GEMM",
+            "scaling": "strong", "value": flops4 / (ms4 * 1e-3) / 1e12, "unit": "TFLOP/s (aggregate, max-over-ranks time)",
+            "ms_per_step": ms4, "ms_per_rank": ms4_ranks, "steps": st4, "rows_per_rank": [shard_rows(M4, world, r)[1] for r in range(world)],
+            "gemm_only_ms": ms4_gemm, "gemm_only_tflops_aggregate": flops4 / (ms4_gemm * 1e-3) / 1e12,
+        }
+        del w4qs, w4sfs, x4, x4q, x4sf, d4, w4q, w4sf
+        torch.cuda.empty_cache()
 
     # ---------------- e2e: host buffers through the C-ABI (H2D + quantise + GEMM + D2H inside the timed region)
     if not args.no_e2e:
@@ -351,6 +493,7 @@ def main():
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         x_host = torch.randn(M, K, dtype=torch.bfloat16).pin_memory()
         d_host = torch.empty(M, N, dtype=torch.bfloat16).pin_memory()
+        d_host.zero_()                       # first touch on this rank's (NUMA-bound) CPUs
 
         def e2e_step(i):
             _lib.check(lib.b200q_linear_fp4_host(x_host.data_ptr(), H.data_ptr(), wqs[i % NSETS].data_ptr(),
@@ -358,10 +501,34 @@ def main():
                                                  d_host.data_ptr(), ws.data_ptr(), M, N, K, args.had, knd, stream))
 
         e2e_steps = max(3, min(args.steps, 20))
-        ms_e2e = timed(e2e_step, e2e_steps, 3)
+        ms_e2e, ms_e2e_ranks = timed(e2e_step, e2e_steps, 3, per_rank=True)
+        # the host ceiling: the SAME bytes (H2D of x, D2H of D) with no kernels at all, both directions concurrently, all
+        # ranks at once -- what the PCIe / host-memory path of this box sustains for this traffic pattern
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        x_dev = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
+        cur = torch.cuda.current_stream()
+
+        def copy_only(i):
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            s_up.wait_event(ev)
+            s_dn.wait_event(ev)
+            with torch.cuda.stream(s_up):
+                x_dev.copy_(x_host, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                d_host.copy_(outs[i % NSETS], non_blocking=True)
+            cur.wait_stream(s_up)
+            cur.wait_stream(s_dn)
+
+        ms_copy = timed(copy_only, e2e_steps, 2)
         line["e2e"] = {"value": flops * world / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s",
                        "h2d_bytes_per_step": M * K * 2, "d2h_bytes_per_step": M * N * 2, "ms_per_step": ms_e2e,
-                       "api": "b200q_linear_fp4_host (C-ABI, pinned host buffers)"}
+                       "ms_per_rank": ms_e2e_ranks, "numa_node": numa_node,
+                       "host_copy_ceiling_ms": ms_copy,
+                       "host_copy_ceiling_note": "same H2D + D2H bytes per rank, no kernels, both directions concurrent, all ranks "
+                                                 "at once: the PCIe / host-memory bound of this box for the e2e traffic",
+                       "frac_of_host_ceiling": ms_copy / ms_e2e,
+                       "api": "b200q_linear_fp4_host (C-ABI, pinned host buffers, abs_max)"}
 
     # ---------------- cpu_baseline (rank 0, N=1 only): bounded sample on the host cores
     # (the baseline leg is the one place of this arm that executes oracle/: the CPU port, and -- reported beside it, after
@@ -369,12 +536,20 @@ def main():
     # sources compiled for sm_100a by oracle/build_ref.py, run in a child process because it registers the same torch op
     # namespace as our drop-in.  A reported comparison on the same box and shape; it can never fail the bench line.)
     if rank == 0 and world == 1 and not args.no_cpu:
+        if orig_affinity is not None:
+            try:
+                os.sched_setaffinity(0, orig_affinity)      # the CPU baseline gets every core, not just the GPU's NUMA node
+            except Exception:
+                pass
         from oracle import cpu_baseline as C
         r = C.time_cpu_path(M, N, K, kind, steps=1, warmup=1)
         line["cpu_baseline"] = {"value": r["tflops"], "unit": "TFLOP/s", "cores": r["threads"], "kind": "port",
                                 "sample": f"1 step of the full config (M={M}): LUT dequantise A,B + fp32 torch.matmul + bf16"}
-        if not args.no_ref_gpu:
-            line["reference_gpu"] = _reference_gpu(kind, args.had, min(args.steps, 200))
+    if rank == 0 and not args.no_ref_gpu and not args.no_cpu:
+        # every N: rank 0's GPU runs the compiled reference kernels while the other ranks wait at the barrier below
+        line["reference_gpu"] = _reference_gpu(kind, args.had, min(args.steps, 200))
+    if world > 1:
+        dist.barrier()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -10,7 +10,9 @@ No reference source is copied: nvcc / g++ read the files where they lie; only ob
 oracle/_ref/.  The reference's own build system (setup.py + cmake; needs a GPU at import, setup.py:45-51,112-118) is
 not run; flags follow setup.py:60-92,158-176 (sm_100a only, TARGET_CUDA_ARCH=100).
 
-usage: python oracle/build_ref.py [--jobs N] [--force]     (tens of minutes: CUTLASS template instantiation)
+It also stages the reference's own tests/ and sm_100 benchmarks/ unmodified under oracle/_ref/ref_suite/ (stage_suite()).
+
+usage: python oracle/build_ref.py [--jobs N] [--force] [--suite-only]     (minutes: CUTLASS template instantiation)
 """
 from __future__ import annotations
 
@@ -82,6 +84,45 @@ def build(jobs: int = 4, force: bool = False) -> str:
     return LIB
 
 
+SUITE = os.path.join(OUT, "ref_suite")
+SUITE_FILES = ["tests/__init__.py", "tests/mxfp4_test.py", "tests/nvfp4_test.py", "tests/mxfp8_test.py",
+               "tests/quartet_test.py", "benchmarks/__init__.py", "benchmarks/bench_mxfp4_sm100.py",
+               "benchmarks/bench_nvfp4_sm100.py"]
+
+
+def stage_suite() -> str:
+    """Stage the reference's OWN tests/ and sm_100 benchmarks/, byte for byte, under oracle/_ref/ref_suite/ (git-ignored like the
+    compiled library, travels to the GPU box like it) together with a sha256 manifest, so that tests/test_gpu_reference_suite.py
+    can run them UNMODIFIED against the `qutlass` drop-in package and prove they were not edited.  /root/reference itself
+    does not exist on the GPU box.  Nothing is copied into the tracked tree."""
+    import hashlib
+    import json
+    import shutil
+    if not os.path.isdir(os.path.join(REF, "tests")):
+        raise RuntimeError(f"{REF}/tests not found: the reference checkout is only present in the build container")
+    manifest = {}
+    for rel in SUITE_FILES:
+        src, dst = os.path.join(REF, rel), os.path.join(SUITE, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(src, dst)
+        manifest[rel] = hashlib.sha256(open(src, "rb").read()).hexdigest()
+    with open(os.path.join(SUITE, "MANIFEST.json"), "w") as f:
+        json.dump({"source": REF, "sha256": manifest}, f, indent=1, sort_keys=True)
+    # The reference's own Python package around the compiled library (qutlass/__init__.py does `import qutlass._CUDA`;
+    # bindings.cpp:538 REGISTER_EXTENSION(_CUDA) -> PyInit__CUDA is exported by qutlass_ref_C.so): with
+    # PYTHONPATH=oracle/_ref/ref_pkg the SAME unmodified tests / benchmarks run against the REAL reference on the GPU box,
+    # which is how tools/run_ref_benchmarks.sh produces the reference's curve next to ours.
+    pkg = os.path.join(OUT, "ref_pkg", "qutlass")
+    os.makedirs(pkg, exist_ok=True)
+    for name in ("__init__.py", "utils.py"):
+        shutil.copyfile(os.path.join(REF, "qutlass", name), os.path.join(pkg, name))
+    if os.path.exists(LIB):
+        shutil.copyfile(LIB, os.path.join(pkg, "_CUDA.so"))
+    return SUITE
+
+
 if __name__ == "__main__":
     jobs = int(sys.argv[sys.argv.index("--jobs") + 1]) if "--jobs" in sys.argv else 4
-    print(build(jobs=jobs, force="--force" in sys.argv))
+    if "--suite-only" not in sys.argv:
+        print(build(jobs=jobs, force="--force" in sys.argv))
+    print(stage_suite())

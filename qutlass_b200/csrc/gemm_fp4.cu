@@ -379,20 +379,32 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
         }
       };
-      // Only with static_weights: by default B / SFB may come from the kernel right in front of us (QAT re-quantises the
-      // weights every step; the reference's own pattern is quantise(a); quantise(b); matmul), so every global read waits.
-      if (!p.static_weights) pdl_wait();
+      // Only with static_weights are the real loads issued early: by default B / SFB may come from the kernel right in front
+      // of us (QAT re-quantises the weights every step; the reference's own pattern is quantise(a); quantise(b); matmul), so
+      // every global READ waits.  What is always safe is an L2 PREFETCH of the same boxes (L2 is the coherence point: a line
+      // the predecessor writes later is updated in place), so the default path still pulls its first ring of weights towards
+      // the chip while the predecessor drains and then loads them from L2.
       {
         Cursor c = cur;
         for (int g = 0; g < pre; ++g) {          // ring is empty: no wait needed for the first STAGES slots
-          if (elected) load_weights(g, c.n0, c.nb0, c.kt);
+          if (elected) {
+            if (p.static_weights) {
+              load_weights(g, c.n0, c.nb0, c.kt);
+            } else {
+              if (!(p.flags & (1 << 20))) tma_prefetch_2d(&tmap_b, c.kt * BK_BYTES, c.nb0);
+              tma_prefetch_3d(&tmap_sfb, 0, c.kt * SFKB, c.n0 / 128);
+            }
+          }
           advance(c);
         }
       }
       pdl_wait();
       for (int g = 0; g < pre; ++g) {
         wait_acts(cur.tm);
-        if (elected) load_acts(g, cur.m0, cur.kt);
+        if (elected) {
+          if (!p.static_weights) load_weights(g, cur.n0, cur.nb0, cur.kt);
+          load_acts(g, cur.m0, cur.kt);
+        }
         advance(cur);
       }
       __syncwarp();

@@ -201,6 +201,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
         ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier).  Always safe with respect to later writers of
+// that memory: L2 is the coherence point, a line written afterwards is simply updated in place.
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // 1-D bulk copy global -> shared (size multiple of 16, both 16-byte aligned)
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),

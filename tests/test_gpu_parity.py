@@ -745,3 +745,163 @@ def test_quantize_full_size_idempotent_layout():
     assert torch.equal(blk.view(torch.uint8), sw.view(torch.uint8))
     codes = O.unpack_e2m1(H.u8_of(q[:64]))
     np.testing.assert_array_equal(O.e2m1_encode(O.e2m1_decode(codes)) & 7, codes & 7)
+
+
+# ----------------------------------------------------------------------------- round 2: call orders / shapes not covered before
+@pytest.mark.parametrize("fmt", ["mx", "nv"])
+@pytest.mark.parametrize("shape", [(16, 384, 512), (160, 1024, 1024), (4096, 14336, 4096)])
+def test_quantise_quantise_matmul_back_to_back_without_host_sync(fmt, shape):
+    """the reference's own pattern `quantise(a); quantise(b); matmul(...)` with NOTHING between the
+    kernels -- alpha and every other device tensor exist beforehand, so all launches are chained by programmatic dependent
+    launch.  The GEMM must not read b_q / b_sf (written by the kernel right in front of it) before that kernel is done:
+    the result must equal the fully synchronised sequence, on every iteration, with garbage-prefilled buffers."""
+    m, n, k = shape
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(128 if k % 128 == 0 else 32))
+    gs = torch.tensor([1.0], device="cuda")
+    alpha = torch.tensor([1.0 / 7.0], device="cuda")
+    g = torch.Generator("cuda").manual_seed(m + n)
+    fq = (lambda t: Q.fusedQuantizeMx(t, R, method="abs_max")) if fmt == "mx" else (lambda t: Q.fusedQuantizeNv(t, R, gs, method="abs_max"))
+    mm = Q.matmul_mxf4_bf16_tn if fmt == "mx" else Q.matmul_nvf4_bf16_tn
+    for it in range(6):
+        a = torch.randn(m, k, dtype=torch.bfloat16, device="cuda", generator=g) * 25
+        b = torch.randn(n, k, dtype=torch.bfloat16, device="cuda", generator=g) * 25
+        # reference result: every step synchronised
+        aq, asf = fq(a); torch.cuda.synchronize()
+        bq, bsf = fq(b); torch.cuda.synchronize()
+        want = mm(aq, bq, Q.to_blocked(asf), Q.to_blocked(bsf), alpha); torch.cuda.synchronize()
+        # poison the caching allocator's free blocks so a premature read sees garbage, not last iteration's identical bytes
+        del aq, asf, bq, bsf
+        junk = [torch.full((n, k // 2), 0x77, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        del junk
+        torch.cuda.synchronize()
+        aq, asf = fq(a)
+        bq, bsf = fq(b)
+        got = mm(aq, bq, Q.to_blocked(asf), Q.to_blocked(bsf), alpha)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), (fmt, shape, it, (got != want).float().mean().item())
+
+
+def test_static_weights_flag_is_bit_identical_when_the_promise_holds():
+    m, n, k = 300, 1000, 2048
+    aq, asf = H.random_fp4_operand(m, k, "mx", seed=7, sf_mode="wide")
+    bq, bsf = H.random_fp4_operand(n, k, "mx", seed=8, sf_mode="wide")
+    a, b = torch.from_numpy(aq).cuda(), torch.from_numpy(bq).cuda()
+    a_sf, b_sf = H.sf_torch(H.blocked_sf(asf), "mx"), H.sf_torch(H.blocked_sf(bsf), "mx")
+    al = torch.tensor([0.5], device="cuda")
+    torch.cuda.synchronize()
+    d0 = Q.matmul_mxf4_bf16_tn(a, b, a_sf, b_sf, al)
+    d1 = Q.matmul_mxf4_bf16_tn(a, b, a_sf, b_sf, al, static_weights=True)
+    torch.cuda.synchronize()
+    assert torch.equal(d0, d1)
+
+
+@pytest.mark.parametrize("kind", ["mx", "nv"])
+def test_config4_llama70b_ffn_shape(kind):
+    """BASELINE.json configs[4]: N=28672, K=8192 (CTA-pair plan, 32 k-tiles), M=16384 -- a random sample of rows against
+    the oracle, and every 2/4/8-way row shard (qutlass_b200.sharding.shard_rows) computed on its own equals the same rows
+    of the full product bit for bit (what the multi-GPU run relies on)."""
+    from qutlass_b200.sharding import shard_rows
+    m, n, k = 16384, 28672, 8192
+    aq, asf = H.random_fp4_operand(m, k, kind, seed=171, sf_mode="narrow")
+    bq, bsf = H.random_fp4_operand(n, k, kind, seed=172, sf_mode="narrow")
+    a, b = torch.from_numpy(aq).cuda(), torch.from_numpy(bq).cuda()
+    b_sf = H.sf_torch(H.blocked_sf(bsf), kind)
+    al = torch.tensor([1.0], device="cuda")
+    knd, dt = (Q.KIND_MXF4, torch.float8_e8m0fnu) if kind == "mx" else (Q.KIND_NVF4, torch.float8_e4m3fn)
+    full = Q._matmul_fp4("t", a, b, H.sf_torch(H.blocked_sf(asf), kind), b_sf, al, knd, dt, 16)
+    rows = np.sort(np.random.default_rng(4).choice(m, size=24, replace=False))
+    want = H.gemm_oracle_bits(aq[rows], asf[rows], bq, bsf, kind, 1.0)
+    got = H.bf16_bits_of(full[torch.from_numpy(rows).cuda()])
+    mism, rel = H.compare_bits(got, want)
+    if kind == "mx":
+        assert mism == 0.0, (mism, rel)
+    else:
+        assert rel <= REL_TOL and mism <= 1e-3, (mism, rel)
+    for world in (2, 8):
+        for rank in (0, world - 1):
+            s0, r = shard_rows(m, world, rank)
+            part = Q._matmul_fp4("t", a[s0:s0 + r], b, H.sf_torch(H.blocked_sf(asf[s0:s0 + r]), kind), b_sf, al, knd, dt, 16)
+            assert torch.equal(part, full[s0:s0 + r]), (world, rank)
+
+
+def test_gemm_output_larger_than_2_31_elements():
+    """The reference's own benchmark sweeps M up to 65536 at N = 57344 (benchmarks/bench_mxfp4_sm100.py:176-193,264): 3.76e9
+    outputs, beyond 32-bit element indices.  K is kept small so the check stays cheap: the last rows against the oracle, and
+    a row block computed on its own equals the same rows of the big product."""
+    m, n, k = 40960, 57344, 256
+    assert m * n > 2 ** 31
+    aq, asf = H.random_fp4_operand(m, k, "mx", seed=271, sf_mode="narrow")
+    bq, bsf = H.random_fp4_operand(n, k, "mx", seed=272, sf_mode="narrow")
+    a, b = torch.from_numpy(aq).cuda(), torch.from_numpy(bq).cuda()
+    b_sf = H.sf_torch(H.blocked_sf(bsf), "mx")
+    al = torch.tensor([1.0], device="cuda")
+    full = Q._matmul_fp4("t", a, b, H.sf_torch(H.blocked_sf(asf), "mx"), b_sf, al, Q.KIND_MXF4, torch.float8_e8m0fnu, 16)
+    rows = np.array([0, 1, 20479, 37448, 40958, 40959])
+    want = H.gemm_oracle_bits(aq[rows], asf[rows], bq, bsf, "mx", 1.0)
+    np.testing.assert_array_equal(H.bf16_bits_of(full[torch.from_numpy(rows).cuda()]), want)
+    s0 = 40960 - 512
+    part = Q._matmul_fp4("t", a[s0:], b, H.sf_torch(H.blocked_sf(asf[s0:]), "mx"), b_sf, al, Q.KIND_MXF4, torch.float8_e8m0fnu, 16)
+    assert torch.equal(part, full[s0:])
+
+
+def test_tensor_map_cache_hits_on_repeated_calls_and_never_serves_a_stale_map():
+    """Host overhead: the second call with the same buffers re-uses all five tensor maps; a different
+    buffer at a recycled address with a different shape gets its own encoding (the key is the full descriptor content)."""
+    import ctypes
+    lib = _lib.load()
+    h, mi = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    aq, asf = H.random_fp4_operand(256, 512, "mx", seed=1)
+    bq, bsf = H.random_fp4_operand(256, 512, "mx", seed=2)
+    want = H.gemm_oracle_bits(aq, asf, bq, bsf, "mx", 1.0)
+    a, b = torch.from_numpy(aq).cuda(), torch.from_numpy(bq).cuda()
+    a_sf, b_sf = H.sf_torch(H.blocked_sf(asf), "mx"), H.sf_torch(H.blocked_sf(bsf), "mx")
+    al = torch.tensor([1.0], device="cuda")
+    out = torch.empty(256, 256, dtype=torch.bfloat16, device="cuda")
+    call = lambda: _lib.check(lib.b200q_gemm_fp4(a.data_ptr(), b.data_ptr(), a_sf.data_ptr(), b_sf.data_ptr(), al.data_ptr(),
+                                                 out.data_ptr(), 256, 256, 512, 0, torch.cuda.current_stream().cuda_stream))
+    call()
+    lib.b200q_debug_tmap_cache_stats(ctypes.byref(h), ctypes.byref(mi))
+    call()
+    lib.b200q_debug_tmap_cache_stats(ctypes.byref(h), ctypes.byref(mi))
+    assert h.value == 5 and mi.value == 0, (h.value, mi.value)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(H.bf16_bits_of(out), want)
+    # same addresses, different logical shape (K halves): must not reuse the old maps
+    want2 = H.gemm_oracle_bits(aq[:, :128], asf[:, :8], bq[:, :128], bsf[:, :8], "mx", 1.0)
+    a2, b2 = a[:, :128].contiguous(), b[:, :128].contiguous()
+    a.copy_(torch.zeros_like(a)); b.copy_(torch.zeros_like(b))
+    a.view(-1)[: a2.numel()].copy_(a2.view(-1)); b.view(-1)[: b2.numel()].copy_(b2.view(-1))
+    a_sf2, b_sf2 = H.sf_torch(H.blocked_sf(asf[:, :8]), "mx"), H.sf_torch(H.blocked_sf(bsf[:, :8]), "mx")
+    _lib.check(lib.b200q_gemm_fp4(a.data_ptr(), b.data_ptr(), a_sf2.data_ptr(), b_sf2.data_ptr(), al.data_ptr(),
+                                  out.data_ptr(), 256, 256, 256, 0, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(H.bf16_bits_of(out), want2)
+
+
+def test_to_blocked_hand_over_and_invalidation():
+    """the blocked copy written by the quantiser is handed over ONCE, only while the row-major tensor is
+    unmodified; an in-place edit, a second call, a raw-op overwrite or an inference-mode tensor all take the swizzle kernel
+    and see the CURRENT bytes."""
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(32))
+    x = torch.randn(200, 256, dtype=torch.bfloat16, device="cuda") * 25
+    q, sf = Q.fusedQuantizeMx(x, R, method="abs_max")
+    first = Q.to_blocked(sf)
+    second = Q.to_blocked(sf)
+    assert first.data_ptr() != second.data_ptr() and torch.equal(first.view(torch.uint8), second.view(torch.uint8))
+    q, sf = Q.fusedQuantizeMx(x, R, method="abs_max")
+    sf.view(torch.uint8)[200:256] = 127                      # the reference tests' `scales[m:m_up] = 1.0` pattern
+    blk = Q.to_blocked(sf)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(H.u8_of(blk), H.blocked_sf(H.u8_of(sf)))
+    # raw op writes OUT_sf through its data pointer: an attached copy from an earlier quantisation must not survive
+    q, sf = Q.fusedQuantizeMx(x, R, method="abs_max")
+    torch.ops._qutlass_C.fusedQuantizeMxAbsMax(x * 4, R, q, sf)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(H.u8_of(Q.to_blocked(sf)), H.blocked_sf(H.u8_of(sf)))
+    with torch.inference_mode():
+        xi = torch.randn(200, 256, dtype=torch.bfloat16, device="cuda") * 25
+        q, sf = Q.fusedQuantizeMx(xi, R.clone(), method="abs_max")
+        sf.view(torch.uint8)[200:256] = 127
+        blk = Q.to_blocked(sf)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(H.u8_of(blk), H.blocked_sf(H.u8_of(sf)))
