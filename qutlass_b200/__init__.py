@@ -178,8 +178,8 @@ def matmul_mxf8_bf16_nn(a: torch.Tensor, b: torch.Tensor, block_scale_a: torch.T
 
 # --------------------------------------------------------------------------------------- quantise
 _ROT_CACHE = {}   # id(tensor) -> (weakref, _version, data_ptr, is_hadamard)
-_ROT_INSPECTIONS = [0]   # host inspections so far (each is one blocking D2H copy)
-_ROT_MAX_INSPECTIONS = 64
+_ROT_DEAD = [0]          # inspected rotation tensors that have since been garbage-collected (= built per call by the caller)
+_ROT_MAX_DEAD = 64       # after that many throw-away rotations stop synchronising for new ones: the device-side check runs
 
 
 def _rotation_hint(r: torch.Tensor) -> int:
@@ -191,7 +191,8 @@ def _rotation_hint(r: torch.Tensor) -> int:
     remembered for as long as that tensor object lives unmodified.  No hint (0: the device-side check runs, always
     correct) whenever the host cannot vouch for the matrix: during CUDA-graph capture, for inference-mode tensors
     (no version counter: an in-place edit would go unnoticed), and once a caller has shown that it builds a new
-    rotation tensor for every call (more than _ROT_MAX_INSPECTIONS inspections -- each is a device synchronisation)."""
+    rotation tensor for every call (_ROT_MAX_DEAD inspected tensors already garbage-collected -- every inspection is a
+    device synchronisation; long-lived per-layer rotations never count)."""
     import weakref
     key = id(r)
     ent = _ROT_CACHE.get(key)
@@ -202,9 +203,12 @@ def _rotation_hint(r: torch.Tensor) -> int:
         return ROT_TRUSTED_HADAMARD if ent[3] else ROT_GENERIC
     if r.is_cuda and torch.cuda.is_current_stream_capturing():
         return 0
-    if _ROT_INSPECTIONS[0] >= _ROT_MAX_INSPECTIONS:
+    dead = [k for k, v in _ROT_CACHE.items() if v[0]() is None]
+    for k in dead:
+        _ROT_CACHE.pop(k, None)
+    _ROT_DEAD[0] += len(dead)
+    if _ROT_DEAD[0] >= _ROT_MAX_DEAD:
         return 0
-    _ROT_INSPECTIONS[0] += 1
     h = r.size(0)
     m = r.detach().to("cpu").view(torch.int16)                 # bit patterns (synchronises once)
     idx = torch.arange(h)
@@ -217,9 +221,6 @@ def _rotation_hint(r: torch.Tensor) -> int:
     want = torch.where(par.bool(), torch.tensor(c ^ -0x8000, dtype=torch.int32), torch.tensor(c, dtype=torch.int32))
     want = ((want + 0x8000) % 0x10000 - 0x8000).to(torch.int16)
     is_h = bool(torch.equal(m, want))
-    if len(_ROT_CACHE) > 64:
-        for k in [k for k, v in _ROT_CACHE.items() if v[0]() is None]:
-            _ROT_CACHE.pop(k, None)
     _ROT_CACHE[key] = (weakref.ref(r), ver, r.data_ptr(), is_h)
     return ROT_TRUSTED_HADAMARD if is_h else ROT_GENERIC
 

@@ -102,6 +102,17 @@ __device__ __forceinline__ void trace_event(int flags, int tile_idx, int ev) {
   if ((flags & (1 << 24)) && blockIdx.x == 0 && tile_idx < kTraceTiles && (threadIdx.x & 31) == 0)
     g_gemm_trace[tile_idx * kTraceEvents + ev] = clock64();
 }
+// Kernel-level events of CTA 0 (same flag): [0] clock64 at entry, [1] globaltimer (ns) at entry, [2] set-up done,
+// [3] producer past griddepcontrol.wait, [5] clock64 at exit, [6] globaltimer at exit.  b200q_debug_read_ktrace.
+__device__ unsigned long long g_gemm_ktrace[8];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void ktrace(int flags, int ev, bool wall = false) {
+  if ((flags & (1 << 24)) && blockIdx.x == 0) g_gemm_ktrace[ev] = wall ? globaltimer_ns() : (unsigned long long)clock64();
+}
 
 struct GemmParams {
   const float* alpha;
@@ -282,6 +293,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   // a dependent grid (e.g. the tail GEMM of a split launch) may start its prologue / weight loads while this one runs
   pdl_launch_dependents();
+  if (threadIdx.x == 0) { ktrace(p.flags, 0); ktrace(p.flags, 1, true); }
 
   // ------------------------------------------------------------------ setup
   if (warp == 0 && lane == 0) {
@@ -311,6 +323,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_gen, 0);
   const uint32_t tmem_sfa = tmem_base + ACC * BN;
   const uint32_t tmem_sfb = tmem_sfa + Cfg::SFA_COLS;
+  if (threadIdx.x == 0) ktrace(p.flags, 2);
 
   // ------------------------------------------------------------------ roles
   if (warp == 0) {
@@ -343,22 +356,25 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       auto advance = [&](Cursor& c) {
         if (++c.kt == p.k_tiles) { c.kt = 0; c.tile += num_clusters; set_tile(c); }
       };
+      // profiling flags (timing only, wrong results): 1 << 20 skips the B tile loads, 1 << 21 the A tile loads; 1 << 22: both are
+      // skipped AFTER the first ring (the stages then keep the random tiles they were filled with: the tensor pipe works on
+      // realistic data with no operand traffic at all -- the power-limited FP4 ceiling of tools/fp4_peak_probe.py)
+      int lflags = p.flags;
       auto load_weights = [&](int stage, int n0, int nb0, int kt) {
         const uint32_t sb = smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
         const uint32_t ssfb = sb + Cfg::B_BYTES + Cfg::SFA_BYTES;
         const uint32_t fb = full0 + 8u * stage;
-        // profiling flags (timing only, wrong results): 1 << 20 skips the B tile loads, 1 << 21 the A tile loads
-        const uint32_t tx = Cfg::TX_BYTES - ((p.flags & (1 << 20)) ? (uint32_t)Cfg::B_BYTES * kCtaGroup : 0u) -
-                            ((p.flags & (1 << 21)) ? (uint32_t)Cfg::A_BYTES * kCtaGroup : 0u);
+        const uint32_t tx = Cfg::TX_BYTES - ((lflags & (1 << 20)) ? (uint32_t)Cfg::B_BYTES * kCtaGroup : 0u) -
+                            ((lflags & (1 << 21)) ? (uint32_t)Cfg::A_BYTES * kCtaGroup : 0u);
         if (is_leader) mbar_arrive_expect_tx(bar_base + 8u * stage, tx);
-        if (!(p.flags & (1 << 20))) tma_load_2d<kCtaGroup>(sb, &tmap_b, fb, kt * BK_BYTES, nb0);
+        if (!(lflags & (1 << 20))) tma_load_2d<kCtaGroup>(sb, &tmap_b, fb, kt * BK_BYTES, nb0);
         tma_load_3d<kCtaGroup>(ssfb, &tmap_sfb, fb, 0, kt * SFKB, n0 / 128);
       };
       auto load_acts = [&](int stage, int m0, int kt) {
         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
         const uint32_t ssfa = sa + Cfg::A_BYTES + Cfg::B_BYTES;
         const uint32_t fb = full0 + 8u * stage;
-        if (p.flags & (1 << 21)) {}
+        if (lflags & (1 << 21)) {}
         else if constexpr (kMC != 0)      // my 64 rows of the A tile, to me and to my counterpart in the other pair
           tma_load_2d_multicast<2>(sa + pair * (64 * BK_BYTES), &tmap_a, fb, kt * BK_BYTES, m0 + (int)pair * 64, mc_mask);
         else if constexpr (kF8 == 2) tma_load_2d<kCtaGroup>(sa, &tmap_a, fb, m0, kt * Cfg::BK_ELEMS);   // A [K, M]: box = 128 K-rows x 128 M-bytes
@@ -391,7 +407,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (p.static_weights) {
               load_weights(g, c.n0, c.nb0, c.kt);
             } else {
-              if (!(p.flags & (1 << 20))) tma_prefetch_2d(&tmap_b, c.kt * BK_BYTES, c.nb0);
+              if (!(lflags & (1 << 20))) tma_prefetch_2d(&tmap_b, c.kt * BK_BYTES, c.nb0);
               tma_prefetch_3d(&tmap_sfb, 0, c.kt * SFKB, c.n0 / 128);
             }
           }
@@ -399,6 +415,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
       }
       pdl_wait();
+      if (lane == 0) ktrace(p.flags, 3);
       for (int g = 0; g < pre; ++g) {
         wait_acts(cur.tm);
         if (elected) {
@@ -408,6 +425,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         advance(cur);
       }
       __syncwarp();
+      if (p.flags & (1 << 22)) lflags |= (3 << 20);
       int stage = (pre == STAGES) ? 0 : pre;
       uint32_t phase = (pre == STAGES) ? 1 : 0;
       for (int g = pre; g < total_kt; ++g) {
@@ -459,6 +477,10 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2);
         tc_fence_after();
         trace_event(p.flags, tidx, 0);
+        if (p.flags & (1 << 24)) {                       // profiling builds: when did this tile's first k-tile land?
+          mbar_wait(bar_base + 8u * stage, phase, 9);    // (non-consuming: the issue loop waits on the same phase again)
+          trace_event(p.flags, tidx, 1);
+        }
         const uint32_t tmem_acc = tmem_base + acc * BN;
         const uint32_t tsfb = tmem_sfb + sfb_shift;
         // One k-tile: wait for the stage, copy its scales into TMEM (each 512-B block -> 4 columns, replicated over the 4
@@ -712,6 +734,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   // ------------------------------------------------------------------ teardown
   tc_fence_before();
   if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
+  if (threadIdx.x == 0) { ktrace(p.flags, 5); ktrace(p.flags, 6, true); }
   if (warp == 1) {
     __syncwarp();   // .sync.aligned: the issuing lane must have reconverged with its warp
     tmem_dealloc<kCtaGroup>(tmem_base, Cfg::TMEM_COLS);
@@ -1448,6 +1471,13 @@ extern "C" int b200q_debug_read_trace(unsigned long long* out, int n) {
   if (n > kTraceTiles * kTraceEvents) n = kTraceTiles * kTraceEvents;
   B200Q_CUDA(cudaDeviceSynchronize());
   B200Q_CUDA(cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(unsigned long long) * n));
+  return 0;
+}
+
+extern "C" int b200q_debug_read_ktrace(unsigned long long* out, int n) {
+  if (n > 8) n = 8;
+  B200Q_CUDA(cudaDeviceSynchronize());
+  B200Q_CUDA(cudaMemcpyFromSymbol(out, g_gemm_ktrace, sizeof(unsigned long long) * n));
   return 0;
 }
 
