@@ -41,6 +41,26 @@ KIND_MXF4, KIND_NVF4, KIND_MXF8, KIND_MXF8_NN = 0, 1, 2, 3
 GEMM_STATIC_WEIGHTS = 0x100    # include/b200q.h: B200Q_GEMM_STATIC_WEIGHTS (OR into kind)
 
 
+def _load_compiled_ops() -> bool:
+    """torch.ops._qutlass_C / _b200q_C from the COMPILED op layer (csrc/torch_ops.cpp -> lib/b200q_torch_ops.so, torch stable
+    ABI like the reference's bindings.cpp:498-540).  False -- and the Python-registered ops + ctypes calls below take over --
+    only when another library already owns the `_qutlass_C` names in this process (tools that load the compiled REFERENCE
+    first to race it) or when the profiling build of the C library was selected (B200Q_LIB=prof)."""
+    if os.environ.get("B200Q_LIB") == "prof" or os.environ.get("B200Q_NO_COMPILED_OPS") == "1":
+        return False
+    path = os.path.join(os.path.dirname(_lib.LIB_PATH), "b200q_torch_ops.so")
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found: build it with `python -m qutlass_b200.build`")
+    if hasattr(torch.ops._qutlass_C, "matmul_mxf4_bf16_tn"):
+        return False
+    _lib.load()
+    torch.ops.load_library(path)
+    return True
+
+
+_COMPILED_OPS = False
+
+
 def _check(cond: bool, msg: str) -> None:
     if not cond:
         raise RuntimeError(msg)
@@ -89,7 +109,11 @@ def _check_contig(name: str, tensors) -> None:
 # --------------------------------------------------------------------------------------- GEMM
 def _matmul_fp4(name: str, a, b, a_sf, b_sf, alpha, kind: int, sf_dtype, min_k_bytes: int, cfg=(0, 0),
                 static_weights: bool = False):
-    """reference checks: qutlass/csrc/bindings.cpp:32-102"""
+    """reference checks: qutlass/csrc/bindings.cpp:32-102 (compiled op layer: csrc/torch_ops.cpp gemm_impl; the Python copy
+    below only runs when that layer is not loaded)"""
+    if _COMPILED_OPS:
+        return torch.ops._b200q_C.gemm_fp4(a, b, a_sf, b_sf, alpha, kind | (GEMM_STATIC_WEIGHTS if static_weights else 0),
+                                           cfg[0], cfg[1])
     _check_contig(name, [("A", a), ("B", b), ("A_sf", a_sf), ("B_sf", b_sf)])
     _check_cuda_same(name, [("A", a), ("B", b), ("A_sf", a_sf), ("B_sf", b_sf), ("alpha", alpha)])
     f8 = kind in (KIND_MXF8, KIND_MXF8_NN)
@@ -143,6 +167,8 @@ def matmul_mxf4_bf16_tn(a: torch.Tensor, b: torch.Tensor, a_sf: torch.Tensor, b_
     kernels right in front of this call on the stream (weights quantised once); the GEMM then prefetches them while the
     preceding kernel drains (include/b200q.h: B200Q_GEMM_STATIC_WEIGHTS).  The default is safe for any call order."""
     _backend_gate(backend)
+    if _COMPILED_OPS and not static_weights:
+        return torch.ops._qutlass_C.matmul_mxf4_bf16_tn(a, b, a_sf, b_sf, alpha)      # like qutlass/__init__.py:42-43
     return _matmul_fp4("matmul_mxf4_bf16_tn", a, b, a_sf, b_sf, alpha, KIND_MXF4, torch.float8_e8m0fnu, 32,
                        static_weights=static_weights)
 
@@ -153,6 +179,8 @@ def matmul_nvf4_bf16_tn(a: torch.Tensor, b: torch.Tensor, a_sf: torch.Tensor, b_
     """D = bf16(alpha * dq(a) @ dq(b).T), NVFP4 (reference: qutlass/__init__.py:89-131).  ``static_weights``: see
     matmul_mxf4_bf16_tn."""
     _backend_gate(backend)
+    if _COMPILED_OPS and not static_weights:
+        return torch.ops._qutlass_C.matmul_nvf4_bf16_tn(a, b, a_sf, b_sf, alpha)
     return _matmul_fp4("matmul_nvf4_bf16_tn", a, b, a_sf, b_sf, alpha, KIND_NVF4, torch.float8_e4m3fn, 16,
                        static_weights=static_weights)
 
@@ -238,6 +266,10 @@ def _quant_checks(name: str, a, r, outs, extra=()):
 
 
 def _quantize_mx_into(a, r, out, out_sf, out_sf_blocked, out_mask, method: int):
+    if _COMPILED_OPS and out_sf is not None:
+        _detach_blocked(out_sf)
+        torch.ops._b200q_C.quantize_mx(a, r, out, out_sf, out_sf_blocked, out_mask, method | _rotation_hint(r))
+        return
     had = _quant_checks("fusedQuantizeMx", a, r, [out, out_sf])
     _check(had in (32, 64, 128), f"Unsupported rotation size {had}; expected 32, 64, or 128.")
     _check(a.size(-1) % 32 == 0, "last dimension of A must be a multiple of 32")
@@ -252,6 +284,13 @@ def _quantize_mx_into(a, r, out, out_sf, out_sf_blocked, out_mask, method: int):
 
 
 def _quantize_nv_into(a, r, out, out_sf, out_sf_blocked, global_scale, method: int):
+    if _COMPILED_OPS and out_sf is not None:
+        _detach_blocked(out_sf)
+        flags = method | _rotation_hint(r)
+        if method == METHOD_ABSMAX and r.dim() == 2 and r.size(0) == 128 and os.environ.get("B200Q_NV128_ORACLE_CODES") == "1":
+            flags |= NV_ORACLE_CODES
+        torch.ops._b200q_C.quantize_nv(a, r, out, out_sf, out_sf_blocked, global_scale, flags)
+        return
     had = _quant_checks("fusedQuantizeNv", a, r, [out, out_sf], extra=[("global_scale", global_scale)])
     _check(global_scale.dtype == torch.float32, "global_scale must be float")
     _check(global_scale.dim() == 1 and global_scale.size(0) == 1, "global_scale must be a scalar")
@@ -546,8 +585,9 @@ def mxfp4_transpose_mxfp8(x_fp4: torch.Tensor, scales: torch.Tensor):
 
 # --------------------------------------------------------------------------------------- torch.ops._qutlass_C
 def _register_ops() -> None:
-    """Same op names and schemas as the reference's STABLE_TORCH_LIBRARY_FRAGMENT(_qutlass_C)
-    (qutlass/csrc/bindings.cpp:498-507), CUDA dispatch key."""
+    """Python registration of the same op names and schemas as the reference's STABLE_TORCH_LIBRARY_FRAGMENT(_qutlass_C)
+    (qutlass/csrc/bindings.cpp:498-507), CUDA dispatch key.  FALLBACK ONLY: normally the compiled layer
+    (lib/b200q_torch_ops.so) owns these names and this function is not called."""
     try:
         lib = torch.library.Library("_qutlass_C", "FRAGMENT")
     except Exception:  # pragma: no cover
@@ -595,4 +635,6 @@ def _register_ops() -> None:
     globals()["_OPS_LIB"] = lib  # keep alive
 
 
-_register_ops()
+_COMPILED_OPS = _load_compiled_ops()
+if not _COMPILED_OPS:
+    _register_ops()

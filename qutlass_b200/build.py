@@ -23,7 +23,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200q.so")
 OBJDIR = os.path.join(HERE, "build")
 
-SOURCES = ["common.cu", "quantize.cu", "gemm_fp4.cu", "linear_host.cu", "backward.cu", "quantize_tc.cu"]
+SOURCES = ["common.cu", "quantize.cu", "gemm_fp4.cu", "gemm_decode.cu", "linear_host.cu", "backward.cu", "quantize_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -45,7 +45,7 @@ def _digest(extra: str = "") -> str:
     h.update(extra.encode())
     for name in sorted(os.listdir(CSRC)) + ["../../include/b200q.h"]:
         p = os.path.join(CSRC, name)
-        if os.path.isfile(p):
+        if os.path.isfile(p) and name != "torch_ops.cpp":
             h.update(name.encode())
             h.update(open(p, "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -61,6 +61,8 @@ def build(force: bool = False, verbose: bool = False, profiling: bool = False) -
     stamp = lib.replace(".so", ".sha256")
     digest = _digest("prof" if profiling else "")
     if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        if not profiling:
+            build_torch_ops(verbose=verbose)
         return lib
     nvcc = _nvcc()
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
@@ -83,7 +85,42 @@ def build(force: bool = False, verbose: bool = False, profiling: bool = False) -
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:
         f.write(digest)
+    if not profiling:
+        build_torch_ops(force=True, verbose=verbose)
     return lib
+
+
+OPS_LIB = os.path.join(LIBDIR, "b200q_torch_ops.so")
+
+
+def build_torch_ops(force: bool = False, verbose: bool = False) -> str:
+    """The compiled torch op layer (csrc/torch_ops.cpp: torch stable ABI, no CUDA code) -> lib/b200q_torch_ops.so, linked
+    against libb200q.so next to it (rpath $ORIGIN).  g++ only; needs torch's headers."""
+    src = os.path.join(CSRC, "torch_ops.cpp")
+    stamp = OPS_LIB.replace(".so", ".sha256")
+    h = hashlib.sha256(open(src, "rb").read() + open(os.path.join(ROOT, "include", "b200q.h"), "rb").read())
+    import torch
+    h.update(torch.__version__.encode())
+    digest = h.hexdigest()
+    if not force and os.path.exists(OPS_LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return OPS_LIB
+    tdir = os.path.dirname(torch.__file__)
+    inc, tlib = os.path.join(tdir, "include"), os.path.join(tdir, "lib")
+    major, minor = (int(x) for x in torch.__version__.split("+")[0].split(".")[:2])
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DUSE_CUDA", "-Wno-attributes",
+           "-DTORCH_TARGET_VERSION=0x%016XULL" % ((major << 56) | (minor << 48)),
+           "-I" + inc, "-I" + os.path.join(inc, "torch", "csrc", "api", "include"), "-I" + os.path.join(ROOT, "include"),
+           src, "-o", OPS_LIB, "-L" + LIBDIR, "-lb200q", "-L" + tlib, "-ltorch_cpu", "-ltorch_cuda", "-lc10",
+           "-Wl,-rpath,$ORIGIN"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for torch_ops.cpp:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return OPS_LIB
 
 
 if __name__ == "__main__":

@@ -1,0 +1,348 @@
+// Weight-streaming block-scaled FP4 GEMM for decode-size batches (M <= 32), sm_100a.
+//
+// Same contract and arithmetic as gemm_fp4_kernel (D = bf16(alpha * (A.SFA)(B.SFB)^T), ONE fp32 accumulation chain per
+// output over all of K in ascending k, alpha once, one RNE) -- replaces, for small M, the reference's 128 x 128 decode tile
+// (qutlass/csrc/gemm.cu:195-203).  What differs is the mapping onto the tensor core, chosen from a measured timeline of the
+// general kernel at M = 16 (profiles/r02_decode_probe_before.jsonl): there the mainloop is NOT bandwidth-bound, it costs
+// ~480 cycles per k-tile of tcgen05 issue (4 scale copies + 4 MMAs whose 128-row A operand is 7/8 padding + commit).  Here:
+//
+//   * operands are SWAPPED: the 128 weight rows of a tile are the M = 128 operand ("A") of tcgen05.mma, the activations
+//     the N = NP (16 or 32) operand ("B"): D^T[n, m] accumulates in 128 TMEM lanes x NP columns.  An MMA is 128 x NP x 64
+//     instead of 128 x 128 x 64: 4-8x less tensor time per instruction, no padded rows.
+//   * ALL of x (NP rows x K/2 bytes, <= 64 KB) and ALL of its scales are loaded ONCE per CTA into shared memory, and
+//     the scales are copied to TMEM once (K/128 resp. K/64 tcgen05.cp at start-up, under the latency of the first weight
+//     tiles): the per-k-tile work of the single issuing thread is 2 (MX) / 4 (NV) weight-scale copies + 4 MMAs + 1 commit.
+//   * the ring holds only weights: 17-18 KB per stage, 8-10 k-tiles in flight per SM.
+//   * epilogue: thread = output column n (TMEM lane), registers = the NP rows m; bf16 stores are 64 contiguous bytes per warp
+//     and row -- D is tiny (M x N x 2 bytes).
+// The products are the same numbers in the same k order as in the general kernel, so the result is bit-identical to it
+// (tests/test_gpu_parity.py::test_decode_kernel_*).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+#include <cuda.h>
+
+namespace b200q {
+using namespace ptx;
+
+constexpr int kDecThreads = 192;          // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue (one per TMEM lane quarter)
+constexpr int kDecMaxStages = 12;
+constexpr int kDecSmemBudget = 227 * 1024;
+constexpr int kDecEarlyStages = 4;        // static weights: stages whose REAL loads are issued before the grid dependency
+
+struct DecodeParams {
+  const float* alpha;
+  __nv_bfloat16* d;
+  int M, N, K, ldd;
+  int k_tiles;        // K / 256
+  int tiles;          // ceil(N / 128)
+  int stages;         // weight ring depth (host: what fits next to x)
+  int static_weights;
+};
+
+template <bool kNV>
+struct DecodeCfg {
+  static constexpr int SFKB = kNV ? 4 : 2;                 // 512-B scale blocks per 128 rows per k-tile
+  static constexpr int W_BYTES = 128 * 128;                // weight tile: 128 rows x 128 bytes (256 e2m1)
+  static constexpr int WSF_BYTES = SFKB * 512;
+  static constexpr int STAGE_BYTES = W_BYTES + WSF_BYTES;  // 17 / 18 KB: multiple of 1024 (128B-swizzle atoms stay aligned)
+  static constexpr int BAR_BYTES = 1024;
+  static_assert(STAGE_BYTES % 1024 == 0, "stage alignment");
+};
+
+template <bool kNV, int NP>
+__global__ void __launch_bounds__(kDecThreads, 1)
+gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                       const __grid_constant__ CUtensorMap tmap_sfx, const __grid_constant__ CUtensorMap tmap_sfw,
+                       const DecodeParams p) {
+  using Cfg = DecodeCfg<kNV>;
+  constexpr int SFKB = Cfg::SFKB;
+  constexpr int ACC = 2;
+  static_assert(NP == 16 || NP == 32, "activation rows per MMA");
+  const int STAGES = p.stages;
+
+  extern __shared__ uint8_t dec_smem_raw[];
+  const uint32_t smem_base = (smem_u32(dec_smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = dec_smem_raw + (smem_base - smem_u32(dec_smem_raw));
+  const uint32_t x_bytes = (uint32_t)p.k_tiles * NP * 128u;                // resident activations, one 128B-swizzled tile per k-tile
+  const uint32_t xsf_bytes = (uint32_t)p.k_tiles * SFKB * 512u;            // resident activation scales (blocked layout)
+  const uint32_t x_base = smem_base;
+  const uint32_t xsf_base = x_base + x_bytes;
+  const uint32_t ring_base = (xsf_base + xsf_bytes + 1023u) & ~1023u;
+  const uint32_t bar_base = ring_base + (uint32_t)STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kDecMaxStages + s); };
+  const uint32_t x_bar = bar_base + 8u * (2 * kDecMaxStages);
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kDecMaxStages + 1 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kDecMaxStages + 1 + ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kDecMaxStages + 1 + 2 * ACC);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * kDecMaxStages + 1 + 2 * ACC));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_w);
+    prefetch_tensormap(&tmap_sfw);
+    prefetch_tensormap(&tmap_x);
+    prefetch_tensormap(&tmap_sfx);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(x_bar, 1);
+    for (int a = 0; a < ACC; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);            // the four epilogue warps
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_gen, 0);
+  const uint32_t tmem_wsf = tmem_base + ACC * NP;              // weight scales of the current k-tile (SFKB blocks x 4 columns)
+  const uint32_t tmem_xsf = tmem_wsf + SFKB * 4;               // ALL activation scales: k_tiles x SFKB blocks x 4 columns
+
+  int my_tiles = 0;
+  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) ++my_tiles;
+  const int total_kt = my_tiles * p.k_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const bool elected = elect_one();
+    auto load_w = [&](int stage, int tile, int kt) {
+      const uint32_t sb = ring_base + (uint32_t)stage * Cfg::STAGE_BYTES;
+      mbar_arrive_expect_tx(full_bar(stage), (uint32_t)Cfg::STAGE_BYTES);
+      tma_load_2d<1>(sb, &tmap_w, full_bar(stage), kt * 128, tile * 128);
+      tma_load_3d<1>(sb + Cfg::W_BYTES, &tmap_sfw, full_bar(stage), 0, kt * SFKB, tile);
+    };
+    auto prefetch_w = [&](int tile, int kt) {
+      tma_prefetch_2d(&tmap_w, kt * 128, tile * 128);
+      tma_prefetch_3d(&tmap_sfw, 0, kt * SFKB, tile);
+    };
+    const int pre = total_kt < STAGES ? total_kt : STAGES;
+    // Before the grid dependency resolves only the weights may be touched, and only for real if the caller vouched for
+    // them (B200Q_GEMM_STATIC_WEIGHTS) -- and then only a few stages, so that the activation loads issued right after the
+    // wait are not queued behind a whole ring of weight traffic; everything else is an L2 prefetch (always safe).
+    const int early = p.static_weights ? (pre < kDecEarlyStages ? pre : kDecEarlyStages) : 0;
+    {
+      int tile = blockIdx.x, kt = 0;
+      for (int g = 0; g < pre; ++g) {
+        if (elected) {
+          if (g < early) load_w(g, tile, kt);
+          else prefetch_w(tile, kt);
+        }
+        if (++kt == p.k_tiles) { kt = 0; tile += gridDim.x; }
+      }
+    }
+    pdl_wait();
+    // the activations (written by the kernel in front of us) and their scales: resident for the whole kernel
+    // (warp-uniform loops with the elected lane issuing inside: no divergent-branch waterfall around the TMA ops)
+    if (elected) {
+      mbar_arrive_expect_tx(x_bar, x_bytes + xsf_bytes);
+      tma_load_3d<1>(xsf_base, &tmap_sfx, x_bar, 0, 0, 0);
+    }
+    for (int kt = 0; kt < p.k_tiles; ++kt) {
+      if (elected) tma_load_2d<1>(x_base + (uint32_t)kt * NP * 128u, &tmap_x, x_bar, kt * 128, 0);
+    }
+    int tile = blockIdx.x, kt = 0;
+    for (int g = 0; g < pre; ++g) {
+      if (elected && g >= early) load_w(g, tile, kt);
+      if (++kt == p.k_tiles) { kt = 0; tile += gridDim.x; }
+    }
+    __syncwarp();
+    int stage = (pre == STAGES) ? 0 : pre;
+    uint32_t phase = (pre == STAGES) ? 1 : 0;
+    for (int g = pre; g < total_kt; ++g) {
+      mbar_wait(empty_bar(stage), phase ^ 1, 1);
+      if (elected) load_w(stage, tile, kt);
+      __syncwarp();
+      if (++kt == p.k_tiles) { kt = 0; tile += gridDim.x; }
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const bool elected = elect_one();
+    constexpr uint32_t idesc_base = make_idesc_fp4(128, NP, !kNV);
+    constexpr uint32_t kDescHiAB = (1024u >> 4) | (1u << 14) | (kLayoutSw128 << 29);   // SBO 1024 B, version 1, 128B swizzle
+    constexpr uint32_t kDescHiSF = (128u >> 4) | (1u << 14);                            // SBO 128 B, version 1, no swizzle
+    auto mk = [](uint32_t lo, uint32_t hi) {
+      uint64_t d;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+      return d;
+    };
+    const uint32_t x_lo0 = ((x_base & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t xsf_lo0 = (xsf_base & 0x3FFFFu) >> 4;
+    const uint32_t ring_lo0 = ((ring_base & 0x3FFFFu) >> 4);
+    // activation scales -> TMEM, once
+    mbar_wait(x_bar, 0, 2);
+    tc_fence_after();
+    {
+      const int nblk = p.k_tiles * SFKB;
+      for (int c = 0; c < nblk; ++c) {
+        if (elected) tmem_cp_32x128b_warpx4<1>(tmem_xsf + (uint32_t)c * 4u, mk(xsf_lo0 + (uint32_t)c * 32u, kDescHiSF));
+      }
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1, 3);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)acc * NP;
+      for (int kt = 0; kt < p.k_tiles; ++kt) {
+        mbar_wait_spin(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t w_lo = (ring_lo0 + (uint32_t)stage * (Cfg::STAGE_BYTES >> 4)) | (1u << 16);
+        const uint32_t wsf_lo = ring_lo0 + (uint32_t)stage * (Cfg::STAGE_BYTES >> 4) + (Cfg::W_BYTES >> 4);
+        const uint32_t x_lo = x_lo0 + (uint32_t)kt * ((NP * 128u) >> 4);
+        const uint32_t txsf = tmem_xsf + (uint32_t)kt * (SFKB * 4u);
+        if (elected) {
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            // scales per MMA (K = 64): MXF4 2 bytes of a 4-byte cell (sf_id 0 / 2), NVF4 the whole cell
+            const uint32_t chunk = kNV ? (uint32_t)kb : (uint32_t)(kb >> 1);
+            if (kNV || (kb & 1) == 0) tmem_cp_32x128b_warpx4<1>(tmem_wsf + chunk * 4u, mk(wsf_lo + chunk * 32u, kDescHiSF));
+            const uint32_t sf_id = kNV ? 0u : (uint32_t)((kb & 1) * 2);
+            // A operand = weights (scales: tmem_wsf), B operand = activations (scales: the resident block of this k-tile)
+            mma_fp4_block_scaled<1, kNV, false>(tmem_acc, mk(w_lo + kb * 2u, kDescHiAB), mk(x_lo + kb * 2u, kDescHiAB),
+                                                idesc_base | (sf_id << 4) | (sf_id << 29), tmem_wsf + chunk * 4u, txsf + chunk * 4u,
+                                                (kb > 0) ? 1u : (kt > 0 ? 1u : 0u));
+          }
+          tc_commit<1>(empty_bar(stage));
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (elected) tc_commit<1>(tfull_bar(acc));
+      __syncwarp();
+      if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5): thread = output column, registers = the rows =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    pdl_wait();                                   // D may still be read by the predecessor kernel
+    const float alpha = __ldg(p.alpha);
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      mbar_wait(tfull_bar(acc), acc_phase, 4);
+      tc_fence_after();
+      uint32_t r[NP];
+      const uint32_t taddr = tmem_base + (uint32_t)acc * NP + ((uint32_t)(q * 32) << 16);
+      if constexpr (NP == 16) tmem_ld_32x32b_x16(taddr, r);
+      else tmem_ld_32x32b_x32(taddr, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      const int n = t * 128 + q * 32 + lane;
+      if (n < p.N) {
+        uint16_t* dcol = reinterpret_cast<uint16_t*>(p.d) + n;
+#pragma unroll
+        for (int m = 0; m < NP; ++m) {
+          if (m < p.M) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(__uint_as_float(r[m]) * alpha);
+            dcol[(int64_t)m * p.ldd] = *reinterpret_cast<const uint16_t*>(&h);
+          }
+        }
+      }
+      if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int decode_stages(int M, int K, bool nv, int* np_out) {
+  const int np = M <= 16 ? 16 : 32;
+  const int k_tiles = K / 256;
+  const int sfkb = nv ? 4 : 2;
+  const int64_t resident = (int64_t)k_tiles * np * 128 + (int64_t)k_tiles * sfkb * 512;
+  const int stage = 128 * 128 + sfkb * 512;
+  const int64_t room = (int64_t)kDecSmemBudget - 1024 /*alignment*/ - 1024 /*ring alignment*/ - 1024 /*barriers*/ - resident;
+  int stages = (int)(room / stage);
+  if (stages > kDecMaxStages) stages = kDecMaxStages;
+  if (np_out) *np_out = np;
+  return stages;
+}
+
+bool decode_eligible(int M, int N, int K, int ldd, int kind) {
+  if (kind != B200Q_KIND_MXF4 && kind != B200Q_KIND_NVF4) return false;
+  if (M < 1 || M > 32 || N < 1 || K < 256 || K % 256 != 0 || ldd < N) return false;
+  const bool nv = kind == B200Q_KIND_NVF4;
+  const int k_tiles = K / 256, sfkb = nv ? 4 : 2;
+  if (2 * 32 + sfkb * 4 + k_tiles * sfkb * 4 > 512) return false;      // TMEM: accumulators + weight scales + ALL activation scales
+  if (k_tiles * sfkb > 256) return false;                                  // one tensor-map box holds all activation scale blocks
+  return decode_stages(M, K, nv, nullptr) >= 4;
+}
+
+template <bool kNV, int NP>
+static int launch_decode_t(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D, int M, int N,
+                           int K, int ldd, bool static_w, cudaStream_t stream) {
+  using Cfg = DecodeCfg<kNV>;
+  auto kern = gemm_fp4_decode_kernel<kNV, NP>;
+  DecodeParams p;
+  p.alpha = alpha;
+  p.d = (__nv_bfloat16*)D;
+  p.M = M; p.N = N; p.K = K; p.ldd = ldd;
+  p.k_tiles = K / 256;
+  p.tiles = (int)ceil_div(N, 128);
+  p.stages = decode_stages(M, K, kNV, nullptr);
+  p.static_weights = static_w ? 1 : 0;
+  const int smem = 1024 + p.k_tiles * NP * 128 + p.k_tiles * Cfg::SFKB * 512 + 1024 + p.stages * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
+  static std::atomic<unsigned long long> smem_attr_done{0};
+  if (int rc_attr = ensure_dynamic_smem(kern, kDecSmemBudget, smem_attr_done)) return rc_attr;
+  const int group = kNV ? 16 : 32;
+  const int64_t sf_col_blocks = ceil_div(ceil_div(K, group), 4);
+  CUtensorMap tx, tw, tsx, tsw;
+  int rc;
+  if ((rc = make_operand_tmap(&tx, A, M, K / 2, NP, "x (decode)"))) return rc;
+  if ((rc = make_operand_tmap(&tw, B, N, K / 2, 128, "W (decode)"))) return rc;
+  if ((rc = make_sf_tmap(&tsx, SFA, ceil_div(M, 128), sf_col_blocks, (int)sf_col_blocks, 1, "SFx (decode)"))) return rc;
+  if ((rc = make_sf_tmap(&tsw, SFB, ceil_div(N, 128), sf_col_blocks, Cfg::SFKB, 1, "SFW (decode)"))) return rc;
+  cudaLaunchConfig_t cfg = {};
+  int ctas = num_sms();
+  if (ctas > p.tiles) ctas = p.tiles;
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(kDecThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = env().no_pdl == 1 ? 0 : 1;
+  B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, tsx, tsw, p));
+  return 0;
+}
+
+int launch_gemm_decode(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D, int M, int N,
+                       int K, int ldd, int kind, bool static_w, cudaStream_t stream) {
+  if (!decode_eligible(M, N, K, ldd, kind)) {
+    set_error("the decode kernel needs an FP4 kind, 1 <= M <= 32, K %% 256 == 0 and K small enough for resident activations "
+              "(M=%d N=%d K=%d kind=%d)", M, N, K, kind);
+    return B200Q_EINVAL;
+  }
+  const bool nv = kind == B200Q_KIND_NVF4;
+  if (M <= 16) return nv ? launch_decode_t<true, 16>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream)
+                         : launch_decode_t<false, 16>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream);
+  return nv ? launch_decode_t<true, 32>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream)
+            : launch_decode_t<false, 32>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream);
+}
+
+}  // namespace b200q

@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "quantize_tile.cuh"
+#include "tmap.cuh"
 #include <type_traits>
 
 #include <cuda.h>
@@ -1158,8 +1159,8 @@ int make_rot_tmap(void* tm, const void* ptr, int had) {
 }
 
 // [rows, row_bytes] uint8 operand, box = [box_rows, 128 bytes], 128B swizzle, zero fill out of bounds
-static int make_operand_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t row_bytes, int box_rows,
-                             const char* what) {
+int make_operand_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t row_bytes, int box_rows,
+                      const char* what) {
   cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
   cuuint32_t box[2] = {(cuuint32_t)BK_BYTES, (cuuint32_t)box_rows};
@@ -1168,8 +1169,8 @@ static int make_operand_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int
 
 // blocked scale buffer as a 3-D tensor {128 x u32 (one 512-B block), col_blocks, row_blocks};
 // box = {128, kblocks, rblocks}; out-of-range blocks read as zero (scale 2^-127 / 0.0: never NaN)
-static int make_sf_tmap(CUtensorMap* tm, const void* ptr, int64_t row_blocks, int64_t col_blocks, int box_kb,
-                        int box_rb, const char* what) {
+int make_sf_tmap(CUtensorMap* tm, const void* ptr, int64_t row_blocks, int64_t col_blocks, int box_kb,
+                 int box_rb, const char* what) {
   cuuint64_t dims[3] = {128, (cuuint64_t)col_blocks, (cuuint64_t)row_blocks};
   cuuint64_t strides[2] = {512, (cuuint64_t)col_blocks * 512};
   cuuint32_t box[3] = {128, (cuuint32_t)box_kb, (cuuint32_t)box_rb};
@@ -1326,6 +1327,11 @@ static int launch_gemm_hybrid(const void* A, const void* B, const void* SFA, con
 template <bool kNV, int kF8>
 static int dispatch_cfg(int cta_group, int block_n, const void* A, const void* B, const void* SFA, const void* SFB,
                         const float* alpha, void* D, int M, int N, int K, int ldd, cudaStream_t s, bool sw) {
+  // decode (M <= 32): the weight-streaming kernel with swapped operands (gemm_decode.cu), configuration (1, 16)
+  if constexpr (kF8 == 0) {
+    if (cta_group == 1 && block_n == 16)
+      return launch_gemm_decode(A, B, SFA, SFB, alpha, D, M, N, K, ldd, kNV ? B200Q_KIND_NVF4 : B200Q_KIND_MXF4, sw, s);
+  }
   // small M: same 128-wide single-CTA tile, fewer A rows staged (more weight k-tiles in flight)
   if constexpr (kF8 != 2) {
     if (cta_group == 1 && block_n == 128 && M <= 16) return launch_gemm<1, 128, kNV, 16, kF8>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, s, sw);
@@ -1377,7 +1383,8 @@ static GemmPlan plan_auto(int M, int N, int K, int kind) {
     // with the tile width that minimises rounds x (k_tiles x w + o) -- w / o = per-k-tile / per-tile cost of one round in
     // us, fitted at K = 4096 and 8192: the 256-wide tile pays the single-buffered accumulator hand-off, the narrower ones
     // are bound by the tcgen05 dispatch rate (same per-k-tile cost for 192 and 128 columns).
-    if (M <= 128) { cta_group = 1; block_n = 128; }
+    if (M <= 32 && decode_eligible(M, N, K, N, kind)) { cta_group = 1; block_n = 16; }
+    else if (M <= 128) { cta_group = 1; block_n = 128; }
     else if (M <= 256 && N <= 4096) { cta_group = 1; block_n = 128; }
     else if (M <= 256 && ceil_div(M, 128) * ceil_div(N, 256) <= num_sms()) { cta_group = 1; block_n = 256; }
     else {

@@ -80,6 +80,8 @@ def to_blocked(input_matrix: torch.Tensor, use_triton_kernel: bool = False) -> t
     if not use_triton_kernel:
         # the reference's torch path asserts the input is already padded (utils.py:187)
         assert (rows, cols) == (ceil_div(rows, 128) * 128, ceil_div(cols, 4) * 4)
+    if hasattr(torch.ops, "_b200q_C") and hasattr(torch.ops._b200q_C, "swizzle_sf"):
+        return torch.ops._b200q_C.swizzle_sf(x)        # compiled op layer (csrc/torch_ops.cpp)
     out = torch.empty(ceil_div(rows, 128) * 128 * ceil_div(cols, 4) * 4, dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().b200q_swizzle_sf(x.data_ptr(), out.data_ptr(), rows, cols,

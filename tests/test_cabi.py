@@ -78,7 +78,14 @@ def test_gemm_planner_choices_without_a_gpu(lib_path):
         assert lib.b200q_gemm_fp4_plan(m, n, k, kind, ctypes.byref(cg), ctypes.byref(bn)) == 0
         return cg.value, bn.value
 
-    assert plan(1, 14336, 4096) == (1, 128) and plan(128, 14336, 4096) == (1, 128)
+    # decode (M <= 32, FP4, K % 256 == 0, activations resident): the swapped-operand weight-streaming kernel, "(1, 16)"
+    assert plan(1, 14336, 4096) == (1, 16) and plan(16, 14336, 4096) == (1, 16) and plan(32, 14336, 4096) == (1, 16)
+    assert plan(16, 28672, 8192) == (1, 16) and plan(32, 28672, 8192) == (1, 128)   # 32 rows x K = 8192: x no longer fits next to a ring
+    assert plan(16, 14336, 4096, 1) == (1, 16)
+    assert plan(16, 28672, 8192, 1) == (1, 128)         # NVFP4 at K = 8192: the activation scales do not fit TMEM next to the rest
+    assert plan(16, 14336, 4096, 2) == (1, 128)         # MXFP8 keeps the general kernel
+    assert plan(16, 14336, 4000) == (1, 128)            # K % 256 != 0
+    assert plan(33, 14336, 4096) == (1, 128) and plan(128, 14336, 4096) == (1, 128)
     assert plan(256, 14336, 4096) == (1, 256)
     assert plan(4096, 14336, 4096) == (2, 256) and plan(4096, 14336, 4096, 1) == (2, 256)      # BASELINE configs 1 / 2
     assert plan(16384, 14336, 4096) == (2, 256) and plan(2048, 28672, 8192) == (2, 256)        # config 4 shard

@@ -912,3 +912,69 @@ def test_to_blocked_hand_over_and_invalidation():
         blk = Q.to_blocked(sf)
         torch.cuda.synchronize()
         np.testing.assert_array_equal(H.u8_of(blk), H.blocked_sf(H.u8_of(sf)))
+
+
+# ----------------------------------------------------------------------------- decode kernel (gemm_decode.cu)
+@pytest.mark.parametrize("kind", ["mx", "nv"])
+@pytest.mark.parametrize("shape", [(1, 504, 4096), (16, 14336, 4096), (7, 1000, 2048), (32, 2816, 1024), (17, 640, 256),
+                                   (16, 128 * 150, 512), (3, 100, 768)])
+def test_decode_kernel_bit_identical_to_the_general_kernel_and_exact_vs_oracle(kind, shape):
+    """The swapped-operand weight-streaming kernel (configuration (1, 16), the default for M <= 32) computes the same
+    products in the same k order as gemm_fp4_kernel: bit-identical to it on wide-dynamic-range operands, bit-exact against
+    the fp64 oracle where fp32 accumulation is exact.  Shapes: N % 128 != 0 (ragged last tile), N % 8 != 0, M = 1 / 17 / 32
+    (16- and 32-row MMA shapes), more tiles than SMs (two accumulators alternate), a single k-tile."""
+    m, n, k = shape
+    for mode in ("narrow", "wide"):
+        aq, asf = H.random_fp4_operand(m, k, kind, seed=m + 31, sf_mode=mode)
+        bq, bsf = H.random_fp4_operand(n, k, kind, seed=n + 32, sf_mode=mode)
+        got = H.run_gemm(aq, asf, bq, bsf, kind, 1.0 / 3.0, cfg=(1, 16))
+        np.testing.assert_array_equal(got, H.run_gemm(aq, asf, bq, bsf, kind, 1.0 / 3.0, cfg=(1, 128)))
+        np.testing.assert_array_equal(got, H.run_gemm(aq, asf, bq, bsf, kind, 1.0 / 3.0))          # and it IS the default
+        if mode == "narrow":
+            want = H.gemm_oracle_bits(aq, asf, bq, bsf, kind, 1.0)
+            mism, rel = H.compare_bits(H.run_gemm(aq, asf, bq, bsf, kind, 1.0, cfg=(1, 16)), want)
+            if kind == "mx":
+                assert mism == 0.0, (mism, rel)
+            else:
+                assert rel <= REL_TOL and mism <= 1e-3, (mism, rel)
+
+
+def test_decode_kernel_is_rejected_where_it_does_not_apply():
+    aq, asf = H.random_fp4_operand(64, 512, "mx", seed=1)
+    bq, bsf = H.random_fp4_operand(256, 512, "mx", seed=2)
+    with pytest.raises(Exception, match="decode kernel"):
+        H.run_gemm(aq, asf, bq, bsf, "mx", 1.0, cfg=(1, 16))
+
+
+@pytest.mark.parametrize("fmt", ["mx", "nv"])
+def test_decode_path_in_a_cuda_graph_with_quantiser_in_front(fmt):
+    """quantise -> (to_blocked no-op) -> decode GEMM captured in one CUDA graph (the reference benchmark's loop at batch 1),
+    replayed with changing activations: equals the eager, synchronised result every time."""
+    m, n, k = 4, 1536, 2048
+    R = H.bf16_tensor_from_f32(O.hadamard_matrix(128))
+    gs = torch.tensor([1.0], device="cuda")
+    al = torch.tensor([0.25], device="cuda")
+    fq = (lambda t: Q.fusedQuantizeMx(t, R, method="abs_max")) if fmt == "mx" else (lambda t: Q.fusedQuantizeNv(t, R, gs, method="abs_max"))
+    mm = Q.matmul_mxf4_bf16_tn if fmt == "mx" else Q.matmul_nvf4_bf16_tn
+    w = torch.randn(n, k, dtype=torch.bfloat16, device="cuda") * 25
+    wq, wsf = fq(w)
+    wblk = Q.to_blocked(wsf)
+    x = torch.randn(m, k, dtype=torch.bfloat16, device="cuda") * 25
+    fq(x)      # the rotation matrix is classified outside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            xq, xsf = fq(x)
+            out = mm(xq, wq, Q.to_blocked(xsf), wblk, al, static_weights=True)
+    for it in range(4):
+        x.copy_(torch.randn(m, k, dtype=torch.bfloat16, device="cuda") * 25)
+        g.replay()
+        torch.cuda.synchronize()
+        xq2, xsf2 = fq(x)
+        torch.cuda.synchronize()
+        want = mm(xq2, wq, Q.to_blocked(xsf2), wblk, al)
+        torch.cuda.synchronize()
+        assert torch.equal(out, want), it
