@@ -107,17 +107,32 @@ def build_torch_ops(force: bool = False, verbose: bool = False) -> str:
     tdir = os.path.dirname(torch.__file__)
     inc, tlib = os.path.join(tdir, "include"), os.path.join(tdir, "lib")
     major, minor = (int(x) for x in torch.__version__.split("+")[0].split(".")[:2])
-    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
-    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DUSE_CUDA", "-Wno-attributes",
-           "-DTORCH_TARGET_VERSION=0x%016XULL" % ((major << 56) | (minor << 48)),
-           "-I" + inc, "-I" + os.path.join(inc, "torch", "csrc", "api", "include"), "-I" + os.path.join(ROOT, "include"),
-           src, "-o", OPS_LIB, "-L" + LIBDIR, "-lb200q", "-L" + tlib, "-ltorch_cpu", "-ltorch_cuda", "-lc10",
-           "-Wl,-rpath,$ORIGIN"]
-    if verbose:
-        print(" ".join(cmd), flush=True)
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"g++ failed for torch_ops.cpp:\n{r.stdout}\n{r.stderr}")
+    # The library throws C++ exceptions into libtorch (STD_TORCH_CHECK), so it MUST share libtorch's C++ runtime: a g++
+    # whose libstdc++.so is missing links libstdc++.a instead (this image's $CXX = /opt/gcc/bin/g++ does: its own copy of
+    # __cxa_throw inside the .so, and a failed argument check then SEGFAULTS on the GPU box instead of raising
+    # RuntimeError -- observed, profiles/r02_notes.md).  Candidates are tried in order and the result is verified with nm.
+    cands = [c for c in ("/usr/bin/g++", shutil.which("g++"), os.environ.get("CXX")) if c and os.path.exists(c)]
+    errors = []
+    for cxx in dict.fromkeys(cands):
+        cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DUSE_CUDA", "-Wno-attributes",
+               "-DTORCH_TARGET_VERSION=0x%016XULL" % ((major << 56) | (minor << 48)),
+               "-I" + inc, "-I" + os.path.join(inc, "torch", "csrc", "api", "include"), "-I" + os.path.join(ROOT, "include"),
+               src, "-o", OPS_LIB, "-L" + LIBDIR, "-lb200q", "-L" + tlib, "-ltorch_cpu", "-ltorch_cuda", "-lc10",
+               "-Wl,-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            errors.append(f"{cxx}: {r.stderr[-400:]}")
+            continue
+        syms = subprocess.run(["nm", "-D", OPS_LIB], capture_output=True, text=True).stdout
+        if any(l.split()[-2:] == ["T", "__cxa_throw"] for l in syms.splitlines() if "__cxa_throw" in l and len(l.split()) >= 2):
+            errors.append(f"{cxx}: linked libstdc++ statically (defines __cxa_throw)")
+            os.remove(OPS_LIB)
+            continue
+        break
+    else:
+        raise RuntimeError("could not build b200q_torch_ops.so with a shared C++ runtime:\n" + "\n".join(errors))
     with open(stamp, "w") as f:
         f.write(digest)
     return OPS_LIB

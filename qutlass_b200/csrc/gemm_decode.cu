@@ -39,7 +39,21 @@ struct DecodeParams {
   int tiles;          // ceil(N / 128)
   int stages;         // weight ring depth (host: what fits next to x)
   int static_weights;
+  int flags;          // profiling builds only: 1 << 24 timeline of CTA 0, 1 << 22 weights loaded for the first ring only
 };
+
+// timeline of CTA 0 (profiling flag 1 << 24), clock64 unless noted: [0] entry, [1] globaltimer at entry, [2] set-up done,
+// [3] producer past griddepcontrol.wait, [4] activations landed, [5] activation scales copied, [6] first weight stage
+// landed, [7] last MMA issued, [8] accumulator complete, [9] stores issued, [10] exit, [11] globaltimer at exit
+__device__ unsigned long long g_decode_trace[16];
+__device__ __forceinline__ void dtrace(int flags, int ev, bool wall = false) {
+  if ((flags & (1 << 24)) && blockIdx.x == 0) {
+    unsigned long long t;
+    if (wall) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    else t = (unsigned long long)clock64();
+    g_decode_trace[ev] = t;
+  }
+}
 
 template <bool kNV>
 struct DecodeCfg {
@@ -81,6 +95,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
+  if (threadIdx.x == 0) { dtrace(p.flags, 0); dtrace(p.flags, 1, true); }
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_w);
@@ -108,6 +123,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_gen, 0);
   const uint32_t tmem_wsf = tmem_base + ACC * NP;              // weight scales of the current k-tile (SFKB blocks x 4 columns)
   const uint32_t tmem_xsf = tmem_wsf + SFKB * 4;               // ALL activation scales: k_tiles x SFKB blocks x 4 columns
+  if (threadIdx.x == 0) dtrace(p.flags, 2);
 
   int my_tiles = 0;
   for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) ++my_tiles;
@@ -142,14 +158,13 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       }
     }
     pdl_wait();
+    if (lane == 0) dtrace(p.flags, 3);
     // the activations (written by the kernel in front of us) and their scales: resident for the whole kernel
     // (warp-uniform loops with the elected lane issuing inside: no divergent-branch waterfall around the TMA ops)
     if (elected) {
       mbar_arrive_expect_tx(x_bar, x_bytes + xsf_bytes);
-      tma_load_3d<1>(xsf_base, &tmap_sfx, x_bar, 0, 0, 0);
-    }
-    for (int kt = 0; kt < p.k_tiles; ++kt) {
-      if (elected) tma_load_2d<1>(x_base + (uint32_t)kt * NP * 128u, &tmap_x, x_bar, kt * 128, 0);
+      tma_load_3d<1>(xsf_base, &tmap_sfx, x_bar, 0, 0, 0);      // all scale blocks of the (one) 128-row block
+      tma_load_3d<1>(x_base, &tmap_x, x_bar, 0, 0, 0);          // all k-tiles: {128 B, NP rows, k_tiles} in ONE box
     }
     int tile = blockIdx.x, kt = 0;
     for (int g = 0; g < pre; ++g) {
@@ -159,9 +174,13 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     __syncwarp();
     int stage = (pre == STAGES) ? 0 : pre;
     uint32_t phase = (pre == STAGES) ? 1 : 0;
+    const bool ring_only = (p.flags & (1 << 22)) != 0;      // profiling: later k-tiles reuse what the first ring loaded
     for (int g = pre; g < total_kt; ++g) {
       mbar_wait(empty_bar(stage), phase ^ 1, 1);
-      if (elected) load_w(stage, tile, kt);
+      if (elected) {
+        if (ring_only) mbar_arrive(full_bar(stage));
+        else load_w(stage, tile, kt);
+      }
       __syncwarp();
       if (++kt == p.k_tiles) { kt = 0; tile += gridDim.x; }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -183,6 +202,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     // activation scales -> TMEM, once
     mbar_wait(x_bar, 0, 2);
     tc_fence_after();
+    if (lane == 0) dtrace(p.flags, 4);
     {
       const int nblk = p.k_tiles * SFKB;
       for (int c = 0; c < nblk; ++c) {
@@ -190,16 +210,21 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       }
     }
     __syncwarp();
+    if (lane == 0) dtrace(p.flags, 5);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (p.flags & (1 << 24)) {
+      mbar_wait(full_bar(0), 0, 9);
+      if (lane == 0) dtrace(p.flags, 6);
+    }
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1, 3);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)acc * NP;
       for (int kt = 0; kt < p.k_tiles; ++kt) {
-        mbar_wait_spin(full_bar(stage), phase);
+        mbar_wait(full_bar(stage), phase, 5);
         tc_fence_after();
         const uint32_t w_lo = (ring_lo0 + (uint32_t)stage * (Cfg::STAGE_BYTES >> 4)) | (1u << 16);
         const uint32_t wsf_lo = ring_lo0 + (uint32_t)stage * (Cfg::STAGE_BYTES >> 4) + (Cfg::W_BYTES >> 4);
@@ -224,6 +249,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       }
       if (elected) tc_commit<1>(tfull_bar(acc));
       __syncwarp();
+      if (lane == 0) dtrace(p.flags, 7);
       if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
     }
   } else {
@@ -236,6 +262,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase, 4);
       tc_fence_after();
+      if (warp == 2 && lane == 0) dtrace(p.flags, 8);
       uint32_t r[NP];
       const uint32_t taddr = tmem_base + (uint32_t)acc * NP + ((uint32_t)(q * 32) << 16);
       if constexpr (NP == 16) tmem_ld_32x32b_x16(taddr, r);
@@ -255,12 +282,14 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
           }
         }
       }
+      if (warp == 2 && lane == 0) dtrace(p.flags, 9);
       if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) { dtrace(p.flags, 10); dtrace(p.flags, 11, true); }
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc<1>(tmem_base, 512);
@@ -288,6 +317,7 @@ bool decode_eligible(int M, int N, int K, int ldd, int kind) {
   const int k_tiles = K / 256, sfkb = nv ? 4 : 2;
   if (2 * 32 + sfkb * 4 + k_tiles * sfkb * 4 > 512) return false;      // TMEM: accumulators + weight scales + ALL activation scales
   if (k_tiles * sfkb > 256) return false;                                  // one tensor-map box holds all activation scale blocks
+  if (k_tiles > 256) return false;                                         // ... and one box all k-tiles of x
   return decode_stages(M, K, nv, nullptr) >= 4;
 }
 
@@ -304,6 +334,7 @@ static int launch_decode_t(const void* A, const void* B, const void* SFA, const 
   p.tiles = (int)ceil_div(N, 128);
   p.stages = decode_stages(M, K, kNV, nullptr);
   p.static_weights = static_w ? 1 : 0;
+  p.flags = env().gemm_flags;
   const int smem = 1024 + p.k_tiles * NP * 128 + p.k_tiles * Cfg::SFKB * 512 + 1024 + p.stages * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
   static std::atomic<unsigned long long> smem_attr_done{0};
   if (int rc_attr = ensure_dynamic_smem(kern, kDecSmemBudget, smem_attr_done)) return rc_attr;
@@ -311,7 +342,7 @@ static int launch_decode_t(const void* A, const void* B, const void* SFA, const 
   const int64_t sf_col_blocks = ceil_div(ceil_div(K, group), 4);
   CUtensorMap tx, tw, tsx, tsw;
   int rc;
-  if ((rc = make_operand_tmap(&tx, A, M, K / 2, NP, "x (decode)"))) return rc;
+  if ((rc = make_operand_ktile_tmap(&tx, A, M, K / 2, NP, "x (decode)"))) return rc;
   if ((rc = make_operand_tmap(&tw, B, N, K / 2, 128, "W (decode)"))) return rc;
   if ((rc = make_sf_tmap(&tsx, SFA, ceil_div(M, 128), sf_col_blocks, (int)sf_col_blocks, 1, "SFx (decode)"))) return rc;
   if ((rc = make_sf_tmap(&tsw, SFB, ceil_div(N, 128), sf_col_blocks, Cfg::SFKB, 1, "SFW (decode)"))) return rc;
@@ -346,3 +377,10 @@ int launch_gemm_decode(const void* A, const void* B, const void* SFA, const void
 }
 
 }  // namespace b200q
+
+extern "C" int b200q_debug_read_decode_trace(unsigned long long* out, int n) {
+  if (n > 16) n = 16;
+  B200Q_CUDA(cudaDeviceSynchronize());
+  B200Q_CUDA(cudaMemcpyFromSymbol(out, b200q::g_decode_trace, sizeof(unsigned long long) * n));
+  return 0;
+}

@@ -1167,6 +1167,15 @@ int make_operand_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t ro
   return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, what);
 }
 
+// [rows, row_bytes] uint8 operand viewed as {128 bytes, rows, k-tiles}: ONE box = {128 B, box_rows, all k-tiles} lands in shared
+// memory as consecutive 128B-swizzled [box_rows x 128 B] slabs, one per k-tile (gemm_decode.cu: the resident activations)
+int make_operand_ktile_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t row_bytes, int box_rows, const char* what) {
+  cuuint64_t dims[3] = {(cuuint64_t)BK_BYTES, (cuuint64_t)rows, (cuuint64_t)(row_bytes / BK_BYTES)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_bytes, (cuuint64_t)BK_BYTES};
+  cuuint32_t box[3] = {(cuuint32_t)BK_BYTES, (cuuint32_t)box_rows, (cuuint32_t)(row_bytes / BK_BYTES)};
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, what);
+}
+
 // blocked scale buffer as a 3-D tensor {128 x u32 (one 512-B block), col_blocks, row_blocks};
 // box = {128, kblocks, rblocks}; out-of-range blocks read as zero (scale 2^-127 / 0.0: never NaN)
 int make_sf_tmap(CUtensorMap* tm, const void* ptr, int64_t row_blocks, int64_t col_blocks, int box_kb,

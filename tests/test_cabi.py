@@ -165,3 +165,20 @@ def test_environment_switches_are_cached_until_reload(lib_path, monkeypatch):
     assert after in (1, 2)
 
 
+
+
+def test_compiled_op_layer_shares_the_c_plus_plus_runtime_with_torch(lib_path):
+    """lib/b200q_torch_ops.so throws C++ exceptions into libtorch (argument checks).  Built with a g++ whose libstdc++.so is
+    missing it silently links libstdc++.a, carries its own __cxa_throw, and a failed check then segfaults on the GPU box
+    instead of raising RuntimeError (observed in round 2).  The build verifies this; so does this test."""
+    import subprocess
+    ops = os.path.join(os.path.dirname(lib_path), "b200q_torch_ops.so")
+    assert os.path.exists(ops)
+    syms = subprocess.run(["nm", "-D", ops], capture_output=True, text=True).stdout
+    lines = [l.split() for l in syms.splitlines() if "__cxa_throw" in l or "__gxx_personality_v0" in l]
+    assert lines and all(l[0] == "U" for l in lines), lines
+    import torch
+    import qutlass_b200 as Q
+    assert Q._COMPILED_OPS
+    with pytest.raises(RuntimeError):          # CPU tensors: the dispatcher (not our code) rejects them -- still an exception, not a crash
+        torch.ops._qutlass_C.matmul_mxf4_bf16_tn(*[torch.zeros(4, 16, dtype=torch.uint8)] * 4, torch.ones(1))
