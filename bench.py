@@ -422,6 +422,13 @@ def main():
                 "frac": (M * K * (2 + 0.5 + 1.0 / group)) / (ms_quant * 1e-3) / 1e9 / pk["hbm_gbs"],
             },
         }
+        # measured with tools/fp4_peak_probe.py on a B200 of this pool (profiles/r02_fp4_peak.md): FP4 MMAs on operands resident
+        # in shared memory, double-buffered accumulators, nothing loaded or stored -- the ceiling of ANY FP4 kernel under the
+        # part's 1 kW power limit with realistic (random) operand data.  A recorded figure, like `traffic`.
+        line["roofline"]["fp4_mma_only_ceiling"] = {"burst": 7262.0, "sustained": 6374.0, "unit": "TFLOP/s",
+                                                    "source": "profiles/r02_fp4_peak.md", "frac_burst": ach / 7262.0}
+        if sus is not None:
+            line["roofline"]["fp4_mma_only_ceiling"]["frac_sustained"] = line["sustained"]["gemm_only_tflops_per_gpu"] / 6374.0
         if sus is not None:
             ach_s = line["sustained"]["gemm_only_tflops_per_gpu"]
             line["roofline"]["achieved_sustained"] = ach_s

@@ -87,6 +87,12 @@ void b200q_reload_env(void);
 /* 1 if this library was built with -DB200Q_PROFILING (B200Q_GEMM_DEBUG_FLAGS honoured: timing-only switches that skip
  * loads / copies / stores and therefore produce WRONG results), 0 for the product build (the variable is ignored). */
 int b200q_profiling_build(void);
+/* Host-only: a counter that changes every time one of the quantise entry points of this library is asked to WRITE the
+ * row-major scale buffer at `sf_rowmajor` (spuriously also when an unrelated buffer hashing to the same slot is written).
+ * The Python surface remembers it next to the blocked copy a quantiser wrote and refuses to hand that copy out from
+ * to_blocked() after ANY later writer went through this library -- including the raw torch.ops._qutlass_C ops, which write
+ * OUT_sf through its data pointer without touching torch's version counter. */
+unsigned b200q_sf_write_generation(const void* sf_rowmajor);
 /* Host-only: hits / misses of the calling thread's tensor-map cache since it was last read (then reset). */
 int b200q_debug_tmap_cache_stats(unsigned long long* hits, unsigned long long* misses);
 

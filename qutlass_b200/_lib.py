@@ -21,6 +21,7 @@ SIGNATURES = {
     "b200q_last_error": (ctypes.c_char_p, []),
     "b200q_reload_env": (None, []),
     "b200q_profiling_build": (_i32, []),
+    "b200q_sf_write_generation": (ctypes.c_uint, [_vp]),
     "b200q_debug_tmap_cache_stats": (_i32, [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]),
     "b200q_quantize_mx": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "b200q_quantize_nv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),

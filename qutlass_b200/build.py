@@ -1,7 +1,8 @@
 """Build libb200q.so (hand-written sm_100a CUDA behind the C-ABI in include/b200q.h).
 
 In-tree build: the .so lands in qutlass_b200/lib/ so it travels with the repo snapshot to
-the GPU box.  nvcc cross-compiles without a GPU.  Usage: python -m qutlass_b200.build [--force] [--profiling]
+the GPU box.  nvcc cross-compiles without a GPU.  Usage: python qutlass_b200/build.py [--force] [--profiling]
+(run it as a script: `python -m qutlass_b200.build` imports the package first, which needs an up-to-date library)
 
 --profiling builds a SECOND library, lib/libb200q_prof.so, with -DB200Q_PROFILING: the only build in which
 B200Q_GEMM_DEBUG_FLAGS (timing-only switches that skip loads / copies / stores -> wrong results) is honoured.

@@ -41,6 +41,7 @@ static void load_env() {
   e.verbose = getenv("B200Q_GEMM_VERBOSE") != nullptr;
   e.gemm_skew = env_int("B200Q_GEMM_SKEW", -1);
   e.no_tmap_cache = env_int("B200Q_NO_TMAP_CACHE", 0) == 1;
+  e.no_fuse_decode = env_int("B200Q_NO_FUSE_DECODE", 0) == 1;
   g_env = e;
   g_env_ready.store(1, std::memory_order_release);
 }
@@ -100,8 +101,20 @@ int num_sms() {
   return g_sm_count[dev] > 0 ? g_sm_count[dev] : 148;
 }
 
+// Write generations of row-major scale buffers (b200q.h: b200q_sf_write_generation): a small table of counters indexed by a
+// hash of the pointer.  Two buffers sharing a slot only cause a spurious "changed" answer, never a missed one.
+static std::atomic<unsigned> g_sf_gen[4096];
+static inline unsigned sf_slot(const void* p) {
+  return (unsigned)((((uintptr_t)p >> 4) * 0x9E3779B97F4A7C15ull) >> 52);
+}
+void note_sf_write(const void* sf_rowmajor) {
+  if (sf_rowmajor) g_sf_gen[sf_slot(sf_rowmajor)].fetch_add(1u, std::memory_order_relaxed);
+}
+unsigned sf_write_generation(const void* sf_rowmajor) { return g_sf_gen[sf_slot(sf_rowmajor)].load(std::memory_order_relaxed); }
+
 }  // namespace b200q
 
+extern "C" unsigned b200q_sf_write_generation(const void* sf_rowmajor) { return b200q::sf_write_generation(sf_rowmajor); }
 extern "C" int b200q_abi_version(void) { return 1; }
 extern "C" void b200q_reload_env(void) { b200q::load_env(); }
 extern "C" int b200q_profiling_build(void) {

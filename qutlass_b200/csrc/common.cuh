@@ -17,6 +17,7 @@ void set_error(const char* fmt, ...);
 int check_device_sm100();          // 0 or B200Q_EUNSUPPORTED (cached per device)
 int num_sms();                     // SM count of the current device (cached)
 int current_device();              // ordinal of the current device, 0 on error
+void note_sf_write(const void* sf_rowmajor);   // every quantise call that writes a row-major scale buffer (b200q_sf_write_generation)
 
 // Environment switches, read ONCE (first use) instead of getenv() on every launch; b200q_reload_env() re-reads them
 // (tests and probe tools that flip a switch inside one process call it).  Switches that change RESULTS (the GEMM's
@@ -34,6 +35,7 @@ struct Env {
   int verbose;       // B200Q_GEMM_VERBOSE
   int gemm_skew;     // B200Q_GEMM_SKEW: -1 unset (planner decides), else forced k-tile skew of the split accumulator
   int no_tmap_cache; // B200Q_NO_TMAP_CACHE=1
+  int no_fuse_decode;// B200Q_NO_FUSE_DECODE=1: b200q_linear_fp4 never uses the single-launch decode kernel
 };
 const Env& env();
 

@@ -19,6 +19,7 @@
 // (tests/test_gpu_parity.py::test_decode_kernel_*).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "quantize_tile.cuh"
 #include "tmap.cuh"
 
 #include <cuda.h>
@@ -27,6 +28,9 @@ namespace b200q {
 using namespace ptx;
 
 constexpr int kDecThreads = 192;          // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue (one per TMEM lane quarter)
+constexpr int kDecQuantWarps = 8;         // fused variant: warps 2-9 rotate + quantise the activations (2-5 then turn epilogue)
+constexpr int kDecFuseThreads = 64 + 32 * kDecQuantWarps;
+constexpr int kDecMaxGroups = 16;         // fused: groups of 4 k-tiles (1024 elements of a row = one quantiser warp-tile)
 constexpr int kDecMaxStages = 12;
 constexpr int kDecSmemBudget = 227 * 1024;
 constexpr int kDecEarlyStages = 4;        // static weights: stages whose REAL loads are issued before the grid dependency
@@ -55,6 +59,17 @@ __device__ __forceinline__ void dtrace(int flags, int ev, bool wall = false) {
   }
 }
 
+// Fused variant (ONE launch for the decode step): every CTA rotates + quantises ALL of x itself --
+// M <= 32 rows are <= 256 K elements, ~30 k warp instructions spread over 8 otherwise idle warps -- straight into the
+// shared-memory tiles / scale blocks the tensor core reads, in groups of 4 k-tiles (= one 1024-element warp-tile per row)
+// that the MMA warp picks up one by one, so the rotation of groups 1.. hides under the weight stream.  Same code
+// (tile_stage_unpack / tile_rotate_hadamard / chunk_quantise) as the standalone butterfly quantiser => same bytes.
+// CTA 0 also writes the codes and scales to global memory (the outputs of b200q_linear_fp4).
+struct DecodeFuse {
+  QuantParams q;
+  int had, method;
+};
+
 template <bool kNV>
 struct DecodeCfg {
   static constexpr int SFKB = kNV ? 4 : 2;                 // 512-B scale blocks per 128 rows per k-tile
@@ -65,11 +80,83 @@ struct DecodeCfg {
   static_assert(STAGE_BYTES % 1024 == 0, "stage alignment");
 };
 
-template <bool kNV, int NP>
-__global__ void __launch_bounds__(kDecThreads, 1)
+// one quantiser warp's share: warp-tiles t = g * M + m (group-major, so group 0 -- k-tiles 0..3 of every row -- completes first)
+template <int HAD, bool NV, int METHOD, int NP>
+__device__ __forceinline__ void decode_quantise(const DecodeFuse& f, uint4* stage, int qw, int lane, uint32_t x_base, uint32_t xsf_base,
+                                                uint32_t xq_bar0, int M, int k_groups, bool write_global) {
+  const QuantParams& p = f.q;
+  const float c_scale = __bfloat162float(p.rot[0]);
+  float gs = 1.f, gs_rcp = 1.f;
+  if constexpr (NV) {
+    gs = *p.gs;
+    gs_rcp = rcp_approx_ftz(gs);
+  }
+  const int n_tiles = k_groups * M;
+  auto load = [&](int t, uint4 (&dst)[4]) {
+    const int g = t / M, m = t - g * M;
+    const int64_t gt = (int64_t)m * k_groups + g;           // warp-tile index in x (row-major [M, K], 1024 elements each)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = (t < n_tiles) ? __ldg(p.x + (gt * 128 + i * 32 + lane)) : make_uint4(0, 0, 0, 0);
+  };
+  uint4 nxt[4];
+  load(qw, nxt);
+  for (int t = qw; t < n_tiles; t += kDecQuantWarps) {
+    uint4 ld[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld[i] = nxt[i];
+    load(t + kDecQuantWarps, nxt);
+    float v[32];
+    tile_stage_unpack(ld, stage, lane, v);
+    tile_rotate_hadamard<HAD>(v, c_scale);
+    uint32_t out[4], sf_bytes, mask_word;
+    chunk_quantise<NV, METHOD, false>(v, gs, gs_rcp, out, sf_bytes, mask_word, p.nv_sm100_codes != 0);
+    const int g = t / M, m = t - g * M;
+    {
+      // codes: lane L owns 32 elements = one 16-byte piece of row m; k-tile g*4 + L/8, piece L%8, 128B swizzle (piece ^= row % 8)
+      const int kt = g * 4 + (lane >> 3), j = lane & 7;
+      const uint32_t addr = x_base + (uint32_t)kt * (NP * 128u) + (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u +
+                            (uint32_t)((j ^ (m & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3]) : "memory");
+      // scales: blocked layout of the (single) 128-row block: block c/4, byte (m % 32) * 16 + (m / 32) * 4 + c % 4
+      const int c = NV ? 2 * (g * 32 + lane) : (g * 32 + lane);
+      const uint32_t saddr = xsf_base + (uint32_t)(c >> 2) * 512u + (uint32_t)(m & 31) * 16u + (uint32_t)(m >> 5) * 4u + (uint32_t)(c & 3);
+      if constexpr (NV) asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((uint16_t)sf_bytes) : "memory");
+      else asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(sf_bytes) : "memory");
+    }
+    fence_proxy_async_smem();          // generic-proxy writes -> the tensor core's (async proxy) reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(xq_bar0 + 8u * (uint32_t)g);
+    if (write_global) chunk_store<NV, false>(p, ((int64_t)m * k_groups + g) * 32 + lane, out, sf_bytes, 0u);
+  }
+}
+
+template <bool NV, int NP>
+__device__ __forceinline__ void decode_quantise_role(const DecodeFuse& f, uint4* stage, int qw, int lane, uint32_t x_base,
+                                                     uint32_t xsf_base, uint32_t xq_bar0, int M, int k_groups, bool wg) {
+#define B200Q_DQ(H)                                                                                                                     \
+  case H:                                                                                                                                \
+    if (f.method == B200Q_METHOD_QUEST) decode_quantise<H, NV, B200Q_METHOD_QUEST, NP>(f, stage, qw, lane, x_base, xsf_base, xq_bar0, M, k_groups, wg); \
+    else decode_quantise<H, NV, B200Q_METHOD_ABSMAX, NP>(f, stage, qw, lane, x_base, xsf_base, xq_bar0, M, k_groups, wg);                \
+    break;
+  switch (f.had) {
+    B200Q_DQ(128)
+    B200Q_DQ(64)
+    B200Q_DQ(32)
+    case 16:
+      if constexpr (NV) {
+        if (f.method == B200Q_METHOD_QUEST) decode_quantise<16, NV, B200Q_METHOD_QUEST, NP>(f, stage, qw, lane, x_base, xsf_base, xq_bar0, M, k_groups, wg);
+        else decode_quantise<16, NV, B200Q_METHOD_ABSMAX, NP>(f, stage, qw, lane, x_base, xsf_base, xq_bar0, M, k_groups, wg);
+      }
+      break;
+  }
+#undef B200Q_DQ
+}
+
+template <bool kNV, int NP, bool kFuse>
+__global__ void __launch_bounds__(kFuse ? kDecFuseThreads : kDecThreads, 1)
 gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                        const __grid_constant__ CUtensorMap tmap_sfx, const __grid_constant__ CUtensorMap tmap_sfw,
-                       const DecodeParams p) {
+                       const DecodeParams p, const DecodeFuse fq) {
   using Cfg = DecodeCfg<kNV>;
   constexpr int SFKB = Cfg::SFKB;
   constexpr int ACC = 2;
@@ -83,7 +170,8 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   const uint32_t xsf_bytes = (uint32_t)p.k_tiles * SFKB * 512u;            // resident activation scales (blocked layout)
   const uint32_t x_base = smem_base;
   const uint32_t xsf_base = x_base + x_bytes;
-  const uint32_t ring_base = (xsf_base + xsf_bytes + 1023u) & ~1023u;
+  const uint32_t qstage_bytes = kFuse ? kDecQuantWarps * 2048u : 0u;     // fused: 2 KB of swizzled staging per quantiser warp
+  const uint32_t ring_base = (xsf_base + xsf_bytes + qstage_bytes + 1023u) & ~1023u;
   const uint32_t bar_base = ring_base + (uint32_t)STAGES * Cfg::STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kDecMaxStages + s); };
@@ -92,6 +180,8 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kDecMaxStages + 1 + ACC + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kDecMaxStages + 1 + 2 * ACC);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * kDecMaxStages + 1 + 2 * ACC));
+  const uint32_t xq_bar0 = bar_base + 8u * (2 * kDecMaxStages + 2 + 2 * ACC);     // fused: one barrier per group of 4 k-tiles
+  const int k_groups = p.k_tiles >> 2;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -100,13 +190,18 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_w);
     prefetch_tensormap(&tmap_sfw);
-    prefetch_tensormap(&tmap_x);
-    prefetch_tensormap(&tmap_sfx);
+    if constexpr (!kFuse) {
+      prefetch_tensormap(&tmap_x);
+      prefetch_tensormap(&tmap_sfx);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(x_bar, 1);
+    if constexpr (kFuse) {
+      for (int g = 0; g < k_groups; ++g) mbar_init(xq_bar0 + 8u * g, (uint32_t)p.M);   // one arrival per row's warp-tile
+    }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 4);            // the four epilogue warps
@@ -159,13 +254,6 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     }
     pdl_wait();
     if (lane == 0) dtrace(p.flags, 3);
-    // the activations (written by the kernel in front of us) and their scales: resident for the whole kernel
-    // (warp-uniform loops with the elected lane issuing inside: no divergent-branch waterfall around the TMA ops)
-    if (elected) {
-      mbar_arrive_expect_tx(x_bar, x_bytes + xsf_bytes);
-      tma_load_3d<1>(xsf_base, &tmap_sfx, x_bar, 0, 0, 0);      // all scale blocks of the (one) 128-row block
-      tma_load_3d<1>(x_base, &tmap_x, x_bar, 0, 0, 0);          // all k-tiles: {128 B, NP rows, k_tiles} in ONE box
-    }
     int tile = blockIdx.x, kt = 0;
     for (int g = 0; g < pre; ++g) {
       if (elected && g >= early) load_w(g, tile, kt);
@@ -199,18 +287,19 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const uint32_t x_lo0 = ((x_base & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t xsf_lo0 = (xsf_base & 0x3FFFFu) >> 4;
     const uint32_t ring_lo0 = ((ring_base & 0x3FFFFu) >> 4);
-    // activation scales -> TMEM, once
-    mbar_wait(x_bar, 0, 2);
-    tc_fence_after();
-    if (lane == 0) dtrace(p.flags, 4);
-    {
+    if constexpr (!kFuse) {
+      // activation scales -> TMEM, once
+      mbar_wait(x_bar, 0, 2);
+      tc_fence_after();
+      if (lane == 0) dtrace(p.flags, 4);
       const int nblk = p.k_tiles * SFKB;
       for (int c = 0; c < nblk; ++c) {
         if (elected) tmem_cp_32x128b_warpx4<1>(tmem_xsf + (uint32_t)c * 4u, mk(xsf_lo0 + (uint32_t)c * 32u, kDescHiSF));
       }
+      __syncwarp();
+      if (lane == 0) dtrace(p.flags, 5);
     }
-    __syncwarp();
-    if (lane == 0) dtrace(p.flags, 5);
+    bool first_tile = true;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -224,7 +313,20 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)acc * NP;
       for (int kt = 0; kt < p.k_tiles; ++kt) {
-        mbar_wait(full_bar(stage), phase, 5);
+        if constexpr (kFuse) {
+          if (first_tile && (kt & 3) == 0) {
+            // fused: group kt/4 of the activations (4 k-tiles of every row) has been quantised into shared memory by the
+            // quantiser warps of THIS CTA -> its scale blocks go to TMEM now
+            mbar_wait(xq_bar0 + 8u * (uint32_t)(kt >> 2), 0, 7);
+            tc_fence_after();
+            if (kt == 0 && lane == 0) dtrace(p.flags, 4);
+            for (int c = kt * SFKB; c < (kt + 4) * SFKB; ++c) {
+              if (elected) tmem_cp_32x128b_warpx4<1>(tmem_xsf + (uint32_t)c * 4u, mk(xsf_lo0 + (uint32_t)c * 32u, kDescHiSF));
+            }
+            __syncwarp();
+          }
+        }
+        mbar_wait_spin(full_bar(stage), phase);       // (a lost arrival is caught by the timed waits of the producer / epilogue)
         tc_fence_after();
         const uint32_t w_lo = (ring_lo0 + (uint32_t)stage * (Cfg::STAGE_BYTES >> 4)) | (1u << 16);
         const uint32_t wsf_lo = ring_lo0 + (uint32_t)stage * (Cfg::STAGE_BYTES >> 4) + (Cfg::W_BYTES >> 4);
@@ -249,6 +351,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       }
       if (elected) tc_commit<1>(tfull_bar(acc));
       __syncwarp();
+      first_tile = false;
       if (lane == 0) dtrace(p.flags, 7);
       if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
     }
@@ -257,7 +360,26 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    pdl_wait();                                   // D may still be read by the predecessor kernel
+    pdl_wait();                                   // x comes from the predecessor kernel; D may still be read by it
+    if constexpr (kFuse) {
+      // warps 2..9: rotate + quantise x into the resident tiles; CTA 0 also writes the outputs of the quantiser to global
+      const int qw = warp - 2;
+      uint4* qstage = reinterpret_cast<uint4*>(smem_gen + (xsf_base - smem_base) + xsf_bytes) + qw * 128;
+      if (blockIdx.x == 0) zero_fill_sf_padding(fq.q, (int64_t)threadIdx.x - 64, (int64_t)kDecQuantWarps * 32);
+      decode_quantise_role<kNV, NP>(fq, qstage, qw, lane, x_base, xsf_base, xq_bar0, p.M, k_groups, blockIdx.x == 0);
+      if (warp >= 6) goto done;                    // the four extra warps have no epilogue duty
+    }
+    if (!kFuse && warp == 2) {
+      // The activations and their scales, resident for the whole kernel: TWO TMA ops, issued by this otherwise idle warp the
+      // moment the grid dependency resolves -- the producer warp is busy issuing a ring of weight loads at that time, and
+      // behind those (measured, profiles/r02_decode_probe2_v1.jsonl) x landed 1.9 k cycles later than it had to.
+      if (elect_one()) {
+        mbar_arrive_expect_tx(x_bar, x_bytes + xsf_bytes);
+        tma_load_3d<1>(xsf_base, &tmap_sfx, x_bar, 0, 0, 0);      // all scale blocks of the (one) 128-row block
+        tma_load_3d<1>(x_base, &tmap_x, x_bar, 0, 0, 0);          // all k-tiles: {128 B, NP rows, k_tiles} in ONE box
+      }
+      __syncwarp();
+    }
     const float alpha = __ldg(p.alpha);
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase, 4);
@@ -272,14 +394,30 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       const int n = t * 128 + q * 32 + lane;
-      if (n < p.N) {
+      if ((p.ldd & 1) == 0) {
+        // rows in pairs: the even lane of a lane pair stores (n, n+1) of row m, the odd lane (n-1, n) of row m+1 -- one 4-byte
+        // store per lane and row pair, 64 contiguous bytes per warp and row
+        const bool odd = lane & 1;
+        const int n_pair = n & ~1;
+#pragma unroll
+        for (int m = 0; m < NP; m += 2) {
+          const uint32_t mine0 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(r[m]) * alpha));
+          const uint32_t mine1 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(r[m + 1]) * alpha));
+          const uint32_t send = odd ? mine0 : mine1;                       // what the partner's row needs from me
+          const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 1);
+          const uint32_t word = odd ? (got | (mine1 << 16)) : (mine0 | (got << 16));
+          const int row = m + (odd ? 1 : 0);
+          if (row < p.M && n_pair < p.N) {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(p.d) + (int64_t)row * p.ldd + n_pair;
+            if (n_pair + 1 < p.N) *reinterpret_cast<uint32_t*>(dst) = word;
+            else dst[0] = (uint16_t)(word & 0xffffu);
+          }
+        }
+      } else if (n < p.N) {
         uint16_t* dcol = reinterpret_cast<uint16_t*>(p.d) + n;
 #pragma unroll
         for (int m = 0; m < NP; ++m) {
-          if (m < p.M) {
-            const __nv_bfloat16 h = __float2bfloat16_rn(__uint_as_float(r[m]) * alpha);
-            dcol[(int64_t)m * p.ldd] = *reinterpret_cast<const uint16_t*>(&h);
-          }
+          if (m < p.M) dcol[(int64_t)m * p.ldd] = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(r[m]) * alpha));
         }
       }
       if (warp == 2 && lane == 0) dtrace(p.flags, 9);
@@ -287,6 +425,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     }
   }
 
+done:
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) { dtrace(p.flags, 10); dtrace(p.flags, 11, true); }
@@ -297,11 +436,11 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 }
 
 // ------------------------------------------------------------------ host side
-static int decode_stages(int M, int K, bool nv, int* np_out) {
+static int decode_stages(int M, int K, bool nv, int* np_out, bool fuse = false) {
   const int np = M <= 16 ? 16 : 32;
   const int k_tiles = K / 256;
   const int sfkb = nv ? 4 : 2;
-  const int64_t resident = (int64_t)k_tiles * np * 128 + (int64_t)k_tiles * sfkb * 512;
+  const int64_t resident = (int64_t)k_tiles * np * 128 + (int64_t)k_tiles * sfkb * 512 + (fuse ? kDecQuantWarps * 2048 : 0);
   const int stage = 128 * 128 + sfkb * 512;
   const int64_t room = (int64_t)kDecSmemBudget - 1024 /*alignment*/ - 1024 /*ring alignment*/ - 1024 /*barriers*/ - resident;
   int stages = (int)(room / stage);
@@ -321,36 +460,52 @@ bool decode_eligible(int M, int N, int K, int ldd, int kind) {
   return decode_stages(M, K, nv, nullptr) >= 4;
 }
 
-template <bool kNV, int NP>
+bool decode_fuse_eligible(int M, int N, int K, int had, int method, int kind) {
+  if (env().no_fuse_decode) return false;
+  if (!decode_eligible(M, N, K, N, kind)) return false;
+  if (!(method & B200Q_ROT_TRUSTED_HADAMARD)) return false;              // in-register butterflies only
+  const bool nv = kind == B200Q_KIND_NVF4;
+  if (!(had == 32 || had == 64 || had == 128 || (nv && had == 16))) return false;
+  if (K % 1024 != 0 || K / 1024 > kDecMaxGroups) return false;           // whole quantiser warp-tiles per row, one barrier per group
+  return decode_stages(M, K, nv, nullptr, true) >= 4;
+}
+
+template <bool kNV, int NP, bool kFuse = false>
 static int launch_decode_t(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D, int M, int N,
-                           int K, int ldd, bool static_w, cudaStream_t stream) {
+                           int K, int ldd, bool static_w, cudaStream_t stream, const DecodeFuse* fuse = nullptr) {
   using Cfg = DecodeCfg<kNV>;
-  auto kern = gemm_fp4_decode_kernel<kNV, NP>;
+  auto kern = gemm_fp4_decode_kernel<kNV, NP, kFuse>;
   DecodeParams p;
   p.alpha = alpha;
   p.d = (__nv_bfloat16*)D;
   p.M = M; p.N = N; p.K = K; p.ldd = ldd;
   p.k_tiles = K / 256;
   p.tiles = (int)ceil_div(N, 128);
-  p.stages = decode_stages(M, K, kNV, nullptr);
+  p.stages = decode_stages(M, K, kNV, nullptr, kFuse);
   p.static_weights = static_w ? 1 : 0;
   p.flags = env().gemm_flags;
-  const int smem = 1024 + p.k_tiles * NP * 128 + p.k_tiles * Cfg::SFKB * 512 + 1024 + p.stages * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
+  const int smem = 1024 + p.k_tiles * NP * 128 + p.k_tiles * Cfg::SFKB * 512 + (kFuse ? kDecQuantWarps * 2048 : 0) + 1024 +
+                   p.stages * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
   static std::atomic<unsigned long long> smem_attr_done{0};
   if (int rc_attr = ensure_dynamic_smem(kern, kDecSmemBudget, smem_attr_done)) return rc_attr;
   const int group = kNV ? 16 : 32;
   const int64_t sf_col_blocks = ceil_div(ceil_div(K, group), 4);
   CUtensorMap tx, tw, tsx, tsw;
   int rc;
-  if ((rc = make_operand_ktile_tmap(&tx, A, M, K / 2, NP, "x (decode)"))) return rc;
   if ((rc = make_operand_tmap(&tw, B, N, K / 2, 128, "W (decode)"))) return rc;
-  if ((rc = make_sf_tmap(&tsx, SFA, ceil_div(M, 128), sf_col_blocks, (int)sf_col_blocks, 1, "SFx (decode)"))) return rc;
   if ((rc = make_sf_tmap(&tsw, SFB, ceil_div(N, 128), sf_col_blocks, Cfg::SFKB, 1, "SFW (decode)"))) return rc;
+  if constexpr (kFuse) {
+    tx = tw;        // the fused kernel quantises x itself: the activation maps are unused
+    tsx = tsw;
+  } else {
+    if ((rc = make_operand_ktile_tmap(&tx, A, M, K / 2, NP, "x (decode)"))) return rc;
+    if ((rc = make_sf_tmap(&tsx, SFA, ceil_div(M, 128), sf_col_blocks, (int)sf_col_blocks, 1, "SFx (decode)"))) return rc;
+  }
   cudaLaunchConfig_t cfg = {};
   int ctas = num_sms();
   if (ctas > p.tiles) ctas = p.tiles;
   cfg.gridDim = dim3((unsigned)ctas);
-  cfg.blockDim = dim3(kDecThreads);
+  cfg.blockDim = dim3(kFuse ? kDecFuseThreads : kDecThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[1];
@@ -358,8 +513,25 @@ static int launch_decode_t(const void* A, const void* B, const void* SFA, const 
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = env().no_pdl == 1 ? 0 : 1;
-  B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, tsx, tsw, p));
+  DecodeFuse fz = {};
+  if (fuse) fz = *fuse;
+  B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, tsx, tsw, p, fz));
   return 0;
+}
+
+// the whole decode step in ONE launch: q describes the quantiser's inputs / outputs (fill_params), had / method as in b200q.h
+int launch_gemm_decode_fused(const QuantParams& q, int had, int method, const void* B, const void* SFB, const float* alpha, void* D,
+                             int M, int N, int K, int kind, cudaStream_t stream) {
+  DecodeFuse f;
+  f.q = q;
+  f.had = had;
+  f.method = method;
+  const bool nv = kind == B200Q_KIND_NVF4;
+  // b200q_linear_fp4 takes pre-quantised weights by contract: static
+  if (M <= 16) return nv ? launch_decode_t<true, 16, true>(nullptr, B, nullptr, SFB, alpha, D, M, N, K, N, true, stream, &f)
+                         : launch_decode_t<false, 16, true>(nullptr, B, nullptr, SFB, alpha, D, M, N, K, N, true, stream, &f);
+  return nv ? launch_decode_t<true, 32, true>(nullptr, B, nullptr, SFB, alpha, D, M, N, K, N, true, stream, &f)
+            : launch_decode_t<false, 32, true>(nullptr, B, nullptr, SFB, alpha, D, M, N, K, N, true, stream, &f);
 }
 
 int launch_gemm_decode(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D, int M, int N,

@@ -1539,6 +1539,7 @@ extern "C" int64_t b200q_linear_fp4_workspace_bytes(int M) {
 
 extern "C" int b200q_linear_fp4_launches(int M, int N, int K, int had, int method, int kind) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (decode_fuse_eligible(M, N, K, had, method, kind)) return 1;
   if (fusable(M, N, K, had, method, kind)) return 1;
   return 1 + b200q_gemm_fp4_launches(M, N, K, kind);
 }
@@ -1553,6 +1554,22 @@ extern "C" int b200q_linear_fp4(const void* x_bf16, const void* rot_bf16, void* 
   B200Q_REQUIRE(x_sf_blocked, "x_sf_blocked is required (the GEMM reads the blocked scales)");
   B200Q_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive (got %d, %d, %d)", M, N, K);
   const bool nv = kind == B200Q_KIND_NVF4;
+  if (decode_fuse_eligible(M, N, K, had, method, kind)) {
+    // decode (M <= 32): ONE launch -- every CTA of the weight-streaming kernel quantises the activations itself (gemm_decode.cu)
+    B200Q_REQUIRE(Wq && Wsf_blocked && alpha_dev && D_bf16, "null pointer argument");
+    const int mth = method & ~(B200Q_ROT_TRUSTED_HADAMARD | B200Q_ROT_GENERIC | B200Q_NV_SM100_CODES | B200Q_NV_ORACLE_CODES);
+    B200Q_REQUIRE(mth == B200Q_METHOD_QUEST || mth == B200Q_METHOD_ABSMAX, "invalid method %d, must be quest (0) or abs_max (1)", mth);
+    B200Q_REQUIRE(!nv || global_scale_dev, "global_scale must be a device pointer to one float");
+    B200Q_REQUIRE((((uintptr_t)Wq | (uintptr_t)Wsf_blocked | (uintptr_t)D_bf16) & 15) == 0, "Wq, Wsf and D must be 16-byte aligned");
+    QuantParams q;
+    rc = fill_params(q, x_bf16, rot_bf16, xq_e2m1, x_sf_rowmajor, x_sf_blocked, (int64_t)M * K, K, had, nv ? 16 : 32);
+    if (rc) return rc;
+    note_sf_write(x_sf_rowmajor);
+    q.gs = global_scale_dev;
+    q.trust_hadamard = 1;
+    q.nv_sm100_codes = (nv && had == 128 && mth == B200Q_METHOD_ABSMAX && !(method & B200Q_NV_ORACLE_CODES)) ? 1 : 0;
+    return launch_gemm_decode_fused(q, had, mth, Wq, Wsf_blocked, alpha_dev, D_bf16, M, N, K, kind, (cudaStream_t)stream);
+  }
   if (!ws || !fusable(M, N, K, had, method, kind)) {
     // two launches: the standalone quantiser, then the GEMM (programmatic dependent launch overlaps its prologue)
     rc = nv ? b200q_quantize_nv(x_bf16, rot_bf16, xq_e2m1, x_sf_rowmajor, x_sf_blocked, global_scale_dev, (int64_t)M * K, K,
@@ -1574,6 +1591,7 @@ extern "C" int b200q_linear_fp4(const void* x_bf16, const void* rot_bf16, void* 
   FuseParams fp = {};
   rc = fill_params(fp.q, x_bf16, rot_bf16, xq_e2m1, x_sf_rowmajor, x_sf_blocked, (int64_t)M * K, K, had, nv ? 16 : 32);
   if (rc) return rc;
+  note_sf_write(x_sf_rowmajor);
   fp.q.gs = global_scale_dev;
   fp.q.trust_hadamard = 1;
   fp.q.nv_sm100_codes = (nv && had == 128 && m == B200Q_METHOD_ABSMAX && !(method & B200Q_NV_ORACLE_CODES)) ? 1 : 0;

@@ -220,12 +220,23 @@ __device__ __forceinline__ void chunk_quantise(float* v, float gs, float gs_rcp,
     }
 }
 
-// chunk_quantise + all stores (codes, row-major and blocked scales, clip mask) of one chunk (= flat element index / 32).
+// all global stores (codes, row-major and blocked scales, clip mask) of one quantised chunk (= flat element index / 32)
+template <bool NV, bool MASK>
+__device__ __forceinline__ void chunk_store(const QuantParams& p, int64_t chunk, const uint32_t (&out)[4], uint32_t sf_bytes,
+                                            uint32_t mask_word);
+
+// chunk_quantise + chunk_store
 template <bool NV, int METHOD, bool MASK>
 __device__ __forceinline__ void chunk_quantise_store(const QuantParams& p, float* v, int64_t chunk, float gs, float gs_rcp) {
     uint32_t out[4];
     uint32_t mask_word, sf_bytes;
     chunk_quantise<NV, METHOD, MASK>(v, gs, gs_rcp, out, sf_bytes, mask_word, p.nv_sm100_codes != 0);
+    chunk_store<NV, MASK>(p, chunk, out, sf_bytes, mask_word);
+}
+
+template <bool NV, bool MASK>
+__device__ __forceinline__ void chunk_store(const QuantParams& p, int64_t chunk, const uint32_t (&out)[4], uint32_t sf_bytes,
+                                            uint32_t mask_word) {
     if (chunk < p.n_chunks) {
       p.q[chunk] = make_uint4(out[0], out[1], out[2], out[3]);
       if constexpr (MASK) {

@@ -19,4 +19,10 @@ bool decode_eligible(int M, int N, int K, int ldd, int kind);
 int launch_gemm_decode(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D, int M, int N,
                        int K, int ldd, int kind, bool static_w, cudaStream_t stream);
 
+// the decode step in one launch (activations rotated + quantised inside every CTA of the decode kernel)
+struct QuantParams;
+bool decode_fuse_eligible(int M, int N, int K, int had, int method, int kind);
+int launch_gemm_decode_fused(const QuantParams& q, int had, int method, const void* B, const void* SFB, const float* alpha, void* D,
+                             int M, int N, int K, int kind, cudaStream_t stream);
+
 }  // namespace b200q

@@ -43,7 +43,10 @@ def _attach_blocked(sf_rowmajor: torch.Tensor, blocked: torch.Tensor) -> None:
     track versions -- for those nothing is attached and to_blocked runs its kernel."""
     ver = _version_of(sf_rowmajor)
     if ver >= 0:
-        setattr(sf_rowmajor, _BLOCKED_ATTR, (blocked, ver, sf_rowmajor.data_ptr()))
+        ptr = sf_rowmajor.data_ptr()
+        # + the library's write generation of that buffer: a later quantise call that writes it through the C-ABI (e.g. the
+        # raw torch.ops._qutlass_C ops, which do not bump torch's version counter) makes the attached copy stale
+        setattr(sf_rowmajor, _BLOCKED_ATTR, (blocked, ver, ptr, _lib.load().b200q_sf_write_generation(ptr)))
 
 
 def _detach_blocked(sf_rowmajor: torch.Tensor) -> None:
@@ -69,7 +72,8 @@ def to_blocked(input_matrix: torch.Tensor, use_triton_kernel: bool = False) -> t
     cached = getattr(input_matrix, _BLOCKED_ATTR, None)
     if cached is not None:
         _detach_blocked(input_matrix)
-        if cached[1] >= 0 and cached[1] == _version_of(input_matrix) and cached[2] == input_matrix.data_ptr():
+        if (cached[1] >= 0 and cached[1] == _version_of(input_matrix) and cached[2] == input_matrix.data_ptr()
+                and cached[3] == _lib.load().b200q_sf_write_generation(cached[2])):
             return cached[0]
     assert input_matrix.dim() == 2, "to_blocked expects a 2-D scale matrix"
     assert input_matrix.element_size() == 1, "Expected element size to be 1 byte (8 bits)"

@@ -19,7 +19,7 @@ def _declared():
     src = open(os.path.join(ROOT, "include", "b200q.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     decls = {}
-    for m in re.finditer(r"\b(int|int64_t|const char\*|void)\s+(b200q_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(int|int64_t|const char\*|void|unsigned)\s+(b200q_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(3).strip()
         n = 0 if args in ("void", "") else len([a for a in args.split(",") if a.strip()])
         decls[m.group(2)] = n

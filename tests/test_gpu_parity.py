@@ -978,3 +978,63 @@ def test_decode_path_in_a_cuda_graph_with_quantiser_in_front(fmt):
         want = mm(xq2, wq, Q.to_blocked(xsf2), wblk, al)
         torch.cuda.synchronize()
         assert torch.equal(out, want), it
+
+
+@pytest.mark.parametrize("fmt,had,method", [("mx", 128, "abs_max"), ("mx", 64, "quest"), ("mx", 32, "abs_max"),
+                                            ("nv", 16, "abs_max"), ("nv", 128, "quest"), ("nv", 128, "abs_max"), ("nv", 64, "abs_max")])
+@pytest.mark.parametrize("shape", [(16, 1536, 2048), (1, 512, 1024), (32, 640, 4096), (7, 1000, 1024), (16, 128 * 150, 1024)])
+def test_decode_step_in_one_launch_equals_two_calls(fmt, had, method, shape):
+    """b200q_linear_fp4 for M <= 32 is ONE launch -- every CTA of the weight-streaming kernel rotates
+    and quantises the activations itself -- and reproduces fusedQuantize* followed by matmul_* bit for bit: the bf16 output,
+    the codes, the row-major scales and the blocked copy (written by CTA 0)."""
+    m, n, k = shape
+    R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, had, method, fmt, seed=m + n + had)
+    lib = _lib.load()
+    meth = (0 if method == "quest" else 1) | Q.ROT_TRUSTED_HADAMARD
+    assert lib.b200q_linear_fp4_launches(m, n, k, had, meth, 0 if fmt == "mx" else 1) == 1
+    for _ in range(2):
+        out, xq2, xsf2 = Q.fused_linear_fp4(x, R, wq, wblk, al, global_scale=gs if fmt == "nv" else None, method=method, fmt=fmt)
+        torch.cuda.synchronize()
+        assert torch.equal(out, want), (out != want).float().mean().item()
+        assert torch.equal(xq2, xq)
+        rows, cols = m, k // (32 if fmt == "mx" else 16)
+        assert torch.equal(xsf2.view(torch.uint8)[:rows, :cols], xsf.view(torch.uint8)[:rows, :cols])
+        np.testing.assert_array_equal(H.u8_of(Q.to_blocked(xsf2)), H.blocked_sf(H.u8_of(xsf).reshape(-1, xsf.shape[-1])[:rows, :cols]))
+
+
+def test_decode_step_one_launch_in_a_cuda_graph_and_switch(b200q_env):
+    m, n, k = 8, 2048, 4096
+    R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, 128, "abs_max", "mx", seed=77)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            out, _, _ = Q.fused_linear_fp4(x, R, wq, wblk, al)
+    for _ in range(3):
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want)
+    b200q_env("B200Q_NO_FUSE_DECODE", "1")
+    assert _lib.load().b200q_linear_fp4_launches(m, n, k, 128, 1 | Q.ROT_TRUSTED_HADAMARD, 0) == 2
+    out2, _, _ = Q.fused_linear_fp4(x, R, wq, wblk, al)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, want)
+
+
+def test_rotation_hint_stops_synchronising_for_throw_away_rotations():
+    """a caller that builds a new rotation tensor for every call must not pay a device sync per call for
+    ever: after 64 inspected-and-collected tensors new ones get no hint (the kernel's own device-side check runs) -- and the
+    results stay identical."""
+    x = torch.randn(64, 1024, dtype=torch.bfloat16, device="cuda") * 25
+    base = H.bf16_tensor_from_f32(O.hadamard_matrix(64))
+    want = Q.fusedQuantizeMx(x, base, method="abs_max")
+    for i in range(80):
+        Rn = base.clone()
+        got = Q.fusedQuantizeMx(x, Rn, method="abs_max")
+        del Rn
+    torch.cuda.synchronize()
+    assert Q._ROT_DEAD[0] >= Q._ROT_MAX_DEAD
+    assert Q._rotation_hint(base.clone()) == 0
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1].view(torch.uint8)[:64], want[1].view(torch.uint8)[:64])

@@ -75,3 +75,35 @@ for M in (1, 16, 32):
             print(json.dumps(dict(M=M, static=bool(kf), weights_first_ring_only=bool(extra), timeline_cycles_from_entry=tl,
                                   ns_entry_to_exit=buf[11] - buf[1], mhz=round((buf[10] - t0) / max(buf[11] - buf[1], 1) * 1e3, 1))), flush=True)
     setenv(0)
+
+
+# ---- the whole decode step through the Python surface: two calls (quantise, GEMM with static weights) vs ONE launch
+sys.path.insert(0, ROOT)
+import qutlass_b200 as Q
+idx = torch.arange(128)
+bits = idx[:, None] & idx[None, :]
+par = torch.zeros_like(bits)
+while bits.any():
+    par ^= bits & 1
+    bits = bits >> 1
+R = ((1.0 - 2.0 * par.double()) * 128 ** -0.5).to(torch.bfloat16).to(dev)
+w = torch.randn(N, K, dtype=torch.bfloat16, device=dev)
+wq, wsf = Q.fusedQuantizeMx(w, R, method="abs_max")
+wblk = Q.to_blocked(wsf)
+for M in (1, 16, 32):
+    x = torch.randn(M, K, dtype=torch.bfloat16, device=dev)
+    Q.fusedQuantizeMx(x, R, method="abs_max")
+
+    def two(i):
+        q, s_ = Q.fusedQuantizeMx(x, R, method="abs_max")
+        return Q.matmul_mxf4_bf16_tn(q, wq, Q.to_blocked(s_), wblk, alpha, static_weights=True)
+
+    def two_safe(i):
+        q, s_ = Q.fusedQuantizeMx(x, R, method="abs_max")
+        return Q.matmul_mxf4_bf16_tn(q, wq, Q.to_blocked(s_), wblk, alpha)
+
+    def one(i):
+        return Q.fused_linear_fp4(x, R, wq, wblk, alpha)[0]
+
+    print(json.dumps(dict(M=M, step="quantise+GEMM, graph replay of 24, us per step",
+                          two_calls_static=graph_time(two, 24), two_calls_safe=graph_time(two_safe, 24), one_launch=graph_time(one, 24))), flush=True)
