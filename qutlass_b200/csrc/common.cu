@@ -41,7 +41,7 @@ static void load_env() {
   e.verbose = getenv("B200Q_GEMM_VERBOSE") != nullptr;
   e.gemm_skew = env_int("B200Q_GEMM_SKEW", -1);
   e.no_tmap_cache = env_int("B200Q_NO_TMAP_CACHE", 0) == 1;
-  e.no_fuse_decode = env_int("B200Q_NO_FUSE_DECODE", 0) == 1;
+  e.fuse_decode = env_int("B200Q_FUSE_DECODE", 0) == 1;
   g_env = e;
   g_env_ready.store(1, std::memory_order_release);
 }

@@ -35,7 +35,7 @@ struct Env {
   int verbose;       // B200Q_GEMM_VERBOSE
   int gemm_skew;     // B200Q_GEMM_SKEW: -1 unset (planner decides), else forced k-tile skew of the split accumulator
   int no_tmap_cache; // B200Q_NO_TMAP_CACHE=1
-  int no_fuse_decode;// B200Q_NO_FUSE_DECODE=1: b200q_linear_fp4 never uses the single-launch decode kernel
+  int fuse_decode;   // B200Q_FUSE_DECODE=1: b200q_linear_fp4 runs the decode step (M <= 32) as ONE launch (measured slower: opt-in)
 };
 const Env& env();
 

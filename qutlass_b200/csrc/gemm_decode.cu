@@ -59,12 +59,15 @@ __device__ __forceinline__ void dtrace(int flags, int ev, bool wall = false) {
   }
 }
 
-// Fused variant (ONE launch for the decode step): every CTA rotates + quantises ALL of x itself --
-// M <= 32 rows are <= 256 K elements, ~30 k warp instructions spread over 8 otherwise idle warps -- straight into the
-// shared-memory tiles / scale blocks the tensor core reads, in groups of 4 k-tiles (= one 1024-element warp-tile per row)
-// that the MMA warp picks up one by one, so the rotation of groups 1.. hides under the weight stream.  Same code
-// (tile_stage_unpack / tile_rotate_hadamard / chunk_quantise) as the standalone butterfly quantiser => same bytes.
-// CTA 0 also writes the codes and scales to global memory (the outputs of b200q_linear_fp4).
+// Fused variant (ONE launch for the decode step).  Every CTA needs ALL of the quantised activations, and
+// quantising them redundantly in every CTA was measured 1.2 - 2.5x SLOWER than two launches (8 warps per SM are latency-bound
+// at ~1.4 us per 1024-element warp-tile: profiles/r02_decode_probe2_v2.jsonl).  So the CTAs run in CLUSTERS OF 8 that share the
+// work: CTA r of a cluster rotates + quantises every 8th warp-tile and writes the codes / scale bytes straight into the
+// resident shared-memory tiles of ALL 8 CTAs (st.shared::cluster), then arrives (release.cluster) on each CTA's barrier of that
+// group of 4 k-tiles; the MMA warps pick the groups up one by one.  At M = 16, K = 4096 that is ONE warp-tile per warp.
+// Same code (tile_stage_unpack / tile_rotate_hadamard / chunk_quantise) as the standalone butterfly quantiser => same bytes.
+// Cluster 0 also writes the codes and scales to global memory (the outputs of b200q_linear_fp4).
+constexpr int kDecCluster = 8;
 struct DecodeFuse {
   QuantParams q;
   int had, method;
@@ -84,6 +87,8 @@ struct DecodeCfg {
 template <int HAD, bool NV, int METHOD, int NP>
 __device__ __forceinline__ void decode_quantise(const DecodeFuse& f, uint4* stage, int qw, int lane, uint32_t x_base, uint32_t xsf_base,
                                                 uint32_t xq_bar0, int M, int k_groups, bool write_global) {
+  // qw = (rank in cluster) + kDecCluster * (quantiser warp): this warp's first warp-tile; stride = all quantiser warps of the cluster
+  constexpr int kStride = kDecCluster * kDecQuantWarps;
   const QuantParams& p = f.q;
   const float c_scale = __bfloat162float(p.rot[0]);
   float gs = 1.f, gs_rcp = 1.f;
@@ -100,11 +105,11 @@ __device__ __forceinline__ void decode_quantise(const DecodeFuse& f, uint4* stag
   };
   uint4 nxt[4];
   load(qw, nxt);
-  for (int t = qw; t < n_tiles; t += kDecQuantWarps) {
+  for (int t = qw; t < n_tiles; t += kStride) {
     uint4 ld[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) ld[i] = nxt[i];
-    load(t + kDecQuantWarps, nxt);
+    load(t + kStride, nxt);
     float v[32];
     tile_stage_unpack(ld, stage, lane, v);
     tile_rotate_hadamard<HAD>(v, c_scale);
@@ -116,16 +121,20 @@ __device__ __forceinline__ void decode_quantise(const DecodeFuse& f, uint4* stag
       const int kt = g * 4 + (lane >> 3), j = lane & 7;
       const uint32_t addr = x_base + (uint32_t)kt * (NP * 128u) + (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u +
                             (uint32_t)((j ^ (m & 7)) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3]) : "memory");
       // scales: blocked layout of the (single) 128-row block: block c/4, byte (m % 32) * 16 + (m / 32) * 4 + c % 4
       const int c = NV ? 2 * (g * 32 + lane) : (g * 32 + lane);
       const uint32_t saddr = xsf_base + (uint32_t)(c >> 2) * 512u + (uint32_t)(m & 31) * 16u + (uint32_t)(m >> 5) * 4u + (uint32_t)(c & 3);
-      if constexpr (NV) asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((uint16_t)sf_bytes) : "memory");
-      else asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(sf_bytes) : "memory");
+      // into the resident tiles of EVERY CTA of the cluster (same offsets: identical shared-memory layout in all of them)
+#pragma unroll
+      for (uint32_t d = 0; d < (uint32_t)kDecCluster; ++d) {
+        st_cluster_v4(mapa(addr, d), out[0], out[1], out[2], out[3]);
+        if constexpr (NV) st_cluster_u16(mapa(saddr, d), sf_bytes);
+        else st_cluster_u8(mapa(saddr, d), sf_bytes);
+      }
     }
-    fence_proxy_async_smem();          // generic-proxy writes -> the tensor core's (async proxy) reads
+    fence_proxy_async_all();           // generic-proxy writes -> the tensor cores' (async proxy) reads, in every CTA of the cluster
     __syncwarp();
-    if (lane == 0) mbar_arrive(xq_bar0 + 8u * (uint32_t)g);
+    if (lane < kDecCluster) mbar_arrive_release_cluster(mapa(xq_bar0 + 8u * (uint32_t)g, (uint32_t)lane));
     if (write_global) chunk_store<NV, false>(p, ((int64_t)m * k_groups + g) * 32 + lane, out, sf_bytes, 0u);
   }
 }
@@ -213,7 +222,8 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     tmem_relinquish<1>();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kFuse) cluster_sync();      // peers write into our tiles and arrive on our barriers: they must be initialised first
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_gen, 0);
   const uint32_t tmem_wsf = tmem_base + ACC * NP;              // weight scales of the current k-tile (SFKB blocks x 4 columns)
@@ -317,7 +327,8 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
           if (first_tile && (kt & 3) == 0) {
             // fused: group kt/4 of the activations (4 k-tiles of every row) has been quantised into shared memory by the
             // quantiser warps of THIS CTA -> its scale blocks go to TMEM now
-            mbar_wait(xq_bar0 + 8u * (uint32_t)(kt >> 2), 0, 7);
+            mbar_wait<true>(xq_bar0 + 8u * (uint32_t)(kt >> 2), 0, 7);      // acquire at cluster scope: the writers are 8 CTAs
+            fence_proxy_async_all();
             tc_fence_after();
             if (kt == 0 && lane == 0) dtrace(p.flags, 4);
             for (int c = kt * SFKB; c < (kt + 4) * SFKB; ++c) {
@@ -362,11 +373,13 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     uint32_t acc_phase = 0;
     pdl_wait();                                   // x comes from the predecessor kernel; D may still be read by it
     if constexpr (kFuse) {
-      // warps 2..9: rotate + quantise x into the resident tiles; CTA 0 also writes the outputs of the quantiser to global
-      const int qw = warp - 2;
-      uint4* qstage = reinterpret_cast<uint4*>(smem_gen + (xsf_base - smem_base) + xsf_bytes) + qw * 128;
+      // warps 2..9: rotate + quantise this CTA's share of x into the resident tiles of the whole cluster; cluster 0 also
+      // writes the outputs of the quantiser to global memory
+      const int qwl = warp - 2;
+      uint4* qstage = reinterpret_cast<uint4*>(smem_gen + (xsf_base - smem_base) + xsf_bytes) + qwl * 128;
       if (blockIdx.x == 0) zero_fill_sf_padding(fq.q, (int64_t)threadIdx.x - 64, (int64_t)kDecQuantWarps * 32);
-      decode_quantise_role<kNV, NP>(fq, qstage, qw, lane, x_base, xsf_base, xq_bar0, p.M, k_groups, blockIdx.x == 0);
+      const int qw = (int)cluster_ctarank() + kDecCluster * qwl;
+      decode_quantise_role<kNV, NP>(fq, qstage, qw, lane, x_base, xsf_base, xq_bar0, p.M, k_groups, blockIdx.x < kDecCluster);
       if (warp >= 6) goto done;                    // the four extra warps have no epilogue duty
     }
     if (!kFuse && warp == 2) {
@@ -427,7 +440,8 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 
 done:
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kFuse) cluster_sync();      // no CTA may exit while a peer can still write into its shared memory
+  else __syncthreads();
   if (threadIdx.x == 0) { dtrace(p.flags, 10); dtrace(p.flags, 11, true); }
   if (warp == 1) {
     __syncwarp();
@@ -461,7 +475,9 @@ bool decode_eligible(int M, int N, int K, int ldd, int kind) {
 }
 
 bool decode_fuse_eligible(int M, int N, int K, int had, int method, int kind) {
-  if (env().no_fuse_decode) return false;
+  // First version (every CTA quantising ALL of x itself; profiles/r02_decode_probe2_v2.jsonl): bit-identical but 9.8 / 14.4 /
+  // 22.5 us at M = 1 / 16 / 32 against 8.6 / 8.4 / 8.9 us for the two launches.  The cluster-of-8 version is opt-in until measured.
+  if (!env().fuse_decode) return false;
   if (!decode_eligible(M, N, K, N, kind)) return false;
   if (!(method & B200Q_ROT_TRUSTED_HADAMARD)) return false;              // in-register butterflies only
   const bool nv = kind == B200Q_KIND_NVF4;
@@ -502,17 +518,43 @@ static int launch_decode_t(const void* A, const void* B, const void* SFA, const 
     if ((rc = make_sf_tmap(&tsx, SFA, ceil_div(M, 128), sf_col_blocks, (int)sf_col_blocks, 1, "SFx (decode)"))) return rc;
   }
   cudaLaunchConfig_t cfg = {};
-  int ctas = num_sms();
-  if (ctas > p.tiles) ctas = p.tiles;
-  cfg.gridDim = dim3((unsigned)ctas);
   cfg.blockDim = dim3(kFuse ? kDecFuseThreads : kDecThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
-  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attrs[2];
   cfg.attrs = attrs;
-  cfg.numAttrs = env().no_pdl == 1 ? 0 : 1;
+  int ctas = num_sms();
+  if (ctas > p.tiles) ctas = p.tiles;
+  int n_attr = 0;
+  if constexpr (kFuse) {
+    // clusters of 8 (one GPC each): as many as are co-resident, every cluster complete (CTAs without a tile still quantise)
+    attrs[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attrs[n_attr].val.clusterDim.x = kDecCluster;
+    attrs[n_attr].val.clusterDim.y = 1;
+    attrs[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+    static std::atomic<int> max_clusters[64];
+    std::atomic<int>& mc_a = max_clusters[current_device() & 63];
+    int mc = mc_a.load(std::memory_order_acquire);
+    if (mc == 0) {
+      cfg.gridDim = dim3((unsigned)(num_sms() / kDecCluster * kDecCluster));
+      cfg.numAttrs = n_attr;
+      int n = 0;
+      B200Q_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      mc = n > 0 ? n : 1;
+      mc_a.store(mc, std::memory_order_release);
+    }
+    int clusters = (int)ceil_div(p.tiles, kDecCluster);
+    if (clusters > mc) clusters = mc;
+    ctas = clusters * kDecCluster;
+  }
+  cfg.gridDim = dim3((unsigned)ctas);
+  if (env().no_pdl != 1) {
+    attrs[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  cfg.numAttrs = n_attr;
   DecodeFuse fz = {};
   if (fuse) fz = *fuse;
   B200Q_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, tsx, tsw, p, fz));

@@ -983,7 +983,7 @@ def test_decode_path_in_a_cuda_graph_with_quantiser_in_front(fmt):
 @pytest.mark.parametrize("fmt,had,method", [("mx", 128, "abs_max"), ("mx", 64, "quest"), ("mx", 32, "abs_max"),
                                             ("nv", 16, "abs_max"), ("nv", 128, "quest"), ("nv", 128, "abs_max"), ("nv", 64, "abs_max")])
 @pytest.mark.parametrize("shape", [(16, 1536, 2048), (1, 512, 1024), (32, 640, 4096), (7, 1000, 1024), (16, 128 * 150, 1024)])
-def test_decode_step_in_one_launch_equals_two_calls(fmt, had, method, shape):
+def test_decode_step_in_one_launch_equals_two_calls(fmt, had, method, shape, b200q_env):
     """b200q_linear_fp4 for M <= 32 is ONE launch -- every CTA of the weight-streaming kernel rotates
     and quantises the activations itself -- and reproduces fusedQuantize* followed by matmul_* bit for bit: the bf16 output,
     the codes, the row-major scales and the blocked copy (written by CTA 0)."""
@@ -991,6 +991,8 @@ def test_decode_step_in_one_launch_equals_two_calls(fmt, had, method, shape):
     R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, had, method, fmt, seed=m + n + had)
     lib = _lib.load()
     meth = (0 if method == "quest" else 1) | Q.ROT_TRUSTED_HADAMARD
+    assert lib.b200q_linear_fp4_launches(m, n, k, had, meth, 0 if fmt == "mx" else 1) == 2     # default: two launches (faster)
+    b200q_env("B200Q_FUSE_DECODE", "1")
     assert lib.b200q_linear_fp4_launches(m, n, k, had, meth, 0 if fmt == "mx" else 1) == 1
     for _ in range(2):
         out, xq2, xsf2 = Q.fused_linear_fp4(x, R, wq, wblk, al, global_scale=gs if fmt == "nv" else None, method=method, fmt=fmt)
@@ -1005,6 +1007,8 @@ def test_decode_step_in_one_launch_equals_two_calls(fmt, had, method, shape):
 def test_decode_step_one_launch_in_a_cuda_graph_and_switch(b200q_env):
     m, n, k = 8, 2048, 4096
     R, x, wq, wblk, al, gs, xq, xsf, want = _fused_case(m, n, k, 128, "abs_max", "mx", seed=77)
+    b200q_env("B200Q_FUSE_DECODE", "1")
+    assert _lib.load().b200q_linear_fp4_launches(m, n, k, 128, 1 | Q.ROT_TRUSTED_HADAMARD, 0) == 1
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
@@ -1016,7 +1020,7 @@ def test_decode_step_one_launch_in_a_cuda_graph_and_switch(b200q_env):
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, want)
-    b200q_env("B200Q_NO_FUSE_DECODE", "1")
+    b200q_env("B200Q_FUSE_DECODE", None)
     assert _lib.load().b200q_linear_fp4_launches(m, n, k, 128, 1 | Q.ROT_TRUSTED_HADAMARD, 0) == 2
     out2, _, _ = Q.fused_linear_fp4(x, R, wq, wblk, al)
     torch.cuda.synchronize()

@@ -105,5 +105,8 @@ for M in (1, 16, 32):
     def one(i):
         return Q.fused_linear_fp4(x, R, wq, wblk, alpha)[0]
 
+    os.environ["B200Q_FUSE_DECODE"] = "1"
+    lib.b200q_reload_env()
+
     print(json.dumps(dict(M=M, step="quantise+GEMM, graph replay of 24, us per step",
                           two_calls_static=graph_time(two, 24), two_calls_safe=graph_time(two_safe, 24), one_launch=graph_time(one, 24))), flush=True)
