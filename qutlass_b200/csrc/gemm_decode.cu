@@ -377,9 +377,10 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       // writes the outputs of the quantiser to global memory
       const int qwl = warp - 2;
       uint4* qstage = reinterpret_cast<uint4*>(smem_gen + (xsf_base - smem_base) + xsf_bytes) + qwl * 128;
-      if (blockIdx.x == 0) zero_fill_sf_padding(fq.q, (int64_t)threadIdx.x - 64, (int64_t)kDecQuantWarps * 32);
       const int qw = (int)cluster_ctarank() + kDecCluster * qwl;
       decode_quantise_role<kNV, NP>(fq, qstage, qw, lane, x_base, xsf_base, xq_bar0, p.M, k_groups, blockIdx.x < kDecCluster);
+      // (after the quantisation: the whole cluster waits for CTA 0's share)
+      if (blockIdx.x == 0) zero_fill_sf_padding(fq.q, (int64_t)threadIdx.x - 64, (int64_t)kDecQuantWarps * 32);
       if (warp >= 6) goto done;                    // the four extra warps have no epilogue duty
     }
     if (!kFuse && warp == 2) {
@@ -475,8 +476,13 @@ bool decode_eligible(int M, int N, int K, int ldd, int kind) {
 }
 
 bool decode_fuse_eligible(int M, int N, int K, int had, int method, int kind) {
-  // First version (every CTA quantising ALL of x itself; profiles/r02_decode_probe2_v2.jsonl): bit-identical but 9.8 / 14.4 /
-  // 22.5 us at M = 1 / 16 / 32 against 8.6 / 8.4 / 8.9 us for the two launches.  The cluster-of-8 version is opt-in until measured.
+  // Measured on B200, quantise + GEMM per step under graph replay, M = 1 / 16 / 32 (profiles/r02_decode_probe2_v{2,3}.jsonl):
+  //   two launches (default)                              8.6 /  8.4 /  8.9 us
+  //   one launch, every CTA quantising ALL of x itself    9.8 / 14.4 / 22.5 us
+  //   one launch, clusters of 8 sharing the quantisation 11.5 / 12.6 / 13.8 us  (timeline: the first group of quantised
+  //     activations reaches the MMA warp 6.5 us after kernel entry -- remote stores + fence.proxy.async + release.cluster
+  //     arrives cost more than the kernel boundary they replace)
+  // Both one-launch forms are bit-identical to the two launches; neither is faster, so the single launch is opt-in.
   if (!env().fuse_decode) return false;
   if (!decode_eligible(M, N, K, N, kind)) return false;
   if (!(method & B200Q_ROT_TRUSTED_HADAMARD)) return false;              // in-register butterflies only

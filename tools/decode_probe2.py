@@ -108,5 +108,18 @@ for M in (1, 16, 32):
     os.environ["B200Q_FUSE_DECODE"] = "1"
     lib.b200q_reload_env()
 
+    # timeline of CTA 0 of the ONE-launch step (eager, after a sync)
+    setenv(1 << 24)
+    os.environ["B200Q_FUSE_DECODE"] = "1"; lib.b200q_reload_env()
+    for i in range(3): one(i)
+    torch.cuda.synchronize()
+    one(0)
+    buf = (ctypes.c_ulonglong * 16)()
+    assert raw.b200q_debug_read_decode_trace(buf, 16) == 0
+    t0 = buf[0]
+    print(json.dumps(dict(M=M, one_launch_timeline_cycles_from_entry={NAMES[i]: buf[i] - t0 for i in (2, 3, 4, 6, 7, 8, 9, 10)},
+                          note="x_landed = MMA warp sees group 0 of the quantised activations", ns_entry_to_exit=buf[11] - buf[1])), flush=True)
+    setenv(0)
+    os.environ["B200Q_FUSE_DECODE"] = "1"; lib.b200q_reload_env()
     print(json.dumps(dict(M=M, step="quantise+GEMM, graph replay of 24, us per step",
                           two_calls_static=graph_time(two, 24), two_calls_safe=graph_time(two_safe, 24), one_launch=graph_time(one, 24))), flush=True)
