@@ -48,8 +48,9 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, interval_ms: int = 20):
         self.index = index
+        self.interval_ms = interval_ms
         self.proc = None
         self.path = os.path.join(ROOT, "gpurun_out", f"bench_clocks_gpu{index}.csv") if os.path.isdir(
             os.path.join(ROOT, "gpurun_out")) else f"/tmp/bench_clocks_gpu{index}.csv"
@@ -57,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
             time.sleep(0.25)   # let the first samples land before the timed region starts
         except Exception:
@@ -347,7 +348,10 @@ def main():
 
     flops = 2.0 * M * N * K
     # every rank samples ITS OWN GPU (the 2.6 % weak-scaling loss needs per-GPU clocks)
-    sampler = ClockSampler(local)
+    # (rank 0 at 20 ms like round 1; the other ranks at 100 ms so that N samplers do not compete with N launch loops for the
+    # host's cores -- their burst leg may see few samples, the 2 s sustained leg sees ~20)
+    smp_ms = 20 if rank == 0 else 100
+    sampler = ClockSampler(local, smp_ms)
     sampler.start()
     ms_step, ms_step_ranks = timed(step, args.steps, args.warmup, per_rank=True)
     clocks = sampler.stop()
@@ -361,7 +365,7 @@ def main():
     sus = None
     if args.sustain_s > 0:
         n_sus = int(min(200000, max(args.steps, args.sustain_s * 1e3 / ms_step)))
-        sampler = ClockSampler(local)
+        sampler = ClockSampler(local, smp_ms)
         sampler.start()
         ms_sus, ms_sus_ranks = timed(step, n_sus, 0, per_rank=True)
         clocks_sus = sampler.stop()

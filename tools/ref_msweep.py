@@ -92,6 +92,10 @@ def sweep(kind, N, K, Ms, had=128):
             q_, s_ = ours_q(x)
             return ours_mm(q_, wq, Q.to_blocked(s_), wblk, alpha)
 
+        def o_both_static():          # a serving stack: weights quantised once -> static_weights=True (b200q.h)
+            q_, s_ = ours_q(x)
+            return ours_mm(q_, wq, Q.to_blocked(s_), wblk, alpha, static_weights=True)
+
         def r_gemm():
             return ref_mm(rq, wq, rblk, wblk, alpha)
 
@@ -104,7 +108,32 @@ def sweep(kind, N, K, Ms, had=128):
 
         rec = dict(kind=kind, N=N, K=K, M=M)
         for name, fn in (("ours_gemm", o_gemm), ("ref_gemm", r_gemm), ("ours_quant", o_quant), ("ref_quant", r_quant),
-                         ("ours_both", o_both), ("ref_both", r_both)):
+                         ("ours_both", o_both), ("ours_both_static", o_both_static), ("ref_both", r_both)):
+            try:
+                rec[name + "_us"] = round(graph_time(fn, iters), 2)
+            except Exception as e:   # noqa: BLE001
+                rec[name + "_us"] = None
+                rec[name + "_error"] = f"{type(e).__name__}: {e}"[:200]
+        fl = 2.0 * M * N * K
+        for side in ("ours", "ref"):
+            t = rec.get(side + "_gemm_us")
+            rec[side + "_gemm_tflops"] = round(fl / t / 1e6, 1) if t else None
+        rows_out.append(rec)
+        print(json.dumps(rec), flush=True)
+
+
+def sweep_f8(N, K, Ms):
+    """MXFP8 GEMM (e4m3 operands, e8m0 scales per 32): ours vs the reference's matmul_mxf8_bf16_tn kernel (gemm.cu:328-380)."""
+    alpha = torch.ones(1, device=dev)
+    w = torch.randint(0, 120, (N, K), dtype=torch.uint8, device=dev).view(torch.float8_e4m3fn)
+    wsf = torch.randint(126, 129, (((N + 127) // 128) * 128 * (K // 32),), dtype=torch.uint8, device=dev).view(torch.float8_e8m0fnu)
+    for M in Ms:
+        a = torch.randint(0, 120, (M, K), dtype=torch.uint8, device=dev).view(torch.float8_e4m3fn)
+        asf = torch.randint(126, 129, (((M + 127) // 128) * 128 * (K // 32),), dtype=torch.uint8, device=dev).view(torch.float8_e8m0fnu)
+        iters = 20 if M <= 4096 else 6
+        rec = dict(kind="mxf8", N=N, K=K, M=M)
+        for name, fn in (("ours_gemm", lambda: Q.matmul_mxf8_bf16_tn(a, w, asf, wsf, alpha)),
+                         ("ref_gemm", lambda: ops.matmul_mxf8_bf16_tn(a, w, asf, wsf, alpha))):
             try:
                 rec[name + "_us"] = round(graph_time(fn, iters), 2)
             except Exception as e:   # noqa: BLE001
@@ -123,11 +152,12 @@ if __name__ == "__main__":
     sweep("mx", 14336, 4096, Ms)
     sweep("nv", 14336, 4096, Ms)
     sweep("mx", 28672, 8192, [2048, 16384])
+    sweep_f8(14336, 4096, [16, 1024, 4096, 16384])
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "ref_msweep.md"), "w") as f:
         f.write("# ours vs the compiled reference, one B200, CUDA-graph replay, best of 3 (us)\n\n")
-        f.write("| kind | N | K | M | GEMM ours | GEMM ref | quantise ours | quantise ref | quant+GEMM ours | quant+GEMM ref (+to_blocked stand-in) |\n")
-        f.write("|---|---|---|---|---|---|---|---|---|---|\n")
+        f.write("| kind | N | K | M | GEMM ours | GEMM ref | quantise ours | quantise ref | quant+GEMM ours | ours, static weights | quant+GEMM ref (+to_blocked stand-in) |\n")
+        f.write("|---|---|---|---|---|---|---|---|---|---|---|\n")
         for r in rows_out:
             f.write(f"| {r['kind']} | {r['N']} | {r['K']} | {r['M']} | {r.get('ours_gemm_us')} | {r.get('ref_gemm_us')} | "
-                    f"{r.get('ours_quant_us')} | {r.get('ref_quant_us')} | {r.get('ours_both_us')} | {r.get('ref_both_us')} |\n")
+                    f"{r.get('ours_quant_us')} | {r.get('ref_quant_us')} | {r.get('ours_both_us')} | {r.get('ours_both_static_us')} | {r.get('ref_both_us')} |\n")
