@@ -169,7 +169,8 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   using Cfg = DecodeCfg<kNV>;
   constexpr int SFKB = Cfg::SFKB;
   constexpr int ACC = 2;
-  static_assert(NP == 16 || NP == 32, "activation rows per MMA");
+  static_assert(NP == 16 || NP == 32 || NP == 64, "activation rows per MMA");
+  static_assert(!kFuse || NP <= 32, "the one-launch variant covers M <= 32");
   const int STAGES = p.stages;
 
   extern __shared__ uint8_t dec_smem_raw[];
@@ -402,7 +403,10 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       uint32_t r[NP];
       const uint32_t taddr = tmem_base + (uint32_t)acc * NP + ((uint32_t)(q * 32) << 16);
       if constexpr (NP == 16) tmem_ld_32x32b_x16(taddr, r);
-      else tmem_ld_32x32b_x32(taddr, r);
+      else {
+#pragma unroll
+        for (int j = 0; j < NP / 32; ++j) tmem_ld_32x32b_x32(taddr + j * 32, r + j * 32);
+      }
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -452,7 +456,7 @@ done:
 
 // ------------------------------------------------------------------ host side
 static int decode_stages(int M, int K, bool nv, int* np_out, bool fuse = false) {
-  const int np = M <= 16 ? 16 : 32;
+  const int np = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
   const int k_tiles = K / 256;
   const int sfkb = nv ? 4 : 2;
   const int64_t resident = (int64_t)k_tiles * np * 128 + (int64_t)k_tiles * sfkb * 512 + (fuse ? kDecQuantWarps * 2048 : 0);
@@ -466,10 +470,11 @@ static int decode_stages(int M, int K, bool nv, int* np_out, bool fuse = false) 
 
 bool decode_eligible(int M, int N, int K, int ldd, int kind) {
   if (kind != B200Q_KIND_MXF4 && kind != B200Q_KIND_NVF4) return false;
-  if (M < 1 || M > 32 || N < 1 || K < 256 || K % 256 != 0 || ldd < N) return false;
+  if (M < 1 || M > 64 || N < 1 || K < 256 || K % 256 != 0 || ldd < N) return false;
   const bool nv = kind == B200Q_KIND_NVF4;
   const int k_tiles = K / 256, sfkb = nv ? 4 : 2;
-  if (2 * 32 + sfkb * 4 + k_tiles * sfkb * 4 > 512) return false;      // TMEM: accumulators + weight scales + ALL activation scales
+  const int np = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
+  if (2 * np + sfkb * 4 + k_tiles * sfkb * 4 > 512) return false;      // TMEM: accumulators + weight scales + ALL activation scales
   if (k_tiles * sfkb > 256) return false;                                  // one tensor-map box holds all activation scale blocks
   if (k_tiles > 256) return false;                                         // ... and one box all k-tiles of x
   return decode_stages(M, K, nv, nullptr) >= 4;
@@ -484,7 +489,7 @@ bool decode_fuse_eligible(int M, int N, int K, int had, int method, int kind) {
   //     arrives cost more than the kernel boundary they replace)
   // Both one-launch forms are bit-identical to the two launches; neither is faster, so the single launch is opt-in.
   if (!env().fuse_decode) return false;
-  if (!decode_eligible(M, N, K, N, kind)) return false;
+  if (M > 32 || !decode_eligible(M, N, K, N, kind)) return false;
   if (!(method & B200Q_ROT_TRUSTED_HADAMARD)) return false;              // in-register butterflies only
   const bool nv = kind == B200Q_KIND_NVF4;
   if (!(had == 32 || had == 64 || had == 128 || (nv && had == 16))) return false;
@@ -585,15 +590,17 @@ int launch_gemm_decode_fused(const QuantParams& q, int had, int method, const vo
 int launch_gemm_decode(const void* A, const void* B, const void* SFA, const void* SFB, const float* alpha, void* D, int M, int N,
                        int K, int ldd, int kind, bool static_w, cudaStream_t stream) {
   if (!decode_eligible(M, N, K, ldd, kind)) {
-    set_error("the decode kernel needs an FP4 kind, 1 <= M <= 32, K %% 256 == 0 and K small enough for resident activations "
+    set_error("the decode kernel needs an FP4 kind, 1 <= M <= 64, K %% 256 == 0 and K small enough for resident activations "
               "(M=%d N=%d K=%d kind=%d)", M, N, K, kind);
     return B200Q_EINVAL;
   }
   const bool nv = kind == B200Q_KIND_NVF4;
   if (M <= 16) return nv ? launch_decode_t<true, 16>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream)
                          : launch_decode_t<false, 16>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream);
-  return nv ? launch_decode_t<true, 32>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream)
-            : launch_decode_t<false, 32>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream);
+  if (M <= 32) return nv ? launch_decode_t<true, 32>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream)
+                         : launch_decode_t<false, 32>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream);
+  return nv ? launch_decode_t<true, 64>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream)
+            : launch_decode_t<false, 64>(A, B, SFA, SFB, alpha, D, M, N, K, ldd, static_w, stream);
 }
 
 }  // namespace b200q

@@ -917,7 +917,7 @@ def test_to_blocked_hand_over_and_invalidation():
 # ----------------------------------------------------------------------------- decode kernel (gemm_decode.cu)
 @pytest.mark.parametrize("kind", ["mx", "nv"])
 @pytest.mark.parametrize("shape", [(1, 504, 4096), (16, 14336, 4096), (7, 1000, 2048), (32, 2816, 1024), (17, 640, 256),
-                                   (16, 128 * 150, 512), (3, 100, 768)])
+                                   (16, 128 * 150, 512), (3, 100, 768), (64, 1024, 2048), (48, 640, 1024)])
 def test_decode_kernel_bit_identical_to_the_general_kernel_and_exact_vs_oracle(kind, shape):
     """The swapped-operand weight-streaming kernel (configuration (1, 16), the default for M <= 32) computes the same
     products in the same k order as gemm_fp4_kernel: bit-identical to it on wide-dynamic-range operands, bit-exact against
@@ -929,7 +929,7 @@ def test_decode_kernel_bit_identical_to_the_general_kernel_and_exact_vs_oracle(k
         bq, bsf = H.random_fp4_operand(n, k, kind, seed=n + 32, sf_mode=mode)
         got = H.run_gemm(aq, asf, bq, bsf, kind, 1.0 / 3.0, cfg=(1, 16))
         np.testing.assert_array_equal(got, H.run_gemm(aq, asf, bq, bsf, kind, 1.0 / 3.0, cfg=(1, 128)))
-        np.testing.assert_array_equal(got, H.run_gemm(aq, asf, bq, bsf, kind, 1.0 / 3.0))          # and it IS the default
+        np.testing.assert_array_equal(got, H.run_gemm(aq, asf, bq, bsf, kind, 1.0 / 3.0))          # ... and to the planner's choice
         if mode == "narrow":
             want = H.gemm_oracle_bits(aq, asf, bq, bsf, kind, 1.0)
             mism, rel = H.compare_bits(H.run_gemm(aq, asf, bq, bsf, kind, 1.0, cfg=(1, 16)), want)
@@ -940,7 +940,7 @@ def test_decode_kernel_bit_identical_to_the_general_kernel_and_exact_vs_oracle(k
 
 
 def test_decode_kernel_is_rejected_where_it_does_not_apply():
-    aq, asf = H.random_fp4_operand(64, 512, "mx", seed=1)
+    aq, asf = H.random_fp4_operand(65, 512, "mx", seed=1)
     bq, bsf = H.random_fp4_operand(256, 512, "mx", seed=2)
     with pytest.raises(Exception, match="decode kernel"):
         H.run_gemm(aq, asf, bq, bsf, "mx", 1.0, cfg=(1, 16))

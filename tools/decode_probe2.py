@@ -43,7 +43,7 @@ def graph_time(fn, iters, reps=5):
 
 NAMES = ["entry", "gt_entry", "setup_done", "past_grid_dependency", "x_landed", "x_scales_copied", "first_weights_landed",
          "last_mma_issued", "acc_complete", "stores_issued", "exit", "gt_exit"]
-for M in (1, 16, 32):
+for M in (1, 16, 32, 48, 64):
     a = torch.randint(0, 256, (M, K // 2), dtype=torch.uint8, device=dev)
     sfa = torch.randint(126, 129, (128 * K // 32,), dtype=torch.uint8, device=dev)
     d = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(NSETS)]
