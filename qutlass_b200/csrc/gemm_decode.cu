@@ -124,17 +124,27 @@ __device__ __forceinline__ void decode_quantise(const DecodeFuse& f, uint4* stag
       // scales: blocked layout of the (single) 128-row block: block c/4, byte (m % 32) * 16 + (m / 32) * 4 + c % 4
       const int c = NV ? 2 * (g * 32 + lane) : (g * 32 + lane);
       const uint32_t saddr = xsf_base + (uint32_t)(c >> 2) * 512u + (uint32_t)(m & 31) * 16u + (uint32_t)(m >> 5) * 4u + (uint32_t)(c & 3);
-      // into the resident tiles of EVERY CTA of the cluster (same offsets: identical shared-memory layout in all of them)
+      // the 4 scale bytes of one blocked cell sit in 4 (MX) / 2 (NV) neighbouring lanes: gather them into the cell's first lane
+      uint32_t cell = sf_bytes;
+      if constexpr (NV) {
+        cell |= __shfl_down_sync(0xffffffffu, sf_bytes, 1) << 16;
+      } else {
+        cell |= __shfl_down_sync(0xffffffffu, sf_bytes, 1) << 8;
+        cell |= __shfl_down_sync(0xffffffffu, sf_bytes, 2) << 16;
+        cell |= __shfl_down_sync(0xffffffffu, sf_bytes, 3) << 24;
+      }
+      const bool cell_owner = NV ? ((lane & 1) == 0) : ((lane & 3) == 0);
+      // Into the resident tiles of EVERY CTA of the cluster (identical shared-memory layout in all of them) with st.async:
+      // each store's bytes are counted on THAT CTA's barrier of the group (armed with expect_tx at set-up), so the producer
+      // needs neither a proxy fence nor a cluster-scope release arrive -- those cost ~3 us in the first cluster version.
+      const uint32_t gbar = xq_bar0 + 8u * (uint32_t)g;
 #pragma unroll
       for (uint32_t d = 0; d < (uint32_t)kDecCluster; ++d) {
-        st_cluster_v4(mapa(addr, d), out[0], out[1], out[2], out[3]);
-        if constexpr (NV) st_cluster_u16(mapa(saddr, d), sf_bytes);
-        else st_cluster_u8(mapa(saddr, d), sf_bytes);
+        const uint32_t rbar = mapa(gbar, d);
+        st_async_v4(mapa(addr, d), out[0], out[1], out[2], out[3], rbar);
+        if (cell_owner) st_async_b32(mapa(saddr, d), cell, rbar);
       }
     }
-    fence_proxy_async_all();           // generic-proxy writes -> the tensor cores' (async proxy) reads, in every CTA of the cluster
-    __syncwarp();
-    if (lane < kDecCluster) mbar_arrive_release_cluster(mapa(xq_bar0 + 8u * (uint32_t)g, (uint32_t)lane));
     if (write_global) chunk_store<NV, false>(p, ((int64_t)m * k_groups + g) * 32 + lane, out, sf_bytes, 0u);
   }
 }
@@ -210,7 +220,12 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     }
     mbar_init(x_bar, 1);
     if constexpr (kFuse) {
-      for (int g = 0; g < k_groups; ++g) mbar_init(xq_bar0 + 8u * g, (uint32_t)p.M);   // one arrival per row's warp-tile
+      // one barrier per group of 4 k-tiles, armed once: M rows x (512 B of codes + 32 / 64 B of scales) arrive by st.async from
+      // the 8 CTAs of the cluster
+      for (int g = 0; g < k_groups; ++g) {
+        mbar_init(xq_bar0 + 8u * g, 1);
+        mbar_arrive_expect_tx(xq_bar0 + 8u * g, (uint32_t)p.M * (512u + (kNV ? 64u : 32u)));
+      }
     }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -329,7 +344,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             // fused: group kt/4 of the activations (4 k-tiles of every row) has been quantised into shared memory by the
             // quantiser warps of THIS CTA -> its scale blocks go to TMEM now
             mbar_wait<true>(xq_bar0 + 8u * (uint32_t)(kt >> 2), 0, 7);      // acquire at cluster scope: the writers are 8 CTAs
-            fence_proxy_async_all();
+            fence_proxy_async_smem();                                       // ... and the readers are the tensor core's async proxy
             tc_fence_after();
             if (kt == 0 && lane == 0) dtrace(p.flags, 4);
             for (int c = kt * SFKB; c < (kt + 4) * SFKB; ++c) {

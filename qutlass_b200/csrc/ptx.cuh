@@ -89,6 +89,17 @@ __device__ __forceinline__ void st_cluster_u16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Asynchronous stores into the shared memory of a CTA of the cluster whose completion is counted (in bytes) on an mbarrier of
+// THAT CTA: the producer needs no fence and no arrive -- the consumer's wait on the barrier (expect_tx armed once) orders the data.
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(v), "r"(cluster_bar)
+               : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
