@@ -1,20 +1,22 @@
-// Weight-streaming block-scaled FP4 GEMM for decode-size batches (M <= 32), sm_100a.
+// Weight-streaming block-scaled FP4 GEMM for decode-size batches (M <= 32 by default, 64-row instantiation on request), sm_100a.
 //
 // Same contract and arithmetic as gemm_fp4_kernel (D = bf16(alpha * (A.SFA)(B.SFB)^T), ONE fp32 accumulation chain per
 // output over all of K in ascending k, alpha once, one RNE) -- replaces, for small M, the reference's 128 x 128 decode tile
 // (qutlass/csrc/gemm.cu:195-203).  What differs is the mapping onto the tensor core, chosen from a measured timeline of the
 // general kernel at M = 16 (profiles/r02_decode_probe_before.jsonl): there the mainloop is NOT bandwidth-bound, it costs
-// ~480 cycles per k-tile of tcgen05 issue (4 scale copies + 4 MMAs whose 128-row A operand is 7/8 padding + commit).  Here:
+// ~480 cycles per k-tile on the one issuing thread: 4 scale copies + a commit + 4 MMAs of ~68 cycles each, because the tensor
+// core fetches BOTH 128-row operands from shared memory (~64 B/clk) and the A operand is 7/8 padding.  Here:
 //
 //   * operands are SWAPPED: the 128 weight rows of a tile are the M = 128 operand ("A") of tcgen05.mma, the activations
-//     the N = NP (16 or 32) operand ("B"): D^T[n, m] accumulates in 128 TMEM lanes x NP columns.  An MMA is 128 x NP x 64
-//     instead of 128 x 128 x 64: 4-8x less tensor time per instruction, no padded rows.
-//   * ALL of x (NP rows x K/2 bytes, <= 64 KB) and ALL of its scales are loaded ONCE per CTA into shared memory, and
-//     the scales are copied to TMEM once (K/128 resp. K/64 tcgen05.cp at start-up, under the latency of the first weight
-//     tiles): the per-k-tile work of the single issuing thread is 2 (MX) / 4 (NV) weight-scale copies + 4 MMAs + 1 commit.
+//     the N = NP (16 / 32 / 64) operand ("B"): D^T[n, m] accumulates in 128 TMEM lanes x NP columns.  An MMA is 128 x NP x 64
+//     instead of 128 x 128 x 64: only the weight operand (4 KB per MMA) is a full 128 rows.
+//   * ALL of x (NP rows x K/2 bytes) and ALL of its scales are loaded ONCE per CTA into shared memory -- two TMA ops, issued by
+//     an idle epilogue warp the moment the grid dependency resolves -- and the scales are copied to TMEM once (K/128 resp.
+//     K/64 tcgen05.cp, under the latency of the first weight tiles): per k-tile the issuing thread does 2 (MX) / 4 (NV)
+//     weight-scale copies + 4 MMAs + 1 commit (measured: 401 cycles per k-tile, 323-346 with no weight traffic at all).
 //   * the ring holds only weights: 17-18 KB per stage, 8-10 k-tiles in flight per SM.
-//   * epilogue: thread = output column n (TMEM lane), registers = the NP rows m; bf16 stores are 64 contiguous bytes per warp
-//     and row -- D is tiny (M x N x 2 bytes).
+//   * epilogue: thread = output column n (TMEM lane), registers = the NP rows m; lane pairs swap one value per row pair so that
+//     every lane stores 4 bytes: 64 contiguous bytes per warp and row -- D is tiny (M x N x 2 bytes).
 // The products are the same numbers in the same k order as in the general kernel, so the result is bit-identical to it
 // (tests/test_gpu_parity.py::test_decode_kernel_*).
 #include "common.cuh"
