@@ -73,22 +73,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
-// arrive on a barrier of another CTA of the cluster WITH release semantics at cluster scope: publishes this thread's (and,
-// after a __syncwarp, its warp's) earlier writes -- e.g. st.shared::cluster into that CTA's shared memory -- to the waiter
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
-// stores into the shared memory of a CTA of the cluster (address from mapa)
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void st_cluster_u8(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_cluster_u16(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // Asynchronous stores into the shared memory of a CTA of the cluster whose completion is counted (in bytes) on an mbarrier of
 // THAT CTA: the producer needs no fence and no arrive -- the consumer's wait on the barrier (expect_tx armed once) orders the data.
 __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t cluster_bar) {

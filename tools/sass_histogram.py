@@ -8,7 +8,7 @@ LIB = os.path.join(ROOT, "qutlass_b200", "lib", "libb200q.so")
 out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r02_sass_histogram.md")
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 names = subprocess.run(["cu++filt"], input="\n".join(re.findall(r"Function : (\S+)", sass)), capture_output=True, text=True).stdout.split("\n")
-KEYS = ["UTCQMMA", "UTCOMMA", "UTCHMMA", "UTCCP", "LDTM", "STTM", "UTCBAR", "UTMALDG", "UTMASTG", "UTMAPF", "UTMACCTL", "SYNCS", "HMMA", "LDGSTS", "REDUX", "ACQBULK"]
+KEYS = ["UTCQMMA", "UTCOMMA", "UTCHMMA", "UTCCP", "LDTM", "STTM", "UTCBAR", "UTMALDG", "UTMASTG", "UTMAPF", "UTMACCTL", "SYNCS", "HMMA", "LDGSTS", "REDUX", "ACQBULK", "STAS"]
 rows, cur, i = [], None, 0
 for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
