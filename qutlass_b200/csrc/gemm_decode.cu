@@ -21,6 +21,17 @@
 // (tests/test_gpu_parity.py::test_decode_kernel_*).
 #include "common.cuh"
 #include "ptx.cuh"
+
+// Profiling switches (timing-only ablations, timelines) exist only in the -DB200Q_PROFILING build: in the product build the
+// flag word is the constant 0 and the compiler removes every branch on it -- also from the single-thread issue loops, where a
+// dormant time-out wait behind a run-time flag cost the small-M kernels 1.5 us (profiles/r02_notes.md).
+#ifndef B200Q_FLAGS
+#ifdef B200Q_PROFILING
+#define B200Q_FLAGS(p) ((p).flags)
+#else
+#define B200Q_FLAGS(p) 0
+#endif
+#endif
 #include "quantize_tile.cuh"
 #include "tmap.cuh"
 
@@ -207,7 +218,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
-  if (threadIdx.x == 0) { dtrace(p.flags, 0); dtrace(p.flags, 1, true); }
+  if (threadIdx.x == 0) { dtrace(B200Q_FLAGS(p), 0); dtrace(B200Q_FLAGS(p), 1, true); }
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_w);
@@ -246,7 +257,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_gen, 0);
   const uint32_t tmem_wsf = tmem_base + ACC * NP;              // weight scales of the current k-tile (SFKB blocks x 4 columns)
   const uint32_t tmem_xsf = tmem_wsf + SFKB * 4;               // ALL activation scales: k_tiles x SFKB blocks x 4 columns
-  if (threadIdx.x == 0) dtrace(p.flags, 2);
+  if (threadIdx.x == 0) dtrace(B200Q_FLAGS(p), 2);
 
   int my_tiles = 0;
   for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) ++my_tiles;
@@ -281,7 +292,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       }
     }
     pdl_wait();
-    if (lane == 0) dtrace(p.flags, 3);
+    if (lane == 0) dtrace(B200Q_FLAGS(p), 3);
     int tile = blockIdx.x, kt = 0;
     for (int g = 0; g < pre; ++g) {
       if (elected && g >= early) load_w(g, tile, kt);
@@ -290,7 +301,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     __syncwarp();
     int stage = (pre == STAGES) ? 0 : pre;
     uint32_t phase = (pre == STAGES) ? 1 : 0;
-    const bool ring_only = (p.flags & (1 << 22)) != 0;      // profiling: later k-tiles reuse what the first ring loaded
+    const bool ring_only = (B200Q_FLAGS(p) & (1 << 22)) != 0;      // profiling: later k-tiles reuse what the first ring loaded
     for (int g = pre; g < total_kt; ++g) {
       mbar_wait(empty_bar(stage), phase ^ 1, 1);
       if (elected) {
@@ -319,22 +330,22 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       // activation scales -> TMEM, once
       mbar_wait(x_bar, 0, 2);
       tc_fence_after();
-      if (lane == 0) dtrace(p.flags, 4);
+      if (lane == 0) dtrace(B200Q_FLAGS(p), 4);
       const int nblk = p.k_tiles * SFKB;
       for (int c = 0; c < nblk; ++c) {
         if (elected) tmem_cp_32x128b_warpx4<1>(tmem_xsf + (uint32_t)c * 4u, mk(xsf_lo0 + (uint32_t)c * 32u, kDescHiSF));
       }
       __syncwarp();
-      if (lane == 0) dtrace(p.flags, 5);
+      if (lane == 0) dtrace(B200Q_FLAGS(p), 5);
     }
     bool first_tile = true;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    if (p.flags & (1 << 24)) {
+    if (B200Q_FLAGS(p) & (1 << 24)) {
       mbar_wait(full_bar(0), 0, 9);
-      if (lane == 0) dtrace(p.flags, 6);
+      if (lane == 0) dtrace(B200Q_FLAGS(p), 6);
     }
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1, 3);
@@ -348,7 +359,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             mbar_wait<true>(xq_bar0 + 8u * (uint32_t)(kt >> 2), 0, 7);      // acquire at cluster scope: the writers are 8 CTAs
             fence_proxy_async_smem();                                       // ... and the readers are the tensor core's async proxy
             tc_fence_after();
-            if (kt == 0 && lane == 0) dtrace(p.flags, 4);
+            if (kt == 0 && lane == 0) dtrace(B200Q_FLAGS(p), 4);
             for (int c = kt * SFKB; c < (kt + 4) * SFKB; ++c) {
               if (elected) tmem_cp_32x128b_warpx4<1>(tmem_xsf + (uint32_t)c * 4u, mk(xsf_lo0 + (uint32_t)c * 32u, kDescHiSF));
             }
@@ -381,7 +392,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       if (elected) tc_commit<1>(tfull_bar(acc));
       __syncwarp();
       first_tile = false;
-      if (lane == 0) dtrace(p.flags, 7);
+      if (lane == 0) dtrace(B200Q_FLAGS(p), 7);
       if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
     }
   } else {
@@ -416,7 +427,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase, 4);
       tc_fence_after();
-      if (warp == 2 && lane == 0) dtrace(p.flags, 8);
+      if (warp == 2 && lane == 0) dtrace(B200Q_FLAGS(p), 8);
       uint32_t r[NP];
       const uint32_t taddr = tmem_base + (uint32_t)acc * NP + ((uint32_t)(q * 32) << 16);
       if constexpr (NP == 16) tmem_ld_32x32b_x16(taddr, r);
@@ -455,7 +466,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
           if (m < p.M) dcol[(int64_t)m * p.ldd] = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(r[m]) * alpha));
         }
       }
-      if (warp == 2 && lane == 0) dtrace(p.flags, 9);
+      if (warp == 2 && lane == 0) dtrace(B200Q_FLAGS(p), 9);
       if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -464,7 +475,7 @@ done:
   tc_fence_before();
   if constexpr (kFuse) cluster_sync();      // no CTA may exit while a peer can still write into its shared memory
   else __syncthreads();
-  if (threadIdx.x == 0) { dtrace(p.flags, 10); dtrace(p.flags, 11, true); }
+  if (threadIdx.x == 0) { dtrace(B200Q_FLAGS(p), 10); dtrace(B200Q_FLAGS(p), 11, true); }
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc<1>(tmem_base, 512);

@@ -27,6 +27,17 @@
 // per output over all of K (no split-K), alpha applied once in fp32, one RNE to bf16.
 #include "common.cuh"
 #include "ptx.cuh"
+
+// Profiling switches (timing-only ablations, timelines) exist only in the -DB200Q_PROFILING build: in the product build the
+// flag word is the constant 0 and the compiler removes every branch on it -- also from the single-thread issue loops, where a
+// dormant time-out wait behind a run-time flag cost the small-M kernels 1.5 us (profiles/r02_notes.md).
+#ifndef B200Q_FLAGS
+#ifdef B200Q_PROFILING
+#define B200Q_FLAGS(p) ((p).flags)
+#else
+#define B200Q_FLAGS(p) 0
+#endif
+#endif
 #include "quantize_tile.cuh"
 #include "tmap.cuh"
 #include <type_traits>
@@ -282,7 +293,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   constexpr int kClusterCtas = kCtaGroup * (kMC ? 2 : 1);
   const int cluster_id = blockIdx.x / kClusterCtas;
   const int num_clusters = gridDim.x / kClusterCtas;
-  const bool nfast = (p.flags & 2048) != 0;   // tile walk: M-fastest (B tiles shared by concurrent clusters); profiling flag 2048: N-fastest
+  const bool nfast = (B200Q_FLAGS(p) & 2048) != 0;   // tile walk: M-fastest (B tiles shared by concurrent clusters); profiling flag 2048: N-fastest
   // kMC: a cluster tile is two N-adjacent tiles (one per pair); an odd tile count leaves the second pair an empty tile
   const int tiles_n_eff = kMC ? (p.tiles_n + 1) / 2 : p.tiles_n;
   const int total_tiles = p.tiles_m * tiles_n_eff;
@@ -294,7 +305,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   // a dependent grid (e.g. the tail GEMM of a split launch) may start its prologue / weight loads while this one runs
   pdl_launch_dependents();
-  if (threadIdx.x == 0) { ktrace(p.flags, 0); ktrace(p.flags, 1, true); }
+  if (threadIdx.x == 0) { ktrace(B200Q_FLAGS(p), 0); ktrace(B200Q_FLAGS(p), 1, true); }
 
   // ------------------------------------------------------------------ setup
   if (warp == 0 && lane == 0) {
@@ -324,7 +335,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_gen, 0);
   const uint32_t tmem_sfa = tmem_base + ACC * BN;
   const uint32_t tmem_sfb = tmem_sfa + Cfg::SFA_COLS;
-  if (threadIdx.x == 0) ktrace(p.flags, 2);
+  if (threadIdx.x == 0) ktrace(B200Q_FLAGS(p), 2);
 
   // ------------------------------------------------------------------ roles
   if (warp == 0) {
@@ -360,7 +371,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // profiling flags (timing only, wrong results): 1 << 20 skips the B tile loads, 1 << 21 the A tile loads; 1 << 22: both are
       // skipped AFTER the first ring (the stages then keep the random tiles they were filled with: the tensor pipe works on
       // realistic data with no operand traffic at all -- the power-limited FP4 ceiling of tools/fp4_peak_probe.py)
-      int lflags = p.flags;
+      int lflags = B200Q_FLAGS(p);
       auto load_weights = [&](int stage, int n0, int nb0, int kt) {
         const uint32_t sb = smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
         const uint32_t ssfb = sb + Cfg::B_BYTES + Cfg::SFA_BYTES;
@@ -388,7 +399,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int ready_tm = -1;
       auto wait_acts = [&](int tm) {
         if constexpr (kFuse) {
-          if (tm != ready_tm && !(p.flags & (1024 | 8192))) {     // profiling flags: 1024 no quantisers + no waits, 8192 no waits
+          if (tm != ready_tm && !(B200Q_FLAGS(p) & (1024 | 8192))) {     // profiling flags: 1024 no quantisers + no waits, 8192 no waits
             const int rows = (p.M - tm * 256) < 256 ? (p.M - tm * 256) : 256;
             wait_counter_ge(fp.ctr + 2 + tm, (uint32_t)rows * fp.tiles_per_row, 7);
             fence_proxy_async_global();     // generic-proxy writes (other SMs) -> this SM's TMA (async proxy) reads
@@ -416,7 +427,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
       }
       pdl_wait();
-      if (lane == 0) ktrace(p.flags, 3);
+      if (lane == 0) ktrace(B200Q_FLAGS(p), 3);
       for (int g = 0; g < pre; ++g) {
         wait_acts(cur.tm);
         if (elected) {
@@ -426,7 +437,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         advance(cur);
       }
       __syncwarp();
-      if (p.flags & (1 << 22)) lflags |= (3 << 20);
+      if (B200Q_FLAGS(p) & (1 << 22)) lflags |= (3 << 20);
       int stage = (pre == STAGES) ? 0 : pre;
       uint32_t phase = (pre == STAGES) ? 1 : 0;
       for (int g = pre; g < total_kt; ++g) {
@@ -464,7 +475,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
         return d;
       };
-      const bool skip_cp = (p.flags & 32) != 0;     // profiling flag 32: no scale copies (timing only)
+      const bool skip_cp = (B200Q_FLAGS(p) & 32) != 0;     // profiling flag 32: no scale copies (timing only)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -477,10 +488,10 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const uint32_t sfb_shift = (uint32_t)((n0 % 128) / 32);     // 0 or 2 columns into the first SFB block
         mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2);
         tc_fence_after();
-        trace_event(p.flags, tidx, 0);
-        if (p.flags & (1 << 24)) {                       // profiling builds: when did this tile's first k-tile land?
+        trace_event(B200Q_FLAGS(p), tidx, 0);
+        if (B200Q_FLAGS(p) & (1 << 24)) {                       // profiling builds: when did this tile's first k-tile land?
           mbar_wait(bar_base + 8u * stage, phase, 9);    // (non-consuming: the issue loop waits on the same phase again)
-          trace_event(p.flags, tidx, 1);
+          trace_event(B200Q_FLAGS(p), tidx, 1);
         }
         const uint32_t tmem_acc = tmem_base + acc * BN;
         const uint32_t tsfb = tmem_sfb + sfb_shift;
@@ -529,7 +540,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (full_kt < p.k_tiles) k_tile(std::true_type{}, full_kt, p.K - full_kt * Cfg::BK_ELEMS);
         if (elected) tc_commit<kCtaGroup>(tfull_bar(acc), (uint16_t)(3u << leader_rank));   // accumulator complete
         __syncwarp();
-        trace_event(p.flags, tidx, 2);
+        trace_event(B200Q_FLAGS(p), tidx, 2);
         if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -537,11 +548,11 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ===================== quantiser (warps 10.., fused kernel only) =====================
     if constexpr (kFuse != 0) {
       pdl_wait();   // x comes from the previous kernel in the stream; the outputs may still be read by it
-      if (!(p.flags & 1024)) zero_fill_sf_padding(fp.q, (int64_t)blockIdx.x * (32 * kFuse) + (threadIdx.x - kGemmThreads),
+      if (!(B200Q_FLAGS(p) & 1024)) zero_fill_sf_padding(fp.q, (int64_t)blockIdx.x * (32 * kFuse) + (threadIdx.x - kGemmThreads),
                            (int64_t)gridDim.x * (32 * kFuse));
       uint4* qstage = reinterpret_cast<uint4*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STG_TOTAL + Cfg::BAR_BYTES) +
                       (warp - 2 - kEpiWarps) * 128;
-      if (!(p.flags & 1024)) quantiser_role<kNV, false>(fp, qstage, lane, 0u);   // profiling flag 1024: GEMM part only
+      if (!(B200Q_FLAGS(p) & 1024)) quantiser_role<kNV, false>(fp, qstage, lane, 0u);   // profiling flag 1024: GEMM part only
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -559,7 +570,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // Until this CTA's first accumulator is complete the 8 epilogue warps have nothing to do: they help quantise
       // (their TMA-store staging buffer doubles as the quantiser staging).  All of A is then written about as fast as
       // by the standalone kernel, and the M-fastest tile walk of the first round can start row block by row block.
-      if (!(p.flags & (1024 | 4096)))
+      if (!(B200Q_FLAGS(p) & (1024 | 4096)))
         quantiser_role<kNV, true>(fp, reinterpret_cast<uint4*>(smem_gen + STAGES * Cfg::STAGE_BYTES + ew * Cfg::STG_BYTES), lane,
                                   tfull_bar(0));
     }
@@ -571,7 +582,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(tfull_bar(acc), acc_phase, 6);
       tc_fence_after();
       const int tidx = (tile - cluster_id) / num_clusters;
-      if (ew == 0) trace_event(p.flags, tidx, 3);
+      if (ew == 0) trace_event(B200Q_FLAGS(p), tidx, 3);
       const uint32_t taddr = tmem_base + acc * BN + col0 + ((uint32_t)(q * 32) << 16);
       if constexpr (kFuse > 2) {
         // 448 threads -> 128 registers: drain chunk by chunk, keeping only packed bf16 pairs (EPI_COLS / 2 registers)
@@ -619,7 +630,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       // drain this warp's 32 x EPI_COLS slice of the accumulator into registers, then release TMEM at once
       uint32_t r[Cfg::EPI_COLS];
-      if (!(p.flags & 2)) {
+      if (!(B200Q_FLAGS(p) & 2)) {
 #pragma unroll
         for (int j = 0; j < Cfg::EPI_COLS / 32; ++j) tmem_ld_32x32b_x32(taddr + j * 32, r + j * 32);
         tmem_ld_wait();
@@ -633,9 +644,9 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if constexpr (kCtaGroup == 2) mbar_arrive_cluster(tempty_leader + 8u * acc);
         else mbar_arrive(tempty_bar(acc));
       }
-      if (ew == 0) trace_event(p.flags, tidx, 4);
-      if (p.flags & 512) __nanosleep((uint32_t)ew * (((p.flags >> 12) & 0xff) * 50u));   // profiling: stagger the warps
-      if (!(p.flags & 1)) {
+      if (ew == 0) trace_event(B200Q_FLAGS(p), tidx, 4);
+      if (B200Q_FLAGS(p) & 512) __nanosleep((uint32_t)ew * (((B200Q_FLAGS(p) >> 12) & 0xff) * 50u));   // profiling: stagger the warps
+      if (!(B200Q_FLAGS(p) & 1)) {
         if (p.tma_store) {
 #pragma unroll
           for (int ch = 0; ch < Cfg::EPI_NCHUNK; ++ch) {
@@ -681,14 +692,14 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0 && !(p.flags & 16)) {
+            if (lane == 0 && !(B200Q_FLAGS(p) & 16)) {
               // profiling flag 8: every store lands on the first tile (same lines over and over: L2-resident)
-              const int cx = (p.flags & 8) ? (col0 + ch * Cfg::EPI_CHUNK) : (n0 + col0 + ch * Cfg::EPI_CHUNK);
-              const int cy = (p.flags & 8) ? (q * 32) : (m0 + q * 32);
+              const int cx = (B200Q_FLAGS(p) & 8) ? (col0 + ch * Cfg::EPI_CHUNK) : (n0 + col0 + ch * Cfg::EPI_CHUNK);
+              const int cy = (B200Q_FLAGS(p) & 8) ? (q * 32) : (m0 + q * 32);
               tma_store_2d(&tmap_d, stg, cx, cy);
               bulk_commit_group();
             }
-            if (p.flags & 256) __nanosleep(((p.flags >> 12) & 0xff) * 50u);   // profiling: pace the stores
+            if (B200Q_FLAGS(p) & 256) __nanosleep(((B200Q_FLAGS(p) >> 12) & 0xff) * 50u);   // profiling: pace the stores
           }
         } else if (p.tma_store == 0 && (p.ldd % 16) == 0) {
           // direct 256-bit stores: thread = row, one full 32-byte sector per instruction
@@ -726,7 +737,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
         }
       }
-      if (ew == 0) trace_event(p.flags, tidx, 5);
+      if (ew == 0) trace_event(B200Q_FLAGS(p), tidx, 5);
       if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait_group<0>();   // all TMA stores of this warp have completed
@@ -735,7 +746,7 @@ gemm_fp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   // ------------------------------------------------------------------ teardown
   tc_fence_before();
   if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
-  if (threadIdx.x == 0) { ktrace(p.flags, 5); ktrace(p.flags, 6, true); }
+  if (threadIdx.x == 0) { ktrace(B200Q_FLAGS(p), 5); ktrace(B200Q_FLAGS(p), 6, true); }
   if (warp == 1) {
     __syncwarp();   // .sync.aligned: the issuing lane must have reconverged with its warp
     tmem_dealloc<kCtaGroup>(tmem_base, Cfg::TMEM_COLS);
@@ -1227,8 +1238,8 @@ static int launch_gemm(const void* A, const void* B, const void* SFA, const void
   p.tma_store = (ldd % 8 == 0) ? 1 : 0;
   p.static_weights = static_w ? 1 : 0;
   p.flags = env().gemm_flags;                              // always 0 unless the library was built with -DB200Q_PROFILING
-  if (p.flags & 4) p.tma_store = 0;
-  if ((p.flags & 128) && p.tma_store) p.tma_store = 2;     // coalesced st.global from the staged tile
+  if (B200Q_FLAGS(p) & 4) p.tma_store = 0;
+  if ((B200Q_FLAGS(p) & 128) && p.tma_store) p.tma_store = 2;     // coalesced st.global from the staged tile
   if (p.tma_store) {
     if ((rc = make_d_tmap(&td, D, M, N, ldd, Cfg::EPI_CHUNK))) return rc;
   } else {

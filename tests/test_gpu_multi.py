@@ -18,6 +18,10 @@ if not torch.cuda.is_available():
 
 def _worker(rank, world, port, fmt, m, n, k):
     sys.path.insert(0, ROOT)
+    # One quantiser kernel for every shard size: by default inputs below 8 M elements take the butterfly kernel and larger ones
+    # the tcgen05 kernel, which differ in fp32 summation order of the rotation (<= 1e-5 of the codes) -- a 512-row shard and
+    # the 4096-row full tensor would then not be bit-comparable (observed at 8 GPUs: 0.12 % of the outputs one ulp apart).
+    os.environ["B200Q_QUANT_TC"] = "1"
     import torch.distributed as dist
     import qutlass_b200 as Q
     from qutlass_b200.sharding import broadcast_weights, shard_rows
