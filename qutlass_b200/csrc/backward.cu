@@ -174,29 +174,10 @@ __device__ __forceinline__ void load_tile_fp4(const BwdParams& p, const uint8_t*
 }
 
 // ------------------------------------------------------------------ backward_t_bf16 / backward_qt_bf16
+// compute phase: shared input tile (input orientation) -> rotated + quantised output tile in shared staging
 template <bool QT, bool TRUST>
-__global__ void __launch_bounds__(kBwdThreads) bwd_transpose_quantize_fp4_kernel(const BwdParams p) {
-  __shared__ __align__(16) uint8_t s_tile[QT ? kBwdTile * 64 : kBwdTile * 256];
-  __shared__ __align__(16) uint8_t s_sc[QT ? kBwdTile * 4 : 16];
-  __shared__ __align__(16) uint8_t s_out[kBwdTile * 64];
-  __shared__ __align__(16) uint8_t s_osf[kBwdTile * 4];
-  __shared__ __align__(16) float s_rot[TRUST ? 4 : 1024];
-
-  const int n0 = blockIdx.x * kBwdTile, m0 = blockIdx.y * kBwdTile, b = blockIdx.z;
-  if constexpr (QT) {
-    load_tile_fp4(p, (const uint8_t*)p.x + (size_t)b * p.N * (p.M >> 1), p.x_sf + (size_t)b * p.N * (p.M >> 5), n0, m0,
-                  s_tile, s_sc);
-  } else {
-    load_tile_bf16(p, (const __nv_bfloat16*)p.x + (size_t)b * p.N * p.M, n0, m0, s_tile);
-  }
-  if constexpr (!TRUST) {
-    for (int i = threadIdx.x; i < 1024; i += kBwdThreads) s_rot[i] = __bfloat162float(p.rot[i]);
-  }
-  const float c_scale = __bfloat162float(p.rot[0]);
-  float alpha = 1.f;
-  if constexpr (QT) alpha = __ldg(p.alpha);
-  __syncthreads();
-
+__device__ __forceinline__ void bwd_tq_compute(const uint8_t* s_tile, const uint8_t* s_sc, uint8_t* s_out, uint8_t* s_osf,
+                                               const float* s_rot, float c_scale, float alpha) {
   const int g = threadIdx.x >> 6, mp = threadIdx.x & 63;   // row group (32 input rows) / column pair
   float v0[32], v1[32];
   if constexpr (QT) {
@@ -224,15 +205,15 @@ __global__ void __launch_bounds__(kBwdThreads) bwd_transpose_quantize_fp4_kernel
   const uint32_t e1 = quantise32_absmax<QT>(v1, alpha, o1);
 
   // stage: output row (2 mp + col) holds 4 groups x 16 B; the 16-byte slot is XOR-swizzled with (row >> 1) & 3
-  {
-    const int slot = (g ^ (mp & 3)) * 16;
-    *reinterpret_cast<uint4*>(s_out + (2 * mp) * 64 + slot) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-    *reinterpret_cast<uint4*>(s_out + (2 * mp + 1) * 64 + slot) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-    s_osf[(2 * mp) * 4 + g] = (uint8_t)e0;
-    s_osf[(2 * mp + 1) * 4 + g] = (uint8_t)e1;
-  }
-  __syncthreads();
+  const int slot = (g ^ (mp & 3)) * 16;
+  *reinterpret_cast<uint4*>(s_out + (2 * mp) * 64 + slot) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+  *reinterpret_cast<uint4*>(s_out + (2 * mp + 1) * 64 + slot) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+  s_osf[(2 * mp) * 4 + g] = (uint8_t)e0;
+  s_osf[(2 * mp + 1) * 4 + g] = (uint8_t)e1;
+}
 
+// store phase: staged output tile -> coalesced 16-byte stores, one 32-bit scale word per output row
+__device__ __forceinline__ void bwd_tq_store(const BwdParams& p, const uint8_t* s_out, const uint8_t* s_osf, int n0, int m0, int b) {
   const int out_row_bytes = p.N >> 1, out_row_sf = p.N >> 5;
   uint8_t* qb = p.q + (size_t)b * p.M * out_row_bytes;
   uint8_t* sb = p.sf + (size_t)b * p.M * out_row_sf;
@@ -263,18 +244,150 @@ __global__ void __launch_bounds__(kBwdThreads) bwd_transpose_quantize_fp4_kernel
   }
 }
 
+template <bool QT, bool TRUST>
+__global__ void __launch_bounds__(kBwdThreads) bwd_transpose_quantize_fp4_kernel(const BwdParams p) {
+  __shared__ __align__(16) uint8_t s_tile[QT ? kBwdTile * 64 : kBwdTile * 256];
+  __shared__ __align__(16) uint8_t s_sc[QT ? kBwdTile * 4 : 16];
+  __shared__ __align__(16) uint8_t s_out[kBwdTile * 64];
+  __shared__ __align__(16) uint8_t s_osf[kBwdTile * 4];
+  __shared__ __align__(16) float s_rot[TRUST ? 4 : 1024];
+
+  const int n0 = blockIdx.x * kBwdTile, m0 = blockIdx.y * kBwdTile, b = blockIdx.z;
+  if constexpr (QT) {
+    load_tile_fp4(p, (const uint8_t*)p.x + (size_t)b * p.N * (p.M >> 1), p.x_sf + (size_t)b * p.N * (p.M >> 5), n0, m0,
+                  s_tile, s_sc);
+  } else {
+    load_tile_bf16(p, (const __nv_bfloat16*)p.x + (size_t)b * p.N * p.M, n0, m0, s_tile);
+  }
+  if constexpr (!TRUST) {
+    for (int i = threadIdx.x; i < 1024; i += kBwdThreads) s_rot[i] = __bfloat162float(p.rot[i]);
+  }
+  const float c_scale = __bfloat162float(p.rot[0]);
+  float alpha = 1.f;
+  if constexpr (QT) alpha = __ldg(p.alpha);
+  __syncthreads();
+  bwd_tq_compute<QT, TRUST>(s_tile, s_sc, s_out, s_osf, s_rot, c_scale, alpha);
+  __syncthreads();
+  bwd_tq_store(p, s_out, s_osf, n0, m0, b);
+}
+
+// ---- persistent, double-buffered form (round 2, session 3): a CTA walks tiles blockIdx.x, + gridDim.x, ... (n-tiles fastest, so the
+// CTAs of one sweep still fill whole output lines together) and requests tile i + 1 with cp.async (zero-filled outside the
+// matrix) before it computes tile i: the one-shot form exposes the DRAM latency of every tile to its two resident CTAs
+// (load -> barrier -> ~900 instructions per thread -> barrier -> store).  Same compute / store code, same bytes.
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// request one input tile (bf16: 128 rows x 256 B; FP4: 128 rows x 64 B of codes + 128 x 4 scale bytes) into shared memory
+template <bool FP4>
+__device__ __forceinline__ void bwd_request_tile(const BwdParams& p, int b, int n0, int m0, uint8_t* s_tile, uint8_t* s_sc) {
+  if constexpr (!FP4) {
+    const __nv_bfloat16* xb = (const __nv_bfloat16*)p.x + (size_t)b * p.N * p.M;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = threadIdx.x + kBwdThreads * i;
+      const int row = c >> 4, ch = c & 15;
+      const int n = n0 + row, m = m0 + ch * 8;
+      const bool ok = n < p.n_valid && m < p.M;
+      cp_async16_zfill(s_tile + c * 16, ok ? (const void*)(xb + (size_t)n * p.M + m) : p.x, ok);
+    }
+  } else {
+    const int row_bytes = p.M >> 1, row_sf = p.M >> 5;
+    const uint8_t* xq = (const uint8_t*)p.x + (size_t)b * p.N * row_bytes;
+    const uint8_t* xs = p.x_sf + (size_t)b * p.N * row_sf;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = threadIdx.x + kBwdThreads * i;
+      const int row = c >> 2, ch = c & 3;
+      const int n = n0 + row, m = m0 + ch * 32;
+      const bool ok = n < p.n_valid && m < p.M;
+      cp_async16_zfill(s_tile + c * 16, ok ? (const void*)(xq + (size_t)n * row_bytes + (m >> 1)) : p.x, ok);
+    }
+    if (threadIdx.x < kBwdTile) {
+      // outside the matrix the codes are zero, so any scale gives 0 (zero-filled scale bytes: 0 * 0 resp. 0 * 2^-127)
+      const int n = n0 + threadIdx.x;
+      const uint8_t* src = xs + (size_t)n * row_sf + (m0 >> 5);
+      if ((row_sf & 3) == 0 && (m0 + 128 <= p.M || n >= p.n_valid)) {
+        cp_async4_zfill(s_sc + threadIdx.x * 4, n < p.n_valid ? (const void*)src : (const void*)p.x_sf, n < p.n_valid);
+      } else {
+        uint32_t w = 0;
+        if (n < p.n_valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (m0 + 32 * j < p.M) w |= (uint32_t)__ldg(src + j) << (8 * j);
+          }
+        }
+        reinterpret_cast<uint32_t*>(s_sc)[threadIdx.x] = w;     // plain store: visible after the barrier that follows the wait
+      }
+    }
+  }
+}
+
+constexpr int kBwdPipeOut = kBwdTile * 64 + kBwdTile * 4;                     // staged output tile + its scale words
+constexpr int bwd_pipe_smem(bool fp4, bool trust) {
+  return 2 * (fp4 ? kBwdTile * 64 + kBwdTile * 4 : kBwdTile * 256) + kBwdPipeOut + (trust ? 0 : 4096);
+}
+
+template <bool QT, bool TRUST>
+__global__ void __launch_bounds__(kBwdThreads) bwd_transpose_quantize_fp4_pipe_kernel(const BwdParams p, int tiles_n, int tiles_m,
+                                                                                     int n_tiles) {
+  extern __shared__ __align__(16) uint8_t bwd_smem[];
+  constexpr int kIn = QT ? kBwdTile * 64 + kBwdTile * 4 : kBwdTile * 256;
+  uint8_t* s_out = bwd_smem + 2 * kIn;
+  uint8_t* s_osf = s_out + kBwdTile * 64;
+  float* s_rot = reinterpret_cast<float*>(s_osf + kBwdTile * 4);
+  auto coords = [&](int t, int& b, int& n0, int& m0) {
+    const int tn = t % tiles_n, r = t / tiles_n;
+    n0 = tn * kBwdTile;
+    m0 = (r % tiles_m) * kBwdTile;
+    b = r / tiles_m;
+  };
+  int t = blockIdx.x, b, n0, m0;
+  if (t < n_tiles) {
+    coords(t, b, n0, m0);
+    bwd_request_tile<QT>(p, b, n0, m0, bwd_smem, bwd_smem + kBwdTile * 64);
+  }
+  cp_async_commit();
+  if constexpr (!TRUST) {
+    for (int i = threadIdx.x; i < 1024; i += kBwdThreads) s_rot[i] = __bfloat162float(p.rot[i]);
+  }
+  const float c_scale = __bfloat162float(p.rot[0]);
+  float alpha = 1.f;
+  if constexpr (QT) alpha = __ldg(p.alpha);
+  int buf = 0;
+  for (; t < n_tiles; t += gridDim.x, buf ^= 1) {
+    coords(t, b, n0, m0);
+    const int tn_next = t + gridDim.x;
+    if (tn_next < n_tiles) {
+      int b2, n2, m2;
+      coords(tn_next, b2, n2, m2);
+      uint8_t* nb = bwd_smem + (buf ^ 1) * kIn;
+      bwd_request_tile<QT>(p, b2, n2, m2, nb, nb + kBwdTile * 64);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();                 // this tile's group (the one before the newest) has landed
+    __syncthreads();                    // ... for every thread; also: the previous tile's stores have read s_out
+    const uint8_t* tile = bwd_smem + buf * kIn;
+    bwd_tq_compute<QT, TRUST>(tile, tile + kBwdTile * 64, s_out, s_osf, s_rot, c_scale, alpha);
+    __syncthreads();                    // staging complete; every thread is done with buffer `buf` (refilled next iteration)
+    bwd_tq_store(p, s_out, s_osf, n0, m0, b);
+  }
+}
+
 // ------------------------------------------------------------------ mxfp4_transpose_mxfp8
 // input rows = m of the reference (grouped by 32 after the transpose), input columns = n (rows of the output).
-__global__ void __launch_bounds__(kBwdThreads) bwd_mxfp4_transpose_mxfp8_kernel(const BwdParams p) {
-  __shared__ __align__(16) uint8_t s_tile[kBwdTile * 64];
-  __shared__ __align__(16) uint8_t s_sc[kBwdTile * 4];
-  __shared__ __align__(16) uint8_t s_out[kBwdTile * 128];
-  __shared__ __align__(16) uint8_t s_osf[kBwdTile * 4];
-
-  const int n0 = blockIdx.x * kBwdTile, m0 = blockIdx.y * kBwdTile;   // n0: input row, m0: input column
-  load_tile_fp4(p, (const uint8_t*)p.x, p.x_sf, n0, m0, s_tile, s_sc);
-  __syncthreads();
-
+__device__ __forceinline__ void bwd_tr8_compute(const uint8_t* s_tile, const uint8_t* s_sc, uint8_t* s_out, uint8_t* s_osf) {
   const int g = threadIdx.x >> 6, mp = threadIdx.x & 63;
   float v0[32], v1[32];
   float a0 = 0.f, a1 = 0.f;
@@ -299,19 +412,18 @@ __global__ void __launch_bounds__(kBwdThreads) bwd_mxfp4_transpose_mxfp8_kernel(
     w1[j] = cvt2_e4m3(v1[4 * j] * i1, v1[4 * j + 1] * i1) | (cvt2_e4m3(v1[4 * j + 2] * i1, v1[4 * j + 3] * i1) << 16);
   }
   // stage: output row (2 mp + col) = 128 B (4 groups x 32 B); 16-byte slots XOR-swizzled with (row >> 1) & 7
-  {
-    const int sw = mp & 7;
-    uint8_t* r0 = s_out + (2 * mp) * 128;
-    uint8_t* r1 = r0 + 128;
-    *reinterpret_cast<uint4*>(r0 + (((2 * g) ^ sw) * 16)) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
-    *reinterpret_cast<uint4*>(r0 + (((2 * g + 1) ^ sw) * 16)) = make_uint4(w0[4], w0[5], w0[6], w0[7]);
-    *reinterpret_cast<uint4*>(r1 + (((2 * g) ^ sw) * 16)) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-    *reinterpret_cast<uint4*>(r1 + (((2 * g + 1) ^ sw) * 16)) = make_uint4(w1[4], w1[5], w1[6], w1[7]);
-    s_osf[(2 * mp) * 4 + g] = (uint8_t)e0;
-    s_osf[(2 * mp + 1) * 4 + g] = (uint8_t)e1;
-  }
-  __syncthreads();
+  const int sw = mp & 7;
+  uint8_t* r0 = s_out + (2 * mp) * 128;
+  uint8_t* r1 = r0 + 128;
+  *reinterpret_cast<uint4*>(r0 + (((2 * g) ^ sw) * 16)) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+  *reinterpret_cast<uint4*>(r0 + (((2 * g + 1) ^ sw) * 16)) = make_uint4(w0[4], w0[5], w0[6], w0[7]);
+  *reinterpret_cast<uint4*>(r1 + (((2 * g) ^ sw) * 16)) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+  *reinterpret_cast<uint4*>(r1 + (((2 * g + 1) ^ sw) * 16)) = make_uint4(w1[4], w1[5], w1[6], w1[7]);
+  s_osf[(2 * mp) * 4 + g] = (uint8_t)e0;
+  s_osf[(2 * mp + 1) * 4 + g] = (uint8_t)e1;
+}
 
+__device__ __forceinline__ void bwd_tr8_store(const BwdParams& p, const uint8_t* s_out, const uint8_t* s_osf, int n0, int m0) {
   const int out_row_bytes = p.N, out_row_sf = p.N >> 5;   // N is the padded row count of the input (multiple of 128)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -327,6 +439,48 @@ __global__ void __launch_bounds__(kBwdThreads) bwd_mxfp4_transpose_mxfp8_kernel(
     const int m = m0 + threadIdx.x;
     if (m < p.M)
       *reinterpret_cast<uint32_t*>(p.sf + (size_t)m * out_row_sf + (n0 >> 5)) = reinterpret_cast<const uint32_t*>(s_osf)[threadIdx.x];
+  }
+}
+
+__global__ void __launch_bounds__(kBwdThreads) bwd_mxfp4_transpose_mxfp8_kernel(const BwdParams p) {
+  __shared__ __align__(16) uint8_t s_tile[kBwdTile * 64];
+  __shared__ __align__(16) uint8_t s_sc[kBwdTile * 4];
+  __shared__ __align__(16) uint8_t s_out[kBwdTile * 128];
+  __shared__ __align__(16) uint8_t s_osf[kBwdTile * 4];
+
+  const int n0 = blockIdx.x * kBwdTile, m0 = blockIdx.y * kBwdTile;   // n0: input row, m0: input column
+  load_tile_fp4(p, (const uint8_t*)p.x, p.x_sf, n0, m0, s_tile, s_sc);
+  __syncthreads();
+  bwd_tr8_compute(s_tile, s_sc, s_out, s_osf);
+  __syncthreads();
+  bwd_tr8_store(p, s_out, s_osf, n0, m0);
+}
+
+// persistent, double-buffered form (see bwd_transpose_quantize_fp4_pipe_kernel)
+constexpr int kBwdTr8PipeSmem = 2 * (kBwdTile * 64 + kBwdTile * 4) + kBwdTile * 128 + kBwdTile * 4;
+__global__ void __launch_bounds__(kBwdThreads) bwd_mxfp4_transpose_mxfp8_pipe_kernel(const BwdParams p, int tiles_n, int n_tiles) {
+  extern __shared__ __align__(16) uint8_t bwd_smem[];
+  constexpr int kIn = kBwdTile * 64 + kBwdTile * 4;
+  uint8_t* s_out = bwd_smem + 2 * kIn;
+  uint8_t* s_osf = s_out + kBwdTile * 128;
+  int t = blockIdx.x;
+  if (t < n_tiles) bwd_request_tile<true>(p, 0, (t % tiles_n) * kBwdTile, (t / tiles_n) * kBwdTile, bwd_smem, bwd_smem + kBwdTile * 64);
+  cp_async_commit();
+  int buf = 0;
+  for (; t < n_tiles; t += gridDim.x, buf ^= 1) {
+    const int n0 = (t % tiles_n) * kBwdTile, m0 = (t / tiles_n) * kBwdTile;
+    const int t2 = t + gridDim.x;
+    if (t2 < n_tiles) {
+      uint8_t* nb = bwd_smem + (buf ^ 1) * kIn;
+      bwd_request_tile<true>(p, 0, (t2 % tiles_n) * kBwdTile, (t2 / tiles_n) * kBwdTile, nb, nb + kBwdTile * 64);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const uint8_t* tile = bwd_smem + buf * kIn;
+    bwd_tr8_compute(tile, tile + kBwdTile * 64, s_out, s_osf);
+    __syncthreads();
+    bwd_tr8_store(p, s_out, s_osf, n0, m0);
   }
 }
 
@@ -409,6 +563,49 @@ __global__ void __launch_bounds__(128) bwd_square_double_mxfp8_kernel(const Squa
 
 static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
+// B200Q_BWD_PIPE=0/1 forces the one-shot / the persistent double-buffered form of the three transposing kernels (same bytes)
+constexpr bool kBwdPipeDefault = false;
+static bool bwd_pipe_enabled() {
+  const int sw = env().bwd_pipe;
+  return sw == 1 || (sw < 0 && kBwdPipeDefault);
+}
+
+// persistent grid: resident CTAs per SM (queried once per kernel and device) x SMs, at most one CTA per tile
+template <typename Kern>
+static int pipe_grid(Kern kern, int smem, std::atomic<int>* occ_cache, int n_tiles) {
+  std::atomic<int>& slot = occ_cache[current_device() & 63];
+  int occ = slot.load(std::memory_order_acquire);
+  if (occ == 0) {
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBwdThreads, smem);
+    if (e != cudaSuccess || n <= 0) {
+      set_error("cudaOccupancyMaxActiveBlocksPerMultiprocessor failed: %s", cudaGetErrorString(e));
+      return -1;
+    }
+    occ = n;
+    slot.store(occ, std::memory_order_release);
+  }
+  const int64_t ctas = (int64_t)occ * num_sms();
+  return (int)(ctas < n_tiles ? ctas : n_tiles);
+}
+
+template <bool QT, bool TRUST>
+static int launch_tq_pipe(const BwdParams& p, dim3 grid, cudaStream_t stream) {
+  auto kern = bwd_transpose_quantize_fp4_pipe_kernel<QT, TRUST>;
+  constexpr int smem = bwd_pipe_smem(QT, TRUST);
+  static std::atomic<unsigned long long> attr_done{0};
+  static std::atomic<int> occ[64];
+  if (int rc = ensure_dynamic_smem(kern, smem, attr_done)) return rc;
+  const int64_t n_tiles64 = (int64_t)grid.x * grid.y * grid.z;
+  B200Q_REQUIRE(n_tiles64 < ((int64_t)1 << 31), "problem too large for one launch");
+  const int n_tiles = (int)n_tiles64;
+  const int ctas = pipe_grid(kern, smem, occ, n_tiles);
+  if (ctas <= 0) return B200Q_ECUDA;
+  kern<<<ctas, kBwdThreads, smem, stream>>>(p, (int)grid.x, (int)grid.y, n_tiles);
+  B200Q_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace b200q
 
 using namespace b200q;
@@ -428,6 +625,8 @@ extern "C" int b200q_backward_t_bf16(const void* x_bf16, const void* rot_bf16, v
   p.N = size_n; p.M = size_m; p.n_valid = size_n;
   dim3 grid((unsigned)ceil_div(size_n, kBwdTile), (unsigned)ceil_div(size_m, kBwdTile), (unsigned)size_b);
   B200Q_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "problem too large for one launch");
+  // (a generic rotation is bound by its 1024 FMAs per group, not by latency: one-shot form only)
+  if (bwd_pipe_enabled() && (flags & B200Q_ROT_TRUSTED_HADAMARD)) return launch_tq_pipe<false, true>(p, grid, (cudaStream_t)stream);
   if (flags & B200Q_ROT_TRUSTED_HADAMARD)
     bwd_transpose_quantize_fp4_kernel<false, true><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(p);
   else
@@ -454,6 +653,8 @@ extern "C" int b200q_backward_qt_bf16(const void* x_e2m1, const void* x_e8m0, co
   p.N = size_n; p.M = size_m; p.n_valid = size_n;
   dim3 grid((unsigned)ceil_div(size_n, kBwdTile), (unsigned)ceil_div(size_m, kBwdTile), (unsigned)size_b);
   B200Q_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "problem too large for one launch");
+  // (a generic rotation is bound by its 1024 FMAs per group, not by latency: one-shot form only)
+  if (bwd_pipe_enabled() && (flags & B200Q_ROT_TRUSTED_HADAMARD)) return launch_tq_pipe<true, true>(p, grid, (cudaStream_t)stream);
   if (flags & B200Q_ROT_TRUSTED_HADAMARD)
     bwd_transpose_quantize_fp4_kernel<true, true><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(p);
   else
@@ -496,6 +697,18 @@ extern "C" int b200q_mxfp4_transpose_mxfp8(const void* x_fp4, const void* scales
   p.N = (int)round_up(m, 256); p.M = n; p.n_valid = m;
   dim3 grid((unsigned)(p.N / kBwdTile), (unsigned)ceil_div(n, kBwdTile));
   B200Q_REQUIRE(grid.y <= 65535u, "problem too large for one launch");
+  if (bwd_pipe_enabled()) {
+    auto kern = bwd_mxfp4_transpose_mxfp8_pipe_kernel;
+    static std::atomic<unsigned long long> attr_done{0};
+    static std::atomic<int> occ[64];
+    if (int rc2 = ensure_dynamic_smem(kern, kBwdTr8PipeSmem, attr_done)) return rc2;
+    const int n_tiles = (int)(grid.x * grid.y);
+    const int ctas = pipe_grid(kern, kBwdTr8PipeSmem, occ, n_tiles);
+    if (ctas <= 0) return B200Q_ECUDA;
+    kern<<<ctas, kBwdThreads, kBwdTr8PipeSmem, (cudaStream_t)stream>>>(p, (int)grid.x, n_tiles);
+    B200Q_CUDA(cudaGetLastError());
+    return 0;
+  }
   bwd_mxfp4_transpose_mxfp8_kernel<<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(p);
   B200Q_CUDA(cudaGetLastError());
   return 0;

@@ -47,6 +47,7 @@ constexpr int kDecMaxGroups = 16;         // fused: groups of 4 k-tiles (1024 el
 constexpr int kDecMaxStages = 12;
 constexpr int kDecSmemBudget = 227 * 1024;
 constexpr int kDecEarlyStages = 4;        // static weights: stages whose REAL loads are issued before the grid dependency
+constexpr int kDecPaceFree = 3;           // paced streaming: the first stages are requested at once, the later ones on a clock
 
 struct DecodeParams {
   const float* alpha;
@@ -56,6 +57,7 @@ struct DecodeParams {
   int tiles;          // ceil(N / 128)
   int stages;         // weight ring depth (host: what fits next to x)
   int static_weights;
+  int pace_cycles;    // > 0: weight stage g is requested no earlier than (g - kDecPaceFree) * pace_cycles after set-up (see launch_decode_t)
   int flags;          // profiling builds only: 1 << 24 timeline of CTA 0, 1 << 22 weights loaded for the first ring only
 };
 
@@ -258,6 +260,18 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   const uint32_t tmem_wsf = tmem_base + ACC * NP;              // weight scales of the current k-tile (SFKB blocks x 4 columns)
   const uint32_t tmem_xsf = tmem_wsf + SFKB * 4;               // ALL activation scales: k_tiles x SFKB blocks x 4 columns
   if (threadIdx.x == 0) dtrace(B200Q_FLAGS(p), 2);
+  // Paced streaming (p.pace_cycles > 0).  The memory system serves everything that is outstanding at once, interleaved:
+  // a whole ring requested at set-up lands as ONE bunch (measured: first stage 2.7-3.6 us after entry with 8-10 stages in
+  // flight on 112 SMs), the refills only start then, and HBM idles for a memory latency between the bunches (7.6 us for
+  // 31.2 MB).  Requesting stage g no earlier than (g - kDecPaceFree) * pace_cycles after set-up -- pace = this CTA's share of
+  // the HBM rate -- keeps the requests of all CTAs in k order and the stream continuous.  Same loads, same bytes.
+  const long long pace_t0 = clock64();
+  auto pace_gate = [&](int g) {
+    if (p.pace_cycles > 0 && g > kDecPaceFree) {
+      const long long due = (long long)(g - kDecPaceFree) * p.pace_cycles;
+      while (clock64() - pace_t0 < due) {}
+    }
+  };
 
   int my_tiles = 0;
   for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) ++my_tiles;
@@ -286,7 +300,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       for (int g = 0; g < pre; ++g) {
         if (elected) {
           if (g < early) load_w(g, tile, kt);
-          else prefetch_w(tile, kt);
+          else if (p.pace_cycles <= 0) prefetch_w(tile, kt);       // paced: warp 3 prefetches EVERY k-tile on the clock
         }
         if (++kt == p.k_tiles) { kt = 0; tile += gridDim.x; }
       }
@@ -295,7 +309,10 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     if (lane == 0) dtrace(B200Q_FLAGS(p), 3);
     int tile = blockIdx.x, kt = 0;
     for (int g = 0; g < pre; ++g) {
-      if (elected && g >= early) load_w(g, tile, kt);
+      if (g >= early) {
+        pace_gate(g);
+        if (elected) load_w(g, tile, kt);
+      }
       if (++kt == p.k_tiles) { kt = 0; tile += gridDim.x; }
     }
     __syncwarp();
@@ -304,6 +321,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const bool ring_only = (B200Q_FLAGS(p) & (1 << 22)) != 0;      // profiling: later k-tiles reuse what the first ring loaded
     for (int g = pre; g < total_kt; ++g) {
       mbar_wait(empty_bar(stage), phase ^ 1, 1);
+      pace_gate(g);
       if (elected) {
         if (ring_only) mbar_arrive(full_bar(stage));
         else load_w(stage, tile, kt);
@@ -400,6 +418,20 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (!kFuse && warp == 3 && p.pace_cycles > 0) {
+      // the weight stream into L2, on the clock, from kernel entry on -- also while the predecessor kernel is still running
+      // (an L2 prefetch never makes stale data visible); the ring loads behind it hit L2 or join the fill in flight
+      if (elect_one()) {
+        int tile = blockIdx.x, kt = 0;
+        for (int g = 0; g < total_kt; ++g) {
+          pace_gate(g);
+          tma_prefetch_2d(&tmap_w, kt * 128, tile * 128);
+          tma_prefetch_3d(&tmap_sfw, 0, kt * SFKB, tile);
+          if (++kt == p.k_tiles) { kt = 0; tile += gridDim.x; }
+        }
+      }
+      __syncwarp();
+    }
     pdl_wait();                                   // x comes from the predecessor kernel; D may still be read by it
     if constexpr (kFuse) {
       // warps 2..9: rotate + quantise this CTA's share of x into the resident tiles of the whole cluster; cluster 0 also
@@ -538,6 +570,7 @@ static int launch_decode_t(const void* A, const void* B, const void* SFA, const 
   p.tiles = (int)ceil_div(N, 128);
   p.stages = decode_stages(M, K, kNV, nullptr, kFuse);
   p.static_weights = static_w ? 1 : 0;
+  p.pace_cycles = kFuse ? 0 : (env().decode_pace > 0 ? env().decode_pace : 0);
   p.flags = env().gemm_flags;
   const int smem = 1024 + p.k_tiles * NP * 128 + p.k_tiles * Cfg::SFKB * 512 + (kFuse ? kDecQuantWarps * 2048 : 0) + 1024 +
                    p.stages * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;

@@ -32,6 +32,14 @@ def bwd_golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "backward_vectors.npz"))
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["oneshot", "pipelined"])
+def bwd_form(request, b200q_env):
+    """every test of this module runs against both forms of the transposing kernels (backward.cu): one CTA per tile, and the
+    persistent double-buffered form (B200Q_BWD_PIPE=1).  Same compute and store code: the same bytes."""
+    b200q_env("B200Q_BWD_PIPE", str(request.param))
+    return request.param
+
+
 def _had():
     return H.bf16_tensor_from_f32(O.hadamard_matrix(32))
 

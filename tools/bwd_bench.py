@@ -98,8 +98,10 @@ def main():
         del xq, y8
         torch.cuda.empty_cache()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    form = "pipelined" if os.environ.get("B200Q_BWD_PIPE") == "1" else ("oneshot" if os.environ.get("B200Q_BWD_PIPE") == "0" else "default")
     with open(os.path.join(ROOT, "gpurun_out", "bwd_bench.jsonl"), "w") as f:
         for r in out:
+            r["form"] = form
             f.write(json.dumps(r) + "\n"); print(json.dumps(r))
 
 

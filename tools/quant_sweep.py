@@ -50,7 +50,9 @@ def graph_time(fn, iters, reps=5):
 
 
 rows = []
-for M in (1, 16, 128, 1024, 4096, 16384):
+MS = tuple(int(v) for v in os.environ.get("QUANT_SWEEP_M", "1,16,128,1024,4096,16384").split(","))
+OUT = os.environ.get("QUANT_SWEEP_OUT", "quant_sweep")
+for M in MS:
     nsets = 2 if M >= 4096 else 4
     nsets = max(nsets, min(8, int(200e6 / (M * K * 2.6)) + 1)) if M >= 1024 else 4      # rotate through > L2 when it matters
     xs = [torch.randn(M, K, dtype=torch.bfloat16, device=dev) for _ in range(nsets)]
@@ -72,7 +74,7 @@ for M in (1, 16, 128, 1024, 4096, 16384):
             rows.append(rec)
             print(json.dumps(rec), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-with open(os.path.join(ROOT, "gpurun_out", "quant_sweep.md"), "w") as f:
+with open(os.path.join(ROOT, "gpurun_out", OUT + ".md"), "w") as f:
     f.write(f"# configs[3]: fusedQuantizeMx, K = 4096, graph replay over rotating sets, median of 5; HBM peak {HBM} GB/s (measured copy)\n\n")
     f.write("| M | Hadamard | method | ours us | reference us | ours GB/s | of measured HBM |\n|---|---|---|---|---|---|---|\n")
     for r in rows:
