@@ -564,10 +564,14 @@ __global__ void __launch_bounds__(128) bwd_square_double_mxfp8_kernel(const Squa
 static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
 // B200Q_BWD_PIPE=0/1 forces the one-shot / the persistent double-buffered form of the three transposing kernels (same bytes)
-constexpr bool kBwdPipeDefault = false;
-static bool bwd_pipe_enabled() {
+// Measured (profiles/r02_s3_bwd_bench_pipe{0,1}.jsonl, graph replay over rotating sets): backward_qt 45.9 -> 43.2 us and
+// mxfp4_transpose_mxfp8 36.3 -> 33.5 us at 16384 x 4096 (41.7 -> 38.2 / 34.1 -> 29.7 at 4096 x 14336); backward_qt slower at
+// 4096 x 4096 (3.5 tiles per CTA: 12.8 -> 13.5), backward_t slower everywhere (its 32 KB tiles halve the resident CTAs).  The
+// kernels are bound by their ~14 instructions per element, not by latency, so the gain is modest.  Library rule: the FP4-input
+// kernels from 2048 tiles on.
+static bool bwd_pipe_enabled(bool fp4_input, int64_t n_tiles) {
   const int sw = env().bwd_pipe;
-  return sw == 1 || (sw < 0 && kBwdPipeDefault);
+  return sw == 1 || (sw < 0 && fp4_input && n_tiles >= 2048);
 }
 
 // persistent grid: resident CTAs per SM (queried once per kernel and device) x SMs, at most one CTA per tile
@@ -626,7 +630,7 @@ extern "C" int b200q_backward_t_bf16(const void* x_bf16, const void* rot_bf16, v
   dim3 grid((unsigned)ceil_div(size_n, kBwdTile), (unsigned)ceil_div(size_m, kBwdTile), (unsigned)size_b);
   B200Q_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "problem too large for one launch");
   // (a generic rotation is bound by its 1024 FMAs per group, not by latency: one-shot form only)
-  if (bwd_pipe_enabled() && (flags & B200Q_ROT_TRUSTED_HADAMARD)) return launch_tq_pipe<false, true>(p, grid, (cudaStream_t)stream);
+  if (bwd_pipe_enabled(false, (int64_t)grid.x * grid.y * grid.z) && (flags & B200Q_ROT_TRUSTED_HADAMARD)) return launch_tq_pipe<false, true>(p, grid, (cudaStream_t)stream);
   if (flags & B200Q_ROT_TRUSTED_HADAMARD)
     bwd_transpose_quantize_fp4_kernel<false, true><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(p);
   else
@@ -654,7 +658,7 @@ extern "C" int b200q_backward_qt_bf16(const void* x_e2m1, const void* x_e8m0, co
   dim3 grid((unsigned)ceil_div(size_n, kBwdTile), (unsigned)ceil_div(size_m, kBwdTile), (unsigned)size_b);
   B200Q_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "problem too large for one launch");
   // (a generic rotation is bound by its 1024 FMAs per group, not by latency: one-shot form only)
-  if (bwd_pipe_enabled() && (flags & B200Q_ROT_TRUSTED_HADAMARD)) return launch_tq_pipe<true, true>(p, grid, (cudaStream_t)stream);
+  if (bwd_pipe_enabled(true, (int64_t)grid.x * grid.y * grid.z) && (flags & B200Q_ROT_TRUSTED_HADAMARD)) return launch_tq_pipe<true, true>(p, grid, (cudaStream_t)stream);
   if (flags & B200Q_ROT_TRUSTED_HADAMARD)
     bwd_transpose_quantize_fp4_kernel<true, true><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(p);
   else
@@ -697,7 +701,7 @@ extern "C" int b200q_mxfp4_transpose_mxfp8(const void* x_fp4, const void* scales
   p.N = (int)round_up(m, 256); p.M = n; p.n_valid = m;
   dim3 grid((unsigned)(p.N / kBwdTile), (unsigned)ceil_div(n, kBwdTile));
   B200Q_REQUIRE(grid.y <= 65535u, "problem too large for one launch");
-  if (bwd_pipe_enabled()) {
+  if (bwd_pipe_enabled(true, (int64_t)grid.x * grid.y)) {
     auto kern = bwd_mxfp4_transpose_mxfp8_pipe_kernel;
     static std::atomic<unsigned long long> attr_done{0};
     static std::atomic<int> occ[64];

@@ -44,8 +44,8 @@ static void load_env() {
   e.fuse_decode = env_int("B200Q_FUSE_DECODE", 0) == 1;
   e.bwd_pipe = env_int("B200Q_BWD_PIPE", -1);
   if (e.bwd_pipe != 0 && e.bwd_pipe != 1) e.bwd_pipe = -1;
-  e.decode_pace = env_int("B200Q_DECODE_PACE", 0);
-  if (e.decode_pace < 0 || e.decode_pace > 100000) e.decode_pace = 0;
+  e.decode_pace = env_int("B200Q_DECODE_PACE", -1);
+  if (e.decode_pace < -1 || e.decode_pace > 100000) e.decode_pace = -1;
   g_env = e;
   g_env_ready.store(1, std::memory_order_release);
 }

@@ -35,7 +35,7 @@ struct Env {
   int verbose;       // B200Q_GEMM_VERBOSE
   int gemm_skew;     // B200Q_GEMM_SKEW: -1 unset (planner decides), else forced k-tile skew of the split accumulator
   int no_tmap_cache; // B200Q_NO_TMAP_CACHE=1
-  int decode_pace;   // B200Q_DECODE_PACE: SM cycles between the weight-stage requests of a decode-kernel CTA (0 / unset: all at once)
+  int decode_pace;   // B200Q_DECODE_PACE: SM cycles between the weight-stage requests of a decode-kernel CTA (-1 unset: library rule, 0: all at once)
   int bwd_pipe;      // B200Q_BWD_PIPE: -1 unset (library default), 0 = one-shot CTAs, 1 = persistent double-buffered transposing kernels
   int fuse_decode;   // B200Q_FUSE_DECODE=1: b200q_linear_fp4 runs the decode step (M <= 32) as ONE launch (measured slower: opt-in)
 };

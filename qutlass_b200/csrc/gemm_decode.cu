@@ -345,7 +345,9 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const uint32_t xsf_lo0 = (xsf_base & 0x3FFFFu) >> 4;
     const uint32_t ring_lo0 = ((ring_base & 0x3FFFFu) >> 4);
     if constexpr (!kFuse) {
-      // activation scales -> TMEM, once
+      // activation scales -> TMEM, once, all up front.  (Measured, profiles/r02_s3_decode_interleave_*.jsonl: copying only the first
+      // k-tile's blocks here and the rest one k-tile ahead inside the loop is SLOWER -- M = 16, L2-resident weights: 5.90 -> 6.39
+      // us; the tensor pipe runs cp / mma in order and the extra copies lengthen every k-tile of the issue-bound loop.)
       mbar_wait(x_bar, 0, 2);
       tc_fence_after();
       if (lane == 0) dtrace(B200Q_FLAGS(p), 4);
@@ -570,7 +572,20 @@ static int launch_decode_t(const void* A, const void* B, const void* SFA, const 
   p.tiles = (int)ceil_div(N, 128);
   p.stages = decode_stages(M, K, kNV, nullptr, kFuse);
   p.static_weights = static_w ? 1 : 0;
-  p.pace_cycles = kFuse ? 0 : (env().decode_pace > 0 ? env().decode_pace : 0);
+  // Paced weight streaming (kernel comment at pace_gate).  Measured (profiles/r02_s3_decode_pace_{mx,nv}.jsonl, N = 14336,
+  // K = 4096, graph replay, weights from HBM): default launches 8.14 / 7.83 / 8.51 us -> 7.97 / 7.75 / 8.12 (M = 1 / 16 / 32) at the
+  // pace below, NVFP4 8.63 / 8.41 / 8.99 -> 8.31 / 8.07 / 8.88; L2-resident weights unchanged (the MMA loop is slower than the
+  // clock).  Static-weights launches gain more from HBM (7.54 -> 7.06 at M = 16) but lose 0.3 us at M = 1 with L2-resident
+  // weights, so they stay unpaced unless B200Q_DECODE_PACE says otherwise.  pace = the CTA's share of ~3600 B per SM cycle
+  // (6.8 TB/s at 1.9 GHz): 540 cycles for 112 CTAs x 17 KB stages.  B200Q_DECODE_PACE=0 switches it off, > 0 forces cycles.
+  p.pace_cycles = 0;
+  if (!kFuse) {
+    const int sw = env().decode_pace;
+    int tiles_now = (int)ceil_div(N, 128);
+    if (tiles_now > num_sms()) tiles_now = num_sms();
+    if (sw > 0) p.pace_cycles = sw;
+    else if (sw < 0 && !static_w) p.pace_cycles = (int)((int64_t)Cfg::STAGE_BYTES * tiles_now / 3600);
+  }
   p.flags = env().gemm_flags;
   const int smem = 1024 + p.k_tiles * NP * 128 + p.k_tiles * Cfg::SFKB * 512 + (kFuse ? kDecQuantWarps * 2048 : 0) + 1024 +
                    p.stages * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;

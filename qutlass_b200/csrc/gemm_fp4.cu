@@ -1414,7 +1414,11 @@ static GemmPlan plan_auto(int M, int N, int K, int kind) {
       const double kt = (double)ceil_div(K, (kind == B200Q_KIND_MXF8 || kind == B200Q_KIND_MXF8_NN) ? 128 : 256);
       double best = -1.0;
       const int cands[3] = {256, 192, 128};
-      const double w[3] = {0.36, 0.30, 0.30}, o[3] = {1.2, 0.85, 0.6};
+      const bool f8 = kind == B200Q_KIND_MXF8 || kind == B200Q_KIND_MXF8_NN;
+      // MXFP8 (k-tile = 128 elements, twice the tensor time per byte): the narrower tiles are not dispatch-bound, their
+      // per-k-tile cost follows the width (profiles/r02_s3_f8_probe.jsonl: 12.0 / 9.4 / 7.45 us per round at K = 4096)
+      const double w4[3] = {0.36, 0.30, 0.30}, w8[3] = {0.3375, 0.267, 0.214}, o[3] = {1.2, 0.85, 0.6};
+      const double* w = f8 ? w8 : w4;
       for (int i = 0; i < 3; ++i) {
         const int bn = cands[i];
         const int64_t rounds = ceil_div(tm * ceil_div(N, bn), clusters);
