@@ -571,6 +571,7 @@ static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr
 // kernels from 2048 tiles on.
 static bool bwd_pipe_enabled(bool fp4_input, int64_t n_tiles) {
   const int sw = env().bwd_pipe;
+  if (n_tiles >= ((int64_t)1 << 31)) return false;             // 32-bit tile index in the persistent kernels
   return sw == 1 || (sw < 0 && fp4_input && n_tiles >= 2048);
 }
 
@@ -694,7 +695,8 @@ extern "C" int b200q_mxfp4_transpose_mxfp8(const void* x_fp4, const void* scales
   B200Q_REQUIRE(x_fp4 && scales_e8m0 && x_fp8 && shared_exps, "null pointer argument");
   B200Q_REQUIRE(m > 0 && n > 0, "sizes must be positive");
   B200Q_REQUIRE(n % 32 == 0, "n (%d) must be a multiple of 32", n);
-  B200Q_REQUIRE(aligned16(x_fp4) && aligned16(x_fp8) && (reinterpret_cast<uintptr_t>(shared_exps) & 3) == 0,
+  B200Q_REQUIRE(aligned16(x_fp4) && aligned16(x_fp8) && (reinterpret_cast<uintptr_t>(shared_exps) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(scales_e8m0) & 3) == 0,
                 "pointers must be 16-byte aligned (scales: 4-byte)");
   BwdParams p{};
   p.x = x_fp4; p.x_sf = (const uint8_t*)scales_e8m0; p.q = (uint8_t*)x_fp8; p.sf = (uint8_t*)shared_exps;

@@ -266,8 +266,10 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   // 31.2 MB).  Requesting stage g no earlier than (g - kDecPaceFree) * pace_cycles after set-up -- pace = this CTA's share of
   // the HBM rate -- keeps the requests of all CTAs in k order and the stream continuous.  Same loads, same bytes.
   const long long pace_t0 = clock64();
+  // Only the CTA's FIRST tile is paced (and prefetched): that is where all CTAs start together; later tiles stream in steady
+  // state, paced by the ring itself -- a clock there could only throttle (and warp 3 has epilogues to run).
   auto pace_gate = [&](int g) {
-    if (p.pace_cycles > 0 && g > kDecPaceFree) {
+    if (p.pace_cycles > 0 && g > kDecPaceFree && g < p.k_tiles) {
       const long long due = (long long)(g - kDecPaceFree) * p.pace_cycles;
       while (clock64() - pace_t0 < due) {}
     }
@@ -300,7 +302,7 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       for (int g = 0; g < pre; ++g) {
         if (elected) {
           if (g < early) load_w(g, tile, kt);
-          else if (p.pace_cycles <= 0) prefetch_w(tile, kt);       // paced: warp 3 prefetches EVERY k-tile on the clock
+          else if (p.pace_cycles <= 0 || g >= p.k_tiles) prefetch_w(tile, kt);   // paced: warp 3 prefetches the first tile's k-tiles on the clock
         }
         if (++kt == p.k_tiles) { kt = 0; tile += gridDim.x; }
       }
@@ -424,12 +426,11 @@ gemm_fp4_decode_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       // the weight stream into L2, on the clock, from kernel entry on -- also while the predecessor kernel is still running
       // (an L2 prefetch never makes stale data visible); the ring loads behind it hit L2 or join the fill in flight
       if (elect_one()) {
-        int tile = blockIdx.x, kt = 0;
-        for (int g = 0; g < total_kt; ++g) {
-          pace_gate(g);
+        const int tile = blockIdx.x;
+        for (int kt = 0; kt < p.k_tiles && kt < total_kt; ++kt) {
+          pace_gate(kt);
           tma_prefetch_2d(&tmap_w, kt * 128, tile * 128);
           tma_prefetch_3d(&tmap_sfw, 0, kt * SFKB, tile);
-          if (++kt == p.k_tiles) { kt = 0; tile += gridDim.x; }
         }
       }
       __syncwarp();
