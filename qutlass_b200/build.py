@@ -24,7 +24,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200q.so")
 OBJDIR = os.path.join(HERE, "build")
 
-SOURCES = ["common.cu", "quantize.cu", "gemm_fp4.cu", "gemm_decode.cu", "linear_host.cu", "backward.cu", "quantize_tc.cu"]
+SOURCES = ["common.cu", "quantize.cu", "gemm_fp4.cu", "gemm_decode.cu", "linear_host.cu", "backward.cu", "quantize_tc.cu", "backward_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

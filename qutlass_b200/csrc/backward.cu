@@ -17,6 +17,7 @@
 // Algorithmic bytes / element: backward_t 2 + 0.5 + 1/32 = 2.53; backward_qt 0.53 + 0.53 = 1.06;
 // square_double 2 + 1 + 2/32 = 3.06; mxfp4_transpose_mxfp8 0.53 + 1 + 1/32 = 1.56.
 #include "quantize_tile.cuh"
+#include "backward_quant.cuh"
 #include <cuda_fp16.h>
 
 namespace b200q {
@@ -57,12 +58,6 @@ __device__ __forceinline__ uint32_t cvt2_e4m3(float lo, float hi) {
   return r;
 }
 
-// exact 2^(127 - e) for a ue8m0 byte e (2^-127 .. 2^127; e = 255 (NaN scale) -> 0)
-__device__ __forceinline__ float inv_pow2_of_e8m0(uint32_t e) {
-  if (e >= 254u) return e == 254u ? __uint_as_float(0x00400000u) : 0.f;
-  return __uint_as_float((254u - e) << 23);
-}
-
 // shared exponent of the MXFP8 re-quantisers: floor(log2(amax)) - 7 (biased), 127 for an all-zero group
 // (quartet_bwd_sm120.cu:497-503 encode_e8m0_shiftm8; tests/quartet_test.py:279-285)
 __device__ __forceinline__ uint32_t e8m0_shift7(float amax) {
@@ -98,34 +93,6 @@ __device__ __forceinline__ void rotate32(float* v, float c_scale, const float* s
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = o[j];
   }
-}
-
-// abs-max MXFP4 quantisation of one rotated 32-group: returns the ue8m0 byte, leaves 4 words of packed e2m1 in out[].
-//   QT == false (quartet_bwd_sm120.cu:303-315):  s = floor_pow2(amax);          q = e2m1(v * (3 / s))
-//   QT == true  (quartet_bwd_sm120.cu:397-410):  s = floor_pow2(amax / alpha);  q = e2m1(v * (3 / (s * alpha)))
-// A group whose floored scale is zero (amax == 0 or denormal) yields scale byte 0 and all-zero codes, like the
-// reference's test oracle (tests/quartet_test.py:155-175); the reference kernel itself produces NaN -> 0x7 there.
-template <bool QT>
-__device__ __forceinline__ uint32_t quantise32_absmax(float* v, float alpha, uint32_t* out) {
-  float amax = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
-  float s = amax;
-  if constexpr (QT) s = __fdiv_rn(amax, alpha);
-  const uint32_t e = (__float_as_uint(s) >> 23) & 0xffu;
-  float f;
-  if constexpr (QT) {
-    const float sp = __uint_as_float(e << 23);
-    f = (e == 0u || e == 255u) ? 0.f : __fdiv_rn(3.0f, sp * alpha);
-  } else {
-    f = (e == 0u || e == 255u) ? 0.f : 3.0f * inv_pow2_of_e8m0(e);
-  }
-  const float2 f2 = make_float2(f, f);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) B200Q_UNPK(v, i, __fmul2_rn(B200Q_PK(v, i), f2));
-#pragma unroll
-  for (int w = 0; w < 4; ++w) out[w] = cvt8_e2m1(v + 8 * w);
-  return e;
 }
 
 // ------------------------------------------------------------------ tile loads (input orientation)
@@ -563,6 +530,10 @@ __global__ void __launch_bounds__(128) bwd_square_double_mxfp8_kernel(const Squa
 
 static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
+// backward_tc.cu: backward_t_bf16 with the transpose + rotation on the tensor cores (any runtime rotation at the streaming rate)
+bool backward_t_tc_eligible(const void* x, const void* rot, const void* q, const void* sf, int size_m, int size_n, int size_b);
+int launch_backward_t_tc(const void* x, const void* rot, void* q, void* sf, int size_m, int size_n, int size_b, cudaStream_t stream);
+
 // B200Q_BWD_PIPE=0/1 forces the one-shot / the persistent double-buffered form of the three transposing kernels (same bytes)
 // Measured (profiles/r02_s3_bwd_bench_pipe{0,1}.jsonl, graph replay over rotating sets): backward_qt 45.9 -> 43.2 us and
 // mxfp4_transpose_mxfp8 36.3 -> 33.5 us at 16384 x 4096 (41.7 -> 38.2 / 34.1 -> 29.7 at 4096 x 14336); backward_qt slower at
@@ -630,6 +601,16 @@ extern "C" int b200q_backward_t_bf16(const void* x_bf16, const void* rot_bf16, v
   p.N = size_n; p.M = size_m; p.n_valid = size_n;
   dim3 grid((unsigned)ceil_div(size_n, kBwdTile), (unsigned)ceil_div(size_m, kBwdTile), (unsigned)size_b);
   B200Q_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "problem too large for one launch");
+  {
+    // B200Q_BWD_T_TC=0/1 forces the CUDA-core / the tcgen05 kernel; library rule: from 8 M elements, and a non-Hadamard rotation from
+    // 1 M elements on (its CUDA-core path costs 1024 FMAs per group)
+    const int sw = env().bwd_t_tc;
+    const int64_t numel = (int64_t)size_m * size_n * size_b;
+    const bool trusted = (flags & B200Q_ROT_TRUSTED_HADAMARD) != 0;
+    if ((sw == 1 || (sw < 0 && numel >= (trusted ? ((int64_t)1 << 23) : ((int64_t)1 << 20)))) &&
+        backward_t_tc_eligible(x_bf16, rot_bf16, xh_e2m1, xh_e8m0, size_m, size_n, size_b))
+      return launch_backward_t_tc(x_bf16, rot_bf16, xh_e2m1, xh_e8m0, size_m, size_n, size_b, (cudaStream_t)stream);
+  }
   // (a generic rotation is bound by its 1024 FMAs per group, not by latency: one-shot form only)
   if (bwd_pipe_enabled(false, (int64_t)grid.x * grid.y * grid.z) && (flags & B200Q_ROT_TRUSTED_HADAMARD)) return launch_tq_pipe<false, true>(p, grid, (cudaStream_t)stream);
   if (flags & B200Q_ROT_TRUSTED_HADAMARD)

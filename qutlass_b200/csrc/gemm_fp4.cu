@@ -1159,6 +1159,15 @@ int make_x128_tmap(void* tm, const void* ptr, int64_t rows) {
   return encode((CUtensorMap*)tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "x[rows,128]");
 }
 
+// bf16 [B, N, M] (M contiguous) as the 3-D tensor {M, N, B}, box = {64 columns, 128 rows, 1}, 128B swizzle: a tile in INPUT
+// orientation for the transposing tensor-core quantiser (backward_tc.cu); rows >= N / columns >= M of a batch read as zero
+int make_xT_tmap(void* tm, const void* ptr, int64_t M, int64_t N, int64_t B) {
+  cuuint64_t dims[3] = {(cuuint64_t)M, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)M * 2, (cuuint64_t)M * (cuuint64_t)N * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  return encode((CUtensorMap*)tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "x[B,N,M]");
+}
+
 // bf16 rotation matrix [H, H] (row k, column n contiguous), box = [min(H, 64) columns, H rows], swizzle span = box row
 int make_rot_tmap(void* tm, const void* ptr, int had) {
   const int bw = had < 64 ? had : 64;
