@@ -11,8 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200q.so")
 # B200Q_LIB=prof selects the profiling build (python -m qutlass_b200.build --profiling): probe tools only
-if os.environ.get("B200Q_LIB") == "prof":
-    LIB_PATH = os.path.join(_HERE, "lib", "libb200q_prof.so")
+if os.environ.get("B200Q_LIB"):
+    LIB_PATH = os.path.join(_HERE, "lib", "libb200q_%s.so" % os.environ["B200Q_LIB"])
 
 # name -> (restype, argtypes); must match include/b200q.h exactly (tests/test_cabi.py checks the header)
 _vp, _i64, _i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int

@@ -37,33 +37,6 @@ struct BwdParams {
   int n_valid;              // TR8: input rows that exist (rows in [n_valid, N) read as zero); otherwise == N
 };
 
-// two e2m1 codes (one byte; element 2i in the low nibble) -> two floats
-__device__ __forceinline__ float2 e2m1x2_to_float2(uint32_t byte) {
-  uint32_t h2;
-  const uint16_t b16 = (uint16_t)byte;
-  asm("{\n"
-      ".reg .b8 lo8, hi8;\n"
-      "mov.b16 {lo8, hi8}, %1;\n"
-      "cvt.rn.f16x2.e2m1x2 %0, lo8;\n"
-      "}"
-      : "=r"(h2)
-      : "h"(b16));
-  return __half22float2(*reinterpret_cast<const __half2*>(&h2));
-}
-
-// two floats -> two e4m3 bytes (RNE, saturate to +-448); `lo` lands in the low byte
-__device__ __forceinline__ uint32_t cvt2_e4m3(float lo, float hi) {
-  uint16_t r;
-  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-
-// shared exponent of the MXFP8 re-quantisers: floor(log2(amax)) - 7 (biased), 127 for an all-zero group
-// (quartet_bwd_sm120.cu:497-503 encode_e8m0_shiftm8; tests/quartet_test.py:279-285)
-__device__ __forceinline__ uint32_t e8m0_shift7(float amax) {
-  return amax == 0.f ? 127u : (((__float_as_uint(amax) >> 23) - 7u) & 0xffu);
-}
-
 // ------------------------------------------------------------------ rotation of one 32-group held in registers
 template <bool TRUST>
 __device__ __forceinline__ void rotate32(float* v, float c_scale, const float* s_rot) {
@@ -166,10 +139,11 @@ __device__ __forceinline__ void bwd_tq_compute(const uint8_t* s_tile, const uint
     }
   }
   uint32_t o0[4], o1[4];
+  const float c3 = QT ? __fdiv_rn(3.0f, alpha) : 0.f;       // once per tile instead of two divisions per group (backward_quant.cuh)
   rotate32<TRUST>(v0, c_scale, s_rot);
-  const uint32_t e0 = quantise32_absmax<QT>(v0, alpha, o0);
+  const uint32_t e0 = quantise32_absmax<QT>(v0, alpha, o0, c3);
   rotate32<TRUST>(v1, c_scale, s_rot);
-  const uint32_t e1 = quantise32_absmax<QT>(v1, alpha, o1);
+  const uint32_t e1 = quantise32_absmax<QT>(v1, alpha, o1, c3);
 
   // stage: output row (2 mp + col) holds 4 groups x 16 B; the 16-byte slot is XOR-swizzled with (row >> 1) & 3
   const int slot = (g ^ (mp & 3)) * 16;
@@ -242,20 +216,6 @@ __global__ void __launch_bounds__(kBwdThreads) bwd_transpose_quantize_fp4_kernel
 // CTAs of one sweep still fill whole output lines together) and requests tile i + 1 with cp.async (zero-filled outside the
 // matrix) before it computes tile i: the one-shot form exposes the DRAM latency of every tile to its two resident CTAs
 // (load -> barrier -> ~900 instructions per thread -> barrier -> store).  Same compute / store code, same bytes.
-__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  const int bytes = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gmem_src, bool valid) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  const int bytes = valid ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // request one input tile (bf16: 128 rows x 256 B; FP4: 128 rows x 64 B of codes + 128 x 4 scale bytes) into shared memory
 template <bool FP4>
 __device__ __forceinline__ void bwd_request_tile(const BwdParams& p, int b, int n0, int m0, uint8_t* s_tile, uint8_t* s_sc) {
@@ -533,6 +493,10 @@ static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr
 // backward_tc.cu: backward_t_bf16 with the transpose + rotation on the tensor cores (any runtime rotation at the streaming rate)
 bool backward_t_tc_eligible(const void* x, const void* rot, const void* q, const void* sf, int size_m, int size_n, int size_b);
 int launch_backward_t_tc(const void* x, const void* rot, void* q, void* sf, int size_m, int size_n, int size_b, cudaStream_t stream);
+bool backward_qt_tc_eligible(const void* xq, const void* xs, const void* rot, const void* q, const void* sf, int size_m, int size_n,
+                             int size_b);
+int launch_backward_qt_tc(const void* xq, const void* xs, const void* rot, const float* alpha, void* q, void* sf, int size_m,
+                          int size_n, int size_b, cudaStream_t stream);
 
 // B200Q_BWD_PIPE=0/1 forces the one-shot / the persistent double-buffered form of the three transposing kernels (same bytes)
 // Measured (profiles/r02_s3_bwd_bench_pipe{0,1}.jsonl, graph replay over rotating sets): backward_qt 45.9 -> 43.2 us and
@@ -640,6 +604,17 @@ extern "C" int b200q_backward_qt_bf16(const void* x_e2m1, const void* x_e8m0, co
   dim3 grid((unsigned)ceil_div(size_n, kBwdTile), (unsigned)ceil_div(size_m, kBwdTile), (unsigned)size_b);
   B200Q_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "problem too large for one launch");
   // (a generic rotation is bound by its 1024 FMAs per group, not by latency: one-shot form only)
+  {
+    // B200Q_BWD_QT_TC=0/1 forces the CUDA-core / the tcgen05 kernel (backward_tc.cu: codes decoded to bf16 in shared memory,
+    // transpose + rotation on the tensor core)
+    const int sw = env().bwd_qt_tc;
+    const int64_t numel = (int64_t)size_m * size_n * size_b;
+    // Measured (profiles/r02_s3_bwd_bench_final_qt_{cudacore,tensorcore}.jsonl): 43.4 -> 40.6 us at 16384 x 4096, 38.5 -> 36.5 at
+    // 4096 x 14336, equal at 4096 x 4096 -- the decode warps (4 instructions per element pair on ONE warp per scheduler) bound it.
+    if ((sw == 1 || (sw < 0 && numel >= ((int64_t)1 << 24) + 1)) &&
+        backward_qt_tc_eligible(x_e2m1, x_e8m0, rot_bf16, xh_e2m1, xh_e8m0, size_m, size_n, size_b))
+      return launch_backward_qt_tc(x_e2m1, x_e8m0, rot_bf16, alpha_dev, xh_e2m1, xh_e8m0, size_m, size_n, size_b, (cudaStream_t)stream);
+  }
   if (bwd_pipe_enabled(true, (int64_t)grid.x * grid.y * grid.z) && (flags & B200Q_ROT_TRUSTED_HADAMARD)) return launch_tq_pipe<true, true>(p, grid, (cudaStream_t)stream);
   if (flags & B200Q_ROT_TRUSTED_HADAMARD)
     bwd_transpose_quantize_fp4_kernel<true, true><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(p);

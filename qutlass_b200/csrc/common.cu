@@ -46,6 +46,8 @@ static void load_env() {
   if (e.bwd_pipe != 0 && e.bwd_pipe != 1) e.bwd_pipe = -1;
   e.bwd_t_tc = env_int("B200Q_BWD_T_TC", -1);
   if (e.bwd_t_tc != 0 && e.bwd_t_tc != 1) e.bwd_t_tc = -1;
+  e.bwd_qt_tc = env_int("B200Q_BWD_QT_TC", -1);
+  if (e.bwd_qt_tc != 0 && e.bwd_qt_tc != 1) e.bwd_qt_tc = -1;
   e.decode_pace = env_int("B200Q_DECODE_PACE", -1);
   if (e.decode_pace < -1 || e.decode_pace > 100000) e.decode_pace = -1;
   g_env = e;

@@ -38,6 +38,7 @@ struct Env {
   int decode_pace;   // B200Q_DECODE_PACE: SM cycles between the weight-stage requests of a decode-kernel CTA (-1 unset: library rule, 0: all at once)
   int bwd_pipe;      // B200Q_BWD_PIPE: -1 unset (library default), 0 = one-shot CTAs, 1 = persistent double-buffered transposing kernels
   int bwd_t_tc;      // B200Q_BWD_T_TC: -1 unset (library rule), 0 = CUDA-core backward_t_bf16, 1 = tcgen05 kernel (backward_tc.cu)
+  int bwd_qt_tc;     // B200Q_BWD_QT_TC: -1 unset (library rule), 0 = CUDA-core backward_qt_bf16, 1 = tcgen05 kernel
   int fuse_decode;   // B200Q_FUSE_DECODE=1: b200q_linear_fp4 runs the decode step (M <= 32) as ONE launch (measured slower: opt-in)
 };
 const Env& env();

@@ -11,7 +11,7 @@
 //   warp 1     MMA issuer: 128 / H groups x H / 16 K-steps of tcgen05.mma.kind::f16 (M = 128, N = H, K = 16): group g
 //              multiplies columns [gH, gH + H) of the tile with R (TMA-loaded once as it lies in memory = an MN-major B operand) into TMEM
 //              columns [gH, gH + H) of one of 4 accumulator stages -- no zero padding, so a NaN / inf stays in its group
-//   warps 2-17 epilogue, 4 groups of 4 warps; group g owns accumulator stage g, i.e. every 4th tile of the CTA, so four
+//   warps 2-13 epilogue, 3 groups of 4 warps; group g owns accumulator stage g, i.e. every 3rd tile of the CTA, so three
 //              tiles are in flight in the CUDA cores.  thread = one 128-element row (TMEM lane): 4 chunks of 32 columns,
 //              two at a time (tcgen05.ld x32 twice -> two independent scale / e2m1 chains), accumulator released after
 //              the last load.  A thread's 64 bytes of codes go through a padded per-warp staging buffer so that every
@@ -34,13 +34,21 @@ using namespace ptx;
 int make_x128_tmap(void* tm, const void* ptr, int64_t rows);   // gemm_fp4.cu (cuTensorMapEncodeTiled plumbing)
 int make_rot_tmap(void* tm, const void* ptr, int had);
 
+// 12 epilogue warps (three groups of four): 14 warps per CTA leave every thread 104-128 registers (four warps per scheduler), so
+// the epilogue neither spills nor serialises; with 16 (18 warps, five on one scheduler) ptxas caps the kernel at 96 registers
+// and spills 32-64 bytes per thread.  Measured (profiles/r02_s3_quant_sweep_epi{16,12}.jsonl): quest H = 128 10.99 -> 10.56 us at
+// 4096 x 4096, 30.4 -> 29.8 at 16384 rows; abs_max unchanged.  -DB200Q_EPI16 builds the former form.
+#ifdef B200Q_EPI16
 constexpr int kTcEpiWarps = 16;
-constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;   // 576
+#else
+constexpr int kTcEpiWarps = 12;
+#endif
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;   // 448
 constexpr int kTcTileRows = 128;
 constexpr int kTcStageBytes = kTcTileRows * 256;    // 32 KB: two 16 KB swizzle atoms columns (K halves)
 constexpr int kTcStages = 4;
 constexpr int kTcRotBytes = 128 * 256;              // R^T for H = 128: two atoms of 128 rows x 128 B
-constexpr int kTcAcc = 4;                           // accumulator stages of 128 TMEM columns
+constexpr int kTcAcc = kTcEpiWarps / 4;             // accumulator stages of 128 TMEM columns
 constexpr int kTcOutRowBytes = 80;                  // 64 B of codes per row + 16 B pad: conflict-free v4 stores
 constexpr int kTcOutWarpBytes = 32 * kTcOutRowBytes;
 constexpr int kTcOutBytes = kTcEpiWarps * kTcOutWarpBytes;
