@@ -609,9 +609,9 @@ extern "C" int b200q_backward_qt_bf16(const void* x_e2m1, const void* x_e8m0, co
     // transpose + rotation on the tensor core)
     const int sw = env().bwd_qt_tc;
     const int64_t numel = (int64_t)size_m * size_n * size_b;
-    // Measured (profiles/r02_s3_bwd_bench_final_qt_{cudacore,tensorcore}.jsonl): 43.4 -> 40.6 us at 16384 x 4096, 38.5 -> 36.5 at
-    // 4096 x 14336, equal at 4096 x 4096 -- the decode warps (4 instructions per element pair on ONE warp per scheduler) bound it.
-    if ((sw == 1 || (sw < 0 && numel >= ((int64_t)1 << 24) + 1)) &&
+    // Measured (profiles/r02_s3_bwd_bench_final_qt_{cudacore,tensorcore}.jsonl): 43.4 -> 38.8 us at 16384 x 4096, 38.5 -> 35.0 at
+    // 4096 x 14336, 13.1 -> 12.4 at 4096 x 4096 -- the decode warps (4 instructions per element pair on ONE warp per scheduler) bound it.
+    if ((sw == 1 || (sw < 0 && numel >= ((int64_t)1 << 24))) &&
         backward_qt_tc_eligible(x_e2m1, x_e8m0, rot_bf16, xh_e2m1, xh_e8m0, size_m, size_n, size_b))
       return launch_backward_qt_tc(x_e2m1, x_e8m0, rot_bf16, alpha_dev, xh_e2m1, xh_e8m0, size_m, size_n, size_b, (cudaStream_t)stream);
   }

@@ -277,7 +277,8 @@ bwd_t_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 // butterfly sums are exact (the reference recipe's few-bit inputs), inside the 1e-4 bar otherwise.
 // 4 decode + 8 epilogue warps = 14 warps: 128 registers per thread, no spills.  Measured at 16384 x 4096 (CUDA-core kernel: 43.4 us):
 // 8 + 8 warps with a one-tile register prefetch 48.5 us, the same with the cp.async ring 49.9, 4 + 12 warps (96 registers, 128
-// bytes of spills) 46.9, this form 40.6 (profiles/r02_s3_bwd_bench_qt_tc1_v*.jsonl, r02_s3_bwd_bench_final_qt_tensorcore.jsonl).
+// bytes of spills) 46.9, this form 40.6, and 38.8 with the conflict-free decode mapping below (profiles/r02_s3_bwd_bench_qt_tc1_v*.jsonl,
+// r02_s3_bwd_bench_final_qt_tensorcore.jsonl).
 constexpr int kBfDeqWarps = 4, kBfEpiWarps = 8;
 constexpr int kBfThreads = 64 + 32 * (kBfDeqWarps + kBfEpiWarps);   // 448
 constexpr int kBfStages = 3;                                         // bf16 operand tiles (32 KB each)
@@ -399,19 +400,24 @@ bwd_qt_tc_kernel(const __grid_constant__ CUtensorMap tmap_r, const BwdFp4Params 
     // ===================== decode warps: e2m1 codes x 2^(e-127) -> bf16 operand tile =====================
     const int dw = warp - (2 + kBfEpiWarps);
     const int row_bytes = p.M >> 1, row_sf = p.M >> 5;
-    // unit = 16 bytes of codes = 32 m-columns of one n-row with ONE scale; a thread owns 4 of its warp's 128 units
+    // unit = 16 bytes of codes = 32 m-columns of one n-row with ONE scale; a thread owns 4 of its warp's 128 units.  Eight
+    // consecutive lanes take the SAME 32-column part of eight consecutive rows: their 16-byte stores into the swizzled operand
+    // tile then differ in `chunk ^ (row & 7)` and hit eight different bank groups (with 2 rows x 4 parts per quarter-warp the
+    // two atoms of a row collided: ncu counted 51 % of the shared wavefronts as conflicts); the raw ring is XOR-swizzled with
+    // (row >> 1) & 3 for the same reason.
     constexpr int kUnits = (kBtTile * 4) / (kBfDeqWarps * 32);
+    static_assert(kUnits == 4, "a decode warp covers 32 rows: 4 units (8 rows each) x 4 parts");
     int urow[kUnits], upart[kUnits];
 #pragma unroll
     for (int i = 0; i < kUnits; ++i) {
-      const int u = dw * (kUnits * 32) + i * 32 + lane;
-      urow[i] = u >> 2;
-      upart[i] = u & 3;
+      urow[i] = dw * 32 + i * 8 + (lane & 7);
+      upart[i] = lane >> 3;
     }
+    auto raw_unit = [&](int i) { return urow[i] * 64 + ((upart[i] ^ ((urow[i] >> 1) & 3)) * 16); };
     // Raw codes + scales reach shared memory by cp.async, kBfRaw - 1 tiles ahead (a register prefetch of ONE tile left 8 KB in
     // flight per SM: latency-bound at 0.7 TB/s, slower than the CUDA-core kernel).  Every thread copies exactly the two units it
-    // decodes itself; the 4-byte scale word of a row is copied by the lane that owns the row's first unit and read by its
-    // three neighbours (same warp: cp.async.wait_group + __syncwarp).
+    // decodes itself; the 4-byte scale word of a row is copied by the lane that owns the row's first unit and read by the
+    // three other lanes of that row (same warp: cp.async.wait_group + __syncwarp).
     uint8_t* raw0 = smem_gen + kBfStages * kBtStageBytes + kBtRotBytes + kBfOutBytes + 1024;
     auto issue = [&](int t, int rs) {
       int b, n0, m0;
@@ -422,7 +428,7 @@ bwd_qt_tc_kernel(const __grid_constant__ CUtensorMap tmap_r, const BwdFp4Params 
         const int n = n0 + urow[i];
         const bool ok = n < p.N;                                   // M % 128 == 0: no partial tiles along m
         const size_t r = (size_t)b * p.N + (ok ? n : 0);
-        cp_async16_zfill(raw + urow[i] * 64 + upart[i] * 16, p.xq + r * row_bytes + (m0 >> 1) + upart[i] * 16, ok);
+        cp_async16_zfill(raw + raw_unit(i), p.xq + r * row_bytes + (m0 >> 1) + upart[i] * 16, ok);
         if (upart[i] == 0) cp_async4_zfill(raw + kBtTile * 64 + urow[i] * 4, p.xs + r * row_sf + (m0 >> 5), ok);
       }
     };
@@ -443,7 +449,7 @@ bwd_qt_tc_kernel(const __grid_constant__ CUtensorMap tmap_r, const BwdFp4Params 
       uint8_t* tile = smem_gen + stage * kBtStageBytes;
 #pragma unroll
       for (int i = 0; i < kUnits; ++i) {
-        const uint4 cur = *reinterpret_cast<const uint4*>(raw + urow[i] * 64 + upart[i] * 16);
+        const uint4 cur = *reinterpret_cast<const uint4*>(raw + raw_unit(i));
         // (uint16) byte << 7 as bf16 == byte << 23 as fp32: 2^(e-127), e = 0 -> 0.0 (quartet_bwd_sm120.cu:360)
         const float sc = __uint_as_float((uint32_t)raw[kBtTile * 64 + urow[i] * 4 + upart[i]] << 23);
         const float2 sc2 = make_float2(sc, sc);
