@@ -93,6 +93,10 @@ def test_gemm_planner_choices_without_a_gpu(lib_path):
     for m in (384, 512, 768, 1024, 1536, 2048, 3072, 8192):
         assert plan(m, 14336, 4096)[0] == 2 and plan(m, 14336, 4096)[1] in (192, 256)
     assert plan(4096, 4096, 14336) == (2, 256)
+    # MXFP8 has cost constants of its own (profiles/r02_s3_f8_probe.jsonl): 224 tiles of 256 x 256 on 74 CTA pairs are 3.03 rounds at
+    # M = 1024 -> (2, 192); the big shapes stay on (2, 256)
+    assert plan(1024, 14336, 4096, 2) == (2, 192) and plan(1024, 14336, 4096, 3) == (2, 192)
+    assert plan(4096, 14336, 4096, 2) == (2, 256) and plan(16384, 14336, 4096, 2) == (2, 256)
     assert lib.b200q_gemm_fp4_plan(0, 1, 1, 0, ctypes.byref(ctypes.c_int()), ctypes.byref(ctypes.c_int())) != 0
 
 
