@@ -278,7 +278,8 @@ bwd_t_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 // 4 decode + 8 epilogue warps = 14 warps: 128 registers per thread, no spills.  Measured at 16384 x 4096 (CUDA-core kernel: 43.4 us):
 // 8 + 8 warps with a one-tile register prefetch 48.5 us, the same with the cp.async ring 49.9, 4 + 12 warps (96 registers, 128
 // bytes of spills) 46.9, this form 40.6, and 38.8 with the conflict-free decode mapping below (profiles/r02_s3_bwd_bench_qt_tc1_v*.jsonl,
-// r02_s3_bwd_bench_final_qt_tensorcore.jsonl).
+// r02_s3_bwd_bench_final_qt_tensorcore.jsonl).  SIX decode warps (16 warps, still 128 registers; work items dealt to quarter-warps,
+// every thread with a private copy of its row's scale word) were slower again: 41.8 us -- the decode is not the only bound.
 constexpr int kBfDeqWarps = 4, kBfEpiWarps = 8;
 constexpr int kBfThreads = 64 + 32 * (kBfDeqWarps + kBfEpiWarps);   // 448
 constexpr int kBfStages = 3;                                         // bf16 operand tiles (32 KB each)
