@@ -15,7 +15,7 @@
 //              {M, N, B} (128B swizzle; rows >= N and columns >= M of a batch read as zero), 4-stage ring
 //   warp 1     MMA issuer: 4 groups x 2 K-steps of tcgen05.mma.kind::f16 (M = 128, N = 32, K = 16), A MN-major (two 64-column
 //              atoms 16 KB apart = LBO, 8 n-rows = 1024 B = SBO), B = R as it lies in memory (MN-major, 64B swizzle); group g
-//              -> TMEM columns [32 g, 32 g + 32) of one of 4 accumulator stages
+//              -> TMEM columns [32 g, 32 g + 32) of one of 3 accumulator stages
 //   warps 2-13 epilogue, 3 groups of 4 warps, group a owns accumulator stage a: thread = output row m (TMEM lane) with its four
 //              32-groups; abs-max scale (quartet_bwd_sm120.cu:303-315: s = floor_pow2(amax), q = e2m1(v * 3 / s)), hardware cvt,
 //              per-warp staging so that every st.global.v4 of a warp covers whole 64-byte row segments, one 32-bit scale word
@@ -194,7 +194,7 @@ bwd_t_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (++acc == kBtAcc) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..17) =====================
+    // ===================== epilogue (warps 2..13) =====================
     const int ew = warp - 2;
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int grp = ew >> 2;                 // accumulator stage / tile residue this warp's group owns

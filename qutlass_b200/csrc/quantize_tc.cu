@@ -10,7 +10,7 @@
 //   warp 0     TMA producer: two 128-row x 64-element boxes (128B swizzle) per tile into a 5-stage ring
 //   warp 1     MMA issuer: 128 / H groups x H / 16 K-steps of tcgen05.mma.kind::f16 (M = 128, N = H, K = 16): group g
 //              multiplies columns [gH, gH + H) of the tile with R (TMA-loaded once as it lies in memory = an MN-major B operand) into TMEM
-//              columns [gH, gH + H) of one of 4 accumulator stages -- no zero padding, so a NaN / inf stays in its group
+//              columns [gH, gH + H) of one of 3 accumulator stages -- no zero padding, so a NaN / inf stays in its group
 //   warps 2-13 epilogue, 3 groups of 4 warps; group g owns accumulator stage g, i.e. every 3rd tile of the CTA, so three
 //              tiles are in flight in the CUDA cores.  thread = one 128-element row (TMEM lane): 4 chunks of 32 columns,
 //              two at a time (tcgen05.ld x32 twice -> two independent scale / e2m1 chains), accumulator released after
@@ -185,7 +185,7 @@ quantize_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         if (++acc == kTcAcc) { acc = 0; acc_phase ^= 1; }
       }
     } else {
-      // ===================== epilogue (warps 2..17) =====================
+      // ===================== epilogue (warps 2..13) =====================
       const int ew = warp - 2;
       const int q = warp & 3;                  // TMEM lane quarter this warp may access
       const int grp = ew >> 2;                 // accumulator stage / tile residue this warp's group owns
