@@ -32,13 +32,17 @@ def bwd_golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "backward_vectors.npz"))
 
 
-@pytest.fixture(autouse=True, params=["oneshot", "pipelined", "tensorcore"])
+@pytest.fixture(autouse=True, params=["oneshot", "pipelined", "tensorcore", "library-rule"])
 def bwd_form(request, b200q_env):
     """every test of this module runs against all forms of the transposing kernels: one CTA per tile (backward.cu), the
     persistent double-buffered form (B200Q_BWD_PIPE=1; same compute and store code: the same bytes) and, for
     backward_t_bf16 / backward_qt_bf16, the tcgen05 kernels (backward_tc.cu, B200Q_BWD_T_TC=1 / B200Q_BWD_QT_TC=1: the tile goes to the tensor core as an MN-major
     operand; same products, fp32 accumulation in the tensor core's order -- inside the same 1e-4 bars, and exactly equal to
     the forward tcgen05 quantiser on the transpose)."""
+    if request.param == "library-rule":       # no switch set: the size-dependent choice the library makes on its own
+        for name in ("B200Q_BWD_PIPE", "B200Q_BWD_T_TC", "B200Q_BWD_QT_TC"):
+            b200q_env(name, None)
+        return request.param
     b200q_env("B200Q_BWD_PIPE", "1" if request.param == "pipelined" else "0")
     b200q_env("B200Q_BWD_T_TC", "1" if request.param == "tensorcore" else "0")
     b200q_env("B200Q_BWD_QT_TC", "1" if request.param == "tensorcore" else "0")
